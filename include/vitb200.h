@@ -1,0 +1,135 @@
+/*
+ * vitb200.h — C ABI of libvitb200.so: hand-written sm_100a kernels for the ViT / DeiT / DETR-encoder
+ * forward+backward hot path of neeresh/vision-transformers.
+ *
+ * The reference has no FFI of its own: its boundary is the Python nn.Module contract, and
+ * every arithmetic step is a PyTorch library call. Each entry point below therefore names the reference
+ * call site (file:line under /root/reference, or torch/... for the PyTorch function the reference routes to)
+ * whose arithmetic it replaces. The Python mirror of the module contract lives in vitb200/{vit,deit,detr}.py.
+ *
+ * Conventions
+ *   - All pointers are caller-allocated DEVICE pointers (PyTorch's caching allocator owns every byte).
+ *     The library never frees or retains them past the call.
+ *   - Every entry point takes an explicit cudaStream_t (as void*), launches asynchronously and never
+ *     synchronises the device.
+ *   - Return value: 0 on success, a negative VB_ERR_* code otherwise; vb_last_error() gives the text.
+ *     Nothing throws across the boundary and nothing calls exit().
+ *   - There is no CPU fallback and no multi-backend dispatch: on a device that is not sm_100 the compute
+ *     entry points return VB_ERR_ARCH.
+ *   - Matrices are row-major; "ld*" are row pitches in ELEMENTS. bf16 = 16-bit brain float.
+ */
+#ifndef VITB200_H
+#define VITB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VB_API __attribute__((visibility("default")))
+#else
+#define VB_API
+#endif
+
+#define VB_OK 0
+#define VB_ERR_ARG (-1)     /* bad argument (alignment, shape, null pointer) */
+#define VB_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+#define VB_ERR_ARCH (-3)    /* device is not sm_100 */
+#define VB_ERR_UNSUPPORTED (-4)
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+VB_API int vb_version(void);                 /* ABI version, currently 1 */
+VB_API const char* vb_last_error(void);      /* thread-local text of the last failure */
+VB_API int vb_device_check(int device);      /* VB_OK iff `device` is an sm_100 part and the kernels can load */
+VB_API int vb_sm_count(int device);          /* number of SMs, or a negative error */
+
+/* ---- GEMM: C[M,N] = epilogue( A[M,K] * B[N,K]^T ), bf16 operands, fp32 accumulation in TMEM ----------
+ * Replaces every nn.Linear / F.linear on the path and its autograd dgrad/wgrad:
+ *   QKV in-proj   torch/nn/functional.py:5835-5847 (called from vanilla_vit.py:77)
+ *   out-proj      torch/nn/functional.py:6690 + residual vanilla_vit.py:78-79
+ *   mlp.0 + GELU  vanilla_vit.py:33-38,50        mlp.3 + residual vanilla_vit.py:41-42,83
+ *   head          vanilla_vit.py:212-213         conv_proj as GEMM vanilla_vit.py:129,196-198
+ *   DETR linear1/linear2/in-proj  transformer.py:195-199,218-224
+ * Operand majors: 0 = the contraction index K is contiguous (matrix stored [rows, K]);
+ *                 1 = the row index is contiguous (matrix stored [K, rows]).
+ *   forward  Y = X W^T           : a_major 0, b_major 0
+ *   dgrad    dX = dY W           : a_major 0 (dY [M,N]), b_major 1 (W stored [N_w, K_w], contraction over N_w)
+ *   wgrad    dW += dY^T X        : a_major 1 (dY stored [tokens, N_out]), b_major 1 (X stored [tokens, K_in])
+ */
+enum {
+    VB_EPI_STORE = 0,    /* C = acc + bias                                                */
+    VB_EPI_GELU = 1,     /* C = acc + bias (pre-activation, optional), C2 = gelu_erf(C)   */
+    VB_EPI_RESIDUAL = 2, /* C = acc + bias + AUX                                          */
+    VB_EPI_RELU = 3,     /* C = max(acc + bias, 0)                                        */
+    VB_EPI_DGELU = 4,    /* C = acc * gelu_erf'(AUX)        (AUX = saved pre-activation)  */
+    VB_EPI_DRELU = 5,    /* C = AUX > 0 ? acc : 0           (AUX = saved relu output)     */
+    VB_EPI_ACCUM = 6     /* C += acc  (fp32 C, TMA reduce-add; used by wgrad and split-K) */
+};
+enum { VB_BF16 = 0, VB_F32 = 1 };
+
+typedef struct VbGemmDesc {
+    int32_t M, N, K;          /* per-batch GEMM dims */
+    int32_t batches;          /* >= 1; batch b uses A + b*batch_stride_a etc. */
+    int32_t a_major, b_major; /* 0 = K contiguous, 1 = row index contiguous */
+    int32_t epilogue;         /* VB_EPI_* */
+    int32_t c_dtype;          /* VB_BF16 or VB_F32; AUX and C2 use the same dtype */
+    int32_t split_k;          /* >= 1; > 1 requires VB_EPI_ACCUM */
+    int32_t c_row_offset;     /* added to the row index when writing C/C2 and reading AUX (token offset) */
+    int32_t c_rows;           /* rows per batch of C/C2/AUX (>= M + c_row_offset); 0 means M */
+    int32_t aux_batch_broadcast; /* 1: AUX has a single batch that every batch reads (position embedding) */
+    const void* A; int64_t lda; int64_t batch_stride_a;   /* bf16 */
+    const void* B; int64_t ldb; int64_t batch_stride_b;   /* bf16; batch_stride_b = 0 shares B */
+    void* C; int64_t ldc; int64_t batch_stride_c;
+    void* C2; int64_t ldc2; int64_t batch_stride_c2;       /* VB_EPI_GELU second output or NULL */
+    const void* AUX; int64_t ldaux; int64_t batch_stride_aux;
+    const float* bias;        /* [N] fp32 or NULL */
+    int32_t max_ctas;         /* 0 = one persistent CTA per SM */
+    int32_t debug_direct_store; /* 1 = bypass the TMA-store epilogue (slow, for bring-up tests) */
+} VbGemmDesc;
+
+VB_API int vb_gemm_bf16(const VbGemmDesc* desc, void* stream);
+
+/* ---- LayerNorm over the last dimension of an fp32 [rows, dim] stream -------------------------------------
+ * Replaces nn.LayerNorm(eps=1e-6) vanilla_vit.py:66,70,100 (ATen native_layer_norm) and the eps=1e-5 norms of
+ * transformer.py:201-202.  dim must be a multiple of 128 and <= 1024.  Row pitches in elements.
+ * fwd: y = (x - mean) * rstd * gamma + beta, written as bf16 (y_bf16) and/or fp32 (y_f32); mean/rstd optional.
+ * bwd: dx = dres + LN'(dy); dgamma/dbeta/dx_colsum are ACCUMULATED (atomicAdd) and may be NULL;
+ *      dx_colsum[c] += sum_rows dx[row, c] (bias gradient of the linear layer feeding this residual stream). */
+VB_API int vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                            int64_t ldy_bf16, float* y_f32, int64_t ldy_f32, float* mean, float* rstd, int32_t rows,
+                            int32_t dim, float eps, void* stream);
+VB_API int vb_layernorm_bwd(const void* dy, int32_t dy_dtype, int64_t lddy, const float* x, int64_t ldx,
+                            const float* mean, const float* rstd, const float* gamma, const float* dres, int64_t lddres,
+                            float* dx, int64_t lddx, void* dx_bf16, int64_t lddx_bf16, float* dgamma, float* dbeta,
+                            float* dx_colsum, int32_t rows, int32_t dim, void* stream);
+
+/* ---- Fused multi-head attention, head_dim 64 ---------------------------------------------------------------
+ * Replaces F.scaled_dot_product_attention reached from nn.MultiheadAttention at vanilla_vit.py:77
+ * (torch/nn/functional.py:6676-6688) and the explicit softmax path of transformer.py:219
+ * (torch/nn/functional.py:6630-6666) with its boolean key_padding_mask (1 = ignore key).
+ * q/k/v/o (and dq/dk/dv/dout) are bf16 matrices whose row is a token and whose columns [h*64, h*64+64) hold
+ * head h; the row of token s of batch element b is b*batch_stride + s*tok_stride (ViT batch-first: S, 1;
+ * DETR sequence-first: 1, N).  lse is [B,H,S] fp32 in the log2 domain; delta is [B,H,S] fp32 scratch.
+ * The softmax scale is 1/sqrt(64), as in the reference. */
+typedef struct VbAttnDesc {
+    int32_t B, H, S, head_dim;
+    int64_t tok_stride, batch_stride;
+    const void* q; const void* k; const void* v;
+    int64_t ldq, ldk, ldv;
+    void* o; int64_t ldo;
+    float* lse;
+    const uint8_t* key_padding_mask; /* [B,S] or NULL */
+    const void* dout; int64_t lddo;  /* backward only from here */
+    float* delta;
+    void* dq; void* dk; void* dv;
+    int64_t lddq, lddk, lddv;
+} VbAttnDesc;
+VB_API int vb_attention_fwd(const VbAttnDesc* desc, void* stream);
+VB_API int vb_attention_bwd(const VbAttnDesc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITB200_H */

@@ -1,0 +1,491 @@
+// Fused flash-style multi-head attention, head_dim = 64: softmax(Q K^T / 8) V with online softmax in registers
+// and warp-shuffle row reductions; forward saves only the per-row log-sum-exp, backward recomputes P.
+//
+// Replaces F.scaled_dot_product_attention as reached from nn.MultiheadAttention at vanilla_vit.py:77
+// (torch/nn/functional.py:6676-6688) and the explicit bmm/softmax/bmm path of the DETR encoder layer
+// (transformer.py:219 -> torch/nn/functional.py:6630-6666), including its boolean key-padding mask.
+//
+// Q, K, V are read in place from the projection output (row = token, head h at column h*64), so no
+// head-major copy is ever made; O is written token-major, ready to be the A operand of the out-proj GEMM.
+// Token row index = b * batch_stride + s * tok_stride (batch-first ViT: (S,1); sequence-first DETR: (1,N)).
+#include "common.h"
+#include <cuda_bf16.h>
+
+namespace vb {
+
+constexpr int HD = 64;       // head dim
+constexpr int TILE = 64;     // rows per smem tile (queries or keys)
+constexpr int TILE_BYTES = TILE * HD * 2;
+
+struct AttnParams {
+    const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v;
+    long long ldq, ldk, ldv;
+    __nv_bfloat16* o; long long ldo;
+    float* lse;                // [B, H, S], log2 domain: lse2 = max + log2(sum)
+    const uint8_t* kpm;        // [B, S], 1 = key is padding; may be null
+    int B, H, S;
+    long long tok_stride, batch_stride;
+    float scale, scale_log2;   // 1/sqrt(hd), scale * log2(e)
+    // backward
+    const __nv_bfloat16* dout; long long lddo;
+    float* delta;              // [B, H, S]
+    __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv;
+    long long lddq, lddk, lddv;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// smem tile: 64 rows x 128 B, 16-byte chunk index XOR-swizzled with (row & 7)
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+// Loads rows [r0, r0+64) x 64 cols of head h (rows >= S zero-filled) with 128 threads.
+__device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g, long long ld, long long tok_stride, long long row_base,
+                                          int r0, int S, int h) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + i * 128;
+        const int row = c >> 3, ch = c & 7;
+        const int s = r0 + row;
+        const bool valid = s < S;
+        const __nv_bfloat16* src = g + (row_base + (long long)(valid ? s : 0) * tok_stride) * ld + h * HD + ch * 8;
+        cp_async16(sbase + tile_off(row, ch), src, valid);
+    }
+}
+
+// A fragments (16 rows x 64 k) of rows [row0, row0+16) of a tile: 4 k-tiles x 4 regs.
+__device__ __forceinline__ void load_a_frags(uint32_t sbase, int row0, uint32_t (&f)[4][4]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) ldsm_x4(sbase + tile_off(row0 + (lane & 15), kt * 2 + (lane >> 4)), f[kt]);
+}
+
+// acc[8][4] (16 x 64) += A(16 x 64 k, register frags) * T^T where T is a smem tile [n=64][k=64] (non-transposed B operand).
+__device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t sT) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ldsm_x4(sT + tile_off(np * 16 + (lane & 7) + ((lane >> 4) << 3), kt * 2 + ((lane >> 3) & 1)), b);
+            mma_bf16(acc[2 * np], a[kt], b[0], b[1]);
+            mma_bf16(acc[2 * np + 1], a[kt], b[2], b[3]);
+        }
+    }
+}
+
+// acc[8][4] (16 x 64 n) += P(16 x 64 k, given as accumulator-layout floats p[8][4]) * T where T is a smem tile [k=64][n=64].
+__device__ __forceinline__ void mma_p_tile(float (&acc)[8][4], const float (&p)[8][4], uint32_t sT) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+        uint32_t a[4];
+        a[0] = pack2(p[2 * kq][0], p[2 * kq][1]);
+        a[1] = pack2(p[2 * kq][2], p[2 * kq][3]);
+        a[2] = pack2(p[2 * kq + 1][0], p[2 * kq + 1][1]);
+        a[3] = pack2(p[2 * kq + 1][2], p[2 * kq + 1][3]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ldsm_x4_t(sT + tile_off(kq * 16 + (lane & 15), np * 2 + (lane >> 4)), b);
+            mma_bf16(acc[2 * np], a, b[0], b[1]);
+            mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+// Writes a warp's 16 x 64 accumulator tile (scaled) as bf16 to global rows via a swizzled smem staging tile.
+__device__ __forceinline__ void store_rows(uint8_t* stage, int row0, const float (&acc)[8][4], float mul, __nv_bfloat16* g, long long ld,
+                                           long long tok_stride, long long row_base, int s0, int S, int h) {
+    const int lane = threadIdx.x & 31;
+    const int r = lane >> 2, cq = (lane & 3) * 2;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int col = nt * 8 + cq;
+        *reinterpret_cast<uint32_t*>(stage + tile_off(row0 + r, col >> 3) + (col & 7) * 2) = pack2(acc[nt][0] * mul, acc[nt][1] * mul);
+        *reinterpret_cast<uint32_t*>(stage + tile_off(row0 + r + 8, col >> 3) + (col & 7) * 2) = pack2(acc[nt][2] * mul, acc[nt][3] * mul);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int id = lane + i * 32;
+        const int row = id >> 3, ch = id & 7;
+        const int s = s0 + row0 + row;
+        if (s < S) {
+            const uint4 w = *reinterpret_cast<const uint4*>(stage + tile_off(row0 + row, ch));
+            *reinterpret_cast<uint4*>(g + (row_base + (long long)s * tok_stride) * ld + h * HD + ch * 8) = w;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Forward: grid (ceil(S/64), H, B), 128 threads; warp w owns query rows [q0 + 16w, q0 + 16w + 16).
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + TILE_BYTES;          // 2 buffers
+    uint8_t* sV = smem + 3 * TILE_BYTES;      // 2 buffers
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
+    const long long row_base = (long long)b * p.batch_stride;
+    const int nkv = (p.S + TILE - 1) / TILE;
+
+    load_tile(smem_addr(sQ), p.q, p.ldq, p.tok_stride, row_base, q0, p.S, h);
+    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, 0, p.S, h);
+    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, 0, p.S, h);
+    cp_async_commit();
+
+    uint32_t qf[4][4];
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < nkv) {
+            load_tile(smem_addr(sK + (buf ^ 1) * TILE_BYTES), p.k, p.ldk, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
+            load_tile(smem_addr(sV + (buf ^ 1) * TILE_BYTES), p.v, p.ldv, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (j == 0) load_a_frags(smem_addr(sQ), warp * 16, qf);
+
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        mma_a_tileT(s, qf, smem_addr(sK + buf * TILE_BYTES));
+
+        // scale to log2 domain, mask invalid / padded keys
+        const int kbase = j * TILE + (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = kbase + nt * 8 + e;
+                bool dead = key >= p.S;
+                if (!dead && p.kpm) dead = p.kpm[(long long)b * p.S + key] != 0;
+                s[nt][e] = dead ? -INFINITY : s[nt][e] * p.scale_log2;
+                s[nt][e + 2] = dead ? -INFINITY : s[nt][e + 2] * p.scale_log2;
+            }
+        }
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float ms0 = (mx0 == -INFINITY) ? 0.f : mx0, ms1 = (mx1 == -INFINITY) ? 0.f : mx1;
+        const float a0 = exp2f(m0 - ms0), a1 = exp2f(m1 - ms1);
+        m0 = mx0; m1 = mx1;
+        l0 *= a0; l1 *= a1;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] - ms0); s[nt][1] = exp2f(s[nt][1] - ms0);
+            s[nt][2] = exp2f(s[nt][2] - ms1); s[nt][3] = exp2f(s[nt][3] - ms1);
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
+            o[nt][0] *= a0; o[nt][1] *= a0; o[nt][2] *= a1; o[nt][3] *= a1;
+        }
+        mma_p_tile(o, s, smem_addr(sV + buf * TILE_BYTES));
+        __syncthreads();  // everyone done with this K/V buffer before it is refilled
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= inv0; o[nt][1] *= inv0; o[nt][2] *= inv1; o[nt][3] *= inv1; }
+    if (p.lse && (lane & 3) == 0) {
+        const int r0 = q0 + warp * 16 + (lane >> 2);
+        float* lse = p.lse + ((long long)b * p.H + h) * p.S;
+        if (r0 < p.S) lse[r0] = m0 + log2f(l0);
+        if (r0 + 8 < p.S) lse[r0 + 8] = m1 + log2f(l1);
+    }
+    store_rows(sQ, warp * 16, o, 1.0f, p.o, p.ldo, p.tok_stride, row_base, q0, p.S, h);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]; one warp per (token, head).
+// ----------------------------------------------------------------------------------------------------------
+__global__ void attn_delta_kernel(const AttnParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long total = (long long)p.B * p.S * p.H;
+    if (wid >= total) return;
+    const int h = wid % p.H;
+    const long long bs = wid / p.H;
+    const int s = bs % p.S;
+    const int b = bs / p.S;
+    const long long row = (long long)b * p.batch_stride + (long long)s * p.tok_stride;
+    const uint32_t ov = *reinterpret_cast<const uint32_t*>(p.o + row * p.ldo + h * HD + lane * 2);
+    const uint32_t dv = *reinterpret_cast<const uint32_t*>(p.dout + row * p.lddo + h * HD + lane * 2);
+    float acc = __uint_as_float(ov << 16) * __uint_as_float(dv << 16) + __uint_as_float(ov & 0xFFFF0000u) * __uint_as_float(dv & 0xFFFF0000u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) p.delta[((long long)b * p.H + h) * p.S + s] = acc;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Backward dK, dV: grid (ceil(S/64), H, B); warp w owns keys [k0 + 16w, +16); loops over query blocks.
+//   S^T = K Q^T, P^T = exp2(S^T*c - lse[q]), dV += P^T dO, dP^T = V dO^T, dS^T = P^T o (dP^T - delta[q]), dK += dS^T Q
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + TILE_BYTES;
+    uint8_t* sQ = smem + 2 * TILE_BYTES;    // 2 buffers
+    uint8_t* sdO = smem + 4 * TILE_BYTES;   // 2 buffers
+    float* sLse = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);  // [2][64]
+    float* sDelta = sLse + 2 * TILE;                                // [2][64]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
+    const long long row_base = (long long)b * p.batch_stride;
+    const int nq = (p.S + TILE - 1) / TILE;
+    const float* lse = p.lse + ((long long)b * p.H + h) * p.S;
+    const float* delta = p.delta + ((long long)b * p.H + h) * p.S;
+
+    auto load_q_block = [&](int j, int buf) {
+        load_tile(smem_addr(sQ + buf * TILE_BYTES), p.q, p.ldq, p.tok_stride, row_base, j * TILE, p.S, h);
+        load_tile(smem_addr(sdO + buf * TILE_BYTES), p.dout, p.lddo, p.tok_stride, row_base, j * TILE, p.S, h);
+        if (threadIdx.x < TILE) {
+            const int s = j * TILE + threadIdx.x;
+            sLse[buf * TILE + threadIdx.x] = s < p.S ? lse[s] : 0.f;
+            sDelta[buf * TILE + threadIdx.x] = s < p.S ? delta[s] : 0.f;
+        }
+    };
+    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, k0, p.S, h);
+    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, k0, p.S, h);
+    load_q_block(0, 0);
+    cp_async_commit();
+
+    uint32_t kf[4][4], vf[4][4];
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+    // key validity of this thread's two rows
+    const int key0 = k0 + warp * 16 + (lane >> 2), key1 = key0 + 8;
+    bool dead0 = key0 >= p.S, dead1 = key1 >= p.S;
+    if (p.kpm) {
+        if (!dead0) dead0 = p.kpm[(long long)b * p.S + key0] != 0;
+        if (!dead1) dead1 = p.kpm[(long long)b * p.S + key1] != 0;
+    }
+
+    for (int j = 0; j < nq; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < nq) {
+            load_q_block(j + 1, buf ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (j == 0) {
+            load_a_frags(smem_addr(sK), warp * 16, kf);
+            load_a_frags(smem_addr(sV), warp * 16, vf);
+        }
+        const uint32_t sQb = smem_addr(sQ + buf * TILE_BYTES), sdOb = smem_addr(sdO + buf * TILE_BYTES);
+        float st[8][4], dpt[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f; dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f; }
+        mma_a_tileT(st, kf, sQb);     // S^T[key, q]
+        mma_a_tileT(dpt, vf, sdOb);   // dP^T[key, q]
+        const int qb = (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int qi = nt * 8 + qb + e;
+                const bool qdead = j * TILE + qi >= p.S;
+                const float l = sLse[buf * TILE + qi], dl = sDelta[buf * TILE + qi];
+                const float p0 = (qdead || dead0) ? 0.f : exp2f(st[nt][e] * p.scale_log2 - l);
+                const float p1 = (qdead || dead1) ? 0.f : exp2f(st[nt][e + 2] * p.scale_log2 - l);
+                st[nt][e] = p0; st[nt][e + 2] = p1;
+                dpt[nt][e] = p0 * (dpt[nt][e] - dl);
+                dpt[nt][e + 2] = p1 * (dpt[nt][e + 2] - dl);
+            }
+        }
+        mma_p_tile(dv, st, sdOb);   // dV += P^T dO
+        mma_p_tile(dk, dpt, sQb);   // dK += dS^T Q
+        __syncthreads();
+    }
+    store_rows(sK, warp * 16, dk, p.scale, p.dk, p.lddk, p.tok_stride, row_base, k0, p.S, h);
+    store_rows(sV, warp * 16, dv, 1.0f, p.dv, p.lddv, p.tok_stride, row_base, k0, p.S, h);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Backward dQ: grid (ceil(S/64), H, B); warp w owns queries [q0 + 16w, +16); loops over key blocks.
+//   S = Q K^T, P = exp2(S*c - lse[row]), dP = dO V^T, dS = P o (dP - delta[row]), dQ += dS K
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sdO = smem + TILE_BYTES;
+    uint8_t* sK = smem + 2 * TILE_BYTES;   // 2 buffers
+    uint8_t* sV = smem + 4 * TILE_BYTES;   // 2 buffers
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
+    const long long row_base = (long long)b * p.batch_stride;
+    const int nkv = (p.S + TILE - 1) / TILE;
+
+    load_tile(smem_addr(sQ), p.q, p.ldq, p.tok_stride, row_base, q0, p.S, h);
+    load_tile(smem_addr(sdO), p.dout, p.lddo, p.tok_stride, row_base, q0, p.S, h);
+    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, 0, p.S, h);
+    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, 0, p.S, h);
+    cp_async_commit();
+
+    const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+    const float* lse = p.lse + ((long long)b * p.H + h) * p.S;
+    const float* delta = p.delta + ((long long)b * p.H + h) * p.S;
+    const float lse0 = r0 < p.S ? lse[r0] : 0.f, lse1 = r1 < p.S ? lse[r1] : 0.f;
+    const float dl0 = r0 < p.S ? delta[r0] : 0.f, dl1 = r1 < p.S ? delta[r1] : 0.f;
+
+    uint32_t qf[4][4], dof[4][4];
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < nkv) {
+            load_tile(smem_addr(sK + (buf ^ 1) * TILE_BYTES), p.k, p.ldk, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
+            load_tile(smem_addr(sV + (buf ^ 1) * TILE_BYTES), p.v, p.ldv, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (j == 0) {
+            load_a_frags(smem_addr(sQ), warp * 16, qf);
+            load_a_frags(smem_addr(sdO), warp * 16, dof);
+        }
+        const uint32_t sKb = smem_addr(sK + buf * TILE_BYTES), sVb = smem_addr(sV + buf * TILE_BYTES);
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+        mma_a_tileT(s, qf, sKb);     // S[q, key]
+        mma_a_tileT(dp, dof, sVb);   // dP[q, key]
+        const int kbase = j * TILE + (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = kbase + nt * 8 + e;
+                bool dead = key >= p.S;
+                if (!dead && p.kpm) dead = p.kpm[(long long)b * p.S + key] != 0;
+                const float p0 = dead ? 0.f : exp2f(s[nt][e] * p.scale_log2 - lse0);
+                const float p1 = dead ? 0.f : exp2f(s[nt][e + 2] * p.scale_log2 - lse1);
+                dp[nt][e] = p0 * (dp[nt][e] - dl0);
+                dp[nt][e + 2] = p1 * (dp[nt][e + 2] - dl1);
+            }
+        }
+        mma_p_tile(dq, dp, sKb);     // dQ += dS K
+        __syncthreads();
+    }
+    store_rows(sQ, warp * 16, dq, p.scale, p.dq, p.lddq, p.tok_stride, row_base, q0, p.S, h);
+}
+
+static int check_common(const VbAttnDesc* d) {
+    VB_REQUIRE(d != nullptr, "attention: null descriptor");
+    VB_REQUIRE(d->head_dim == 64, "attention: head_dim %d unsupported (every reference config has 64)", d->head_dim);
+    VB_REQUIRE(d->B > 0 && d->H > 0 && d->S > 0, "attention: bad dims B=%d H=%d S=%d", d->B, d->H, d->S);
+    VB_REQUIRE(d->q && d->k && d->v && d->o, "attention: null tensor");
+    VB_REQUIRE(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldv % 8 == 0 && d->ldo % 8 == 0, "attention: row pitches must be multiples of 8");
+    VB_REQUIRE(((uintptr_t)d->q & 15) == 0 && ((uintptr_t)d->k & 15) == 0 && ((uintptr_t)d->v & 15) == 0 && ((uintptr_t)d->o & 15) == 0,
+               "attention: tensors must be 16-byte aligned");
+    return VB_OK;
+}
+
+static AttnParams to_params(const VbAttnDesc* d) {
+    AttnParams p{};
+    p.q = (const __nv_bfloat16*)d->q; p.k = (const __nv_bfloat16*)d->k; p.v = (const __nv_bfloat16*)d->v;
+    p.ldq = d->ldq; p.ldk = d->ldk; p.ldv = d->ldv;
+    p.o = (__nv_bfloat16*)d->o; p.ldo = d->ldo;
+    p.lse = d->lse; p.kpm = d->key_padding_mask;
+    p.B = d->B; p.H = d->H; p.S = d->S;
+    p.tok_stride = d->tok_stride; p.batch_stride = d->batch_stride;
+    p.scale = 0.125f;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    p.dout = (const __nv_bfloat16*)d->dout; p.lddo = d->lddo; p.delta = d->delta;
+    p.dq = (__nv_bfloat16*)d->dq; p.dk = (__nv_bfloat16*)d->dk; p.dv = (__nv_bfloat16*)d->dv;
+    p.lddq = d->lddq; p.lddk = d->lddk; p.lddv = d->lddv;
+    return p;
+}
+
+}  // namespace vb
+
+extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    if (int rc = check_common(d)) return rc;
+    const AttnParams p = to_params(d);
+    const int smem = 5 * TILE_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
+    attn_fwd_kernel<<<grid, 128, smem, as_stream(stream)>>>(p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    if (int rc = check_common(d)) return rc;
+    VB_REQUIRE(d->dout && d->dq && d->dk && d->dv && d->lse && d->delta, "attention_bwd: null tensor");
+    VB_REQUIRE(d->lddo % 8 == 0 && d->lddq % 8 == 0 && d->lddk % 8 == 0 && d->lddv % 8 == 0, "attention_bwd: row pitches must be multiples of 8");
+    const AttnParams p = to_params(d);
+    cudaStream_t st = as_stream(stream);
+    const int smem = 6 * TILE_BYTES + 4 * TILE * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_BYTES));
+        configured = true;
+    }
+    const long long nwarps = (long long)d->B * d->S * d->H;
+    attn_delta_kernel<<<(unsigned)((nwarps + 7) / 8), 256, 0, st>>>(p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
+    attn_bwd_dkdv_kernel<<<grid, 128, smem, st>>>(p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    attn_bwd_dq_kernel<<<grid, 128, 6 * TILE_BYTES, st>>>(p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}

@@ -1,0 +1,578 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )     bf16 operands, fp32 accumulation in TMEM.
+//
+// One CTA per SM loops over 128x256 output tiles (or (tile, k-split) units).  Roles:
+//   warp 0      TMA producer: fills a 3/4-stage ring of {A 128x64, B 256x64} bf16 tiles (128B swizzle)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma 128x256x16 into one of two TMEM accumulators
+//   warp 2      TMEM allocator (512 columns = 2 x 256 fp32 accumulator columns)
+//   warps 4-11  epilogue: tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store / reduce-add,
+//               overlapping the MMA of the next tile (double-buffered accumulator)
+// Operand majors are handled in the shared-memory descriptors (K-major or MN-major canonical SW128
+// layouts), never by transposing in HBM: forward uses (K,K), dgrad (K,MN), wgrad (MN,MN).
+//
+// Replaces the cuBLASLt calls behind nn.Linear / F.linear on the reference path
+// (vanilla_vit.py:33-42,77-79,212-213; torch/nn/functional.py:5835-5847,6690) and their autograd formulas.
+#include <cuda.h>
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+constexpr uint32_t BM = 128, BN = 256, BK = 64, UK = 16;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr uint32_t EPI_BUF_BYTES = 32 * 128;     // 32 rows x 128 B
+constexpr uint32_t kEpiWarps = 8;
+constexpr uint32_t kFirstEpiWarp = 4;
+constexpr uint32_t kThreads = (kFirstEpiWarp + kEpiWarps) * 32;  // 384
+constexpr uint32_t kTmemCols = 512;
+
+struct GemmArgs {
+    int M, N, K, batches;
+    int n_blocks, k_blocks, tiles_per_batch, num_tiles;
+    int split_k, kb_per_split, num_units;
+    int c_row_offset, aux_bcast, b_batched;
+    int direct;
+    const float* bias;
+    void* C;
+    void* C2;
+    const void* AUX;
+    long long ldc, ldc2, ldaux, bsc, bsc2, bsaux;
+};
+
+template <int EPI>
+struct EpiTraits {
+    static constexpr bool kHasAux = (EPI == VB_EPI_RESIDUAL || EPI == VB_EPI_DGELU || EPI == VB_EPI_DRELU);
+    static constexpr bool kTwoOut = (EPI == VB_EPI_GELU);
+    static constexpr uint32_t kBufsPerWarp = (kHasAux || kTwoOut) ? 2 : 1;
+    static constexpr uint32_t kStages = (kBufsPerWarp == 2) ? 3 : 4;
+    static constexpr uint32_t kSmemBytes =
+        kStages * (A_STAGE_BYTES + B_STAGE_BYTES) + kEpiWarps * kBufsPerWarp * EPI_BUF_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+struct UnitCoord {
+    int m_blk, n_blk, batch, kb0, kb1;
+};
+__device__ __forceinline__ UnitCoord decode_unit(const GemmArgs& a, int u) {
+    UnitCoord c;
+    const int s = u / a.num_tiles;
+    const int t = u - s * a.num_tiles;
+    c.batch = t / a.tiles_per_batch;
+    const int r = t - c.batch * a.tiles_per_batch;
+    c.m_blk = r / a.n_blocks;
+    c.n_blk = r - c.m_blk * a.n_blocks;
+    c.kb0 = s * a.kb_per_split;
+    c.kb1 = min(c.kb0 + a.kb_per_split, a.k_blocks);
+    return c;
+}
+
+template <int AMAJ, int BMAJ, int EPI, int CDT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+            const __grid_constant__ CUtensorMap tmAux, const GemmArgs args) {
+#if defined(__CUDA_ARCH_FEAT_SM100_ALL)
+    using T = EpiTraits<EPI>;
+    constexpr uint32_t kStages = T::kStages;
+    constexpr uint32_t CPC = (CDT == VB_BF16) ? 64 : 32;  // columns per 128-byte store chunk
+    constexpr uint32_t kChunks = 128 / CPC;               // chunks per epilogue warp per tile
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
+    uint8_t* smem_epi = smem_b + kStages * B_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * T::kBufsPerWarp * EPI_BUF_BYTES);
+    uint64_t* full_bar = bars;                      // [kStages]
+    uint64_t* empty_bar = bars + kStages;           // [kStages]
+    uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+    uint64_t* aux_bar = tmem_empty_bar + 2;         // [kEpiWarps]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+
+    const uint32_t warp_idx = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        if (T::kTwoOut) tma_prefetch_desc(&tmC2);
+        if (T::kHasAux) tma_prefetch_desc(&tmAux);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (uint32_t i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kEpiWarps);
+        }
+        for (uint32_t i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int u = blockIdx.x; u < args.num_units; u += gridDim.x) {
+                const UnitCoord c = decode_unit(args, u);
+                const int bb = args.b_batched ? c.batch : 0;
+                for (int kb = c.kb0; kb < c.kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+                    if (AMAJ == 0) {
+                        tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, c.m_blk * BM, c.batch);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < int(BM / 64); ++j)
+                            tma_load_3d(sa + j * (BK * 128), &tmA, &full_bar[stage], c.m_blk * BM + j * 64, kb * BK, c.batch);
+                    }
+                    if (BMAJ == 0) {
+                        tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, c.n_blk * BN, bb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < int(BN / 64); ++j)
+                            tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[stage], c.n_blk * BN + j * 64, kb * BK, bb);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMAJ, BMAJ);
+            // K-major SW128: 8-row groups 1024 B apart (SBO); MN-major SW128: 64-wide MN atoms BK*128 B apart
+            // (LBO) and 8-deep K groups 1024 B apart (SBO).
+            constexpr uint64_t a_base = (AMAJ == 0) ? umma_smem_desc_base(0, 1024) : umma_smem_desc_base(BK * 128, 1024);
+            constexpr uint64_t b_base = (BMAJ == 0) ? umma_smem_desc_base(0, 1024) : umma_smem_desc_base(BK * 128, 1024);
+            constexpr uint32_t a_kstep = (AMAJ == 0) ? UK * 2 : UK * 128;
+            constexpr uint32_t b_kstep = (BMAJ == 0) ? UK * 2 : UK * 128;
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int u = blockIdx.x; u < args.num_units; u += gridDim.x, ++it) {
+                const UnitCoord c = decode_unit(args, u);
+                const uint32_t as = it & 1, ap = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[as], ap ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = c.kb0; kb < c.kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < BK / UK; ++k) {
+                        const uint64_t ad = umma_smem_desc(a_base, sa + k * a_kstep);
+                        const uint64_t bd = umma_smem_desc(b_base, sb + k * b_kstep);
+                        umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > c.kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[as]);     // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp_idx >= kFirstEpiWarp) {
+        // ===================================== epilogue ==========================================
+        const uint32_t ew = warp_idx - kFirstEpiWarp;
+        const uint32_t quad = warp_idx & 3;   // TMEM lane quadrant this warp may access
+        const uint32_t half = ew >> 2;        // which 128-column half of the tile
+        uint8_t* buf0 = smem_epi + ew * T::kBufsPerWarp * EPI_BUF_BYTES;
+        uint8_t* buf1 = buf0 + EPI_BUF_BYTES;  // aux-in or second output (only if kBufsPerWarp == 2)
+        const uint32_t swz = (lane & 7) << 4;
+        const uint32_t row_off = lane * 128;
+        uint32_t aux_phase = 0;
+
+        // Finds the first valid (unit, chunk) at or after (u, ch) for this warp; returns false when done.
+        auto next_valid = [&](int& u, int& ch) -> bool {
+            while (u < args.num_units) {
+                if (ch < int(kChunks)) {
+                    const UnitCoord c = decode_unit(args, u);
+                    const int col0 = c.n_blk * BN + half * 128 + ch * CPC;
+                    if (col0 < args.N) return true;
+                }
+                u += gridDim.x;
+                ch = 0;
+            }
+            return false;
+        };
+        auto issue_aux = [&](int u, int ch) {
+            const UnitCoord c = decode_unit(args, u);
+            const int col0 = c.n_blk * BN + half * 128 + ch * CPC;
+            const int row0 = args.c_row_offset + c.m_blk * BM + quad * 32;
+            mbar_arrive_expect_tx(&aux_bar[ew], EPI_BUF_BYTES);
+            tma_load_3d(buf1, &tmAux, &aux_bar[ew], col0, row0, args.aux_bcast ? 0 : c.batch);
+        };
+
+        if constexpr (T::kHasAux) {
+            if (!args.direct && lane == 0) {
+                int u = blockIdx.x, ch = 0;
+                if (next_valid(u, ch)) issue_aux(u, ch);
+            }
+        }
+
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < args.num_units; u += gridDim.x, ++it) {
+            const UnitCoord c = decode_unit(args, u);
+            const uint32_t as = it & 1, ap = (it >> 1) & 1;
+            mbar_wait(&tmem_full_bar[as], ap);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((quad * 32) << 16) + as * BN + half * 128;
+            const int row_in_batch = c.m_blk * BM + quad * 32 + lane;  // GEMM row of this thread
+            const int row0 = args.c_row_offset + c.m_blk * BM + quad * 32;
+
+            int n_valid_chunks = 0;
+#pragma unroll
+            for (int ch = 0; ch < int(kChunks); ++ch)
+                if (c.n_blk * BN + half * 128 + ch * int(CPC) < args.N) n_valid_chunks = ch + 1;
+            if (n_valid_chunks == 0) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                continue;
+            }
+
+            for (int ch = 0; ch < n_valid_chunks; ++ch) {
+                const int col0 = c.n_blk * BN + half * 128 + ch * CPC;
+                if constexpr (T::kHasAux) {
+                    if (!args.direct) {
+                        mbar_wait(&aux_bar[ew], aux_phase);
+                        aux_phase ^= 1;
+                    }
+                }
+                const bool write_c = (EPI != VB_EPI_GELU) || args.C != nullptr;
+#pragma unroll
+                for (int g = 0; g < int(CPC / 32); ++g) {
+                    const int colg = col0 + g * 32;
+                    // ---- accumulator -> registers (32 fp32 columns of this thread's row) ----
+                    uint32_t acc[32];
+                    tmem_ld_32x32b_x32(t_addr + ch * CPC + g * 32, acc);
+                    tmem_ld_wait();
+                    if (ch == n_valid_chunks - 1 && g == int(CPC / 32) - 1) {
+                        // all TMEM reads of this tile by this warp are done -> hand the accumulator back
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                    // ---- bias ----
+                    if (args.bias != nullptr) {
+                        if (colg + 32 <= args.N) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + colg + j));
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (colg + j < args.N) v[j] += __ldg(args.bias + colg + j);
+                        }
+                    }
+                    // ---- aux operand (same dtype / geometry as C) ----
+                    float x[32];
+                    if constexpr (T::kHasAux) {
+                        if (!args.direct) {
+                            if constexpr (CDT == VB_F32) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const uint4 w = *reinterpret_cast<const uint4*>(buf1 + row_off + ((q << 4) ^ swz));
+                                    x[q * 4 + 0] = __uint_as_float(w.x); x[q * 4 + 1] = __uint_as_float(w.y);
+                                    x[q * 4 + 2] = __uint_as_float(w.z); x[q * 4 + 3] = __uint_as_float(w.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint4 w = *reinterpret_cast<const uint4*>(buf1 + row_off + ((((g * 4 + q)) << 4) ^ swz));
+                                    x[q * 8 + 0] = bf16_lo(w.x); x[q * 8 + 1] = bf16_hi(w.x);
+                                    x[q * 8 + 2] = bf16_lo(w.y); x[q * 8 + 3] = bf16_hi(w.y);
+                                    x[q * 8 + 4] = bf16_lo(w.z); x[q * 8 + 5] = bf16_hi(w.z);
+                                    x[q * 8 + 6] = bf16_lo(w.w); x[q * 8 + 7] = bf16_hi(w.w);
+                                }
+                            }
+                        } else {
+                            const long long ab = args.aux_bcast ? 0 : (long long)c.batch * args.bsaux;
+                            const long long off = ab + (long long)(args.c_row_offset + row_in_batch) * args.ldaux + colg;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const bool ok = row_in_batch < args.M && colg + j < args.N;
+                                if constexpr (CDT == VB_F32) x[j] = ok ? reinterpret_cast<const float*>(args.AUX)[off + j] : 0.f;
+                                else x[j] = ok ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(args.AUX)[off + j]) : 0.f;
+                            }
+                        }
+                    }
+                    // ---- fused math ----
+                    float gl[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if constexpr (EPI == VB_EPI_GELU) gl[j] = gelu_erf(v[j]);
+                        if constexpr (EPI == VB_EPI_RESIDUAL) v[j] += x[j];
+                        if constexpr (EPI == VB_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
+                        if constexpr (EPI == VB_EPI_DGELU) v[j] *= dgelu_erf(x[j]);
+                        if constexpr (EPI == VB_EPI_DRELU) v[j] = x[j] > 0.f ? v[j] : 0.f;
+                    }
+                    // ---- registers -> swizzled staging buffer (or straight to global on the bring-up path) ----
+                    if (!args.direct) {
+                        if (g == 0) {
+                            if (lane == 0) tma_store_wait_read<0>();  // previous TMA store out of buf0/buf1 has drained
+                            __syncwarp();
+                        }
+                        if constexpr (CDT == VB_F32) {
+                            if (write_c) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    uint4 w;
+                                    w.x = __float_as_uint(v[q * 4 + 0]); w.y = __float_as_uint(v[q * 4 + 1]);
+                                    w.z = __float_as_uint(v[q * 4 + 2]); w.w = __float_as_uint(v[q * 4 + 3]);
+                                    *reinterpret_cast<uint4*>(buf0 + row_off + ((q << 4) ^ swz)) = w;
+                                }
+                            }
+                        } else {
+                            if (write_c) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    uint4 w;
+                                    w.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                                    w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                                    *reinterpret_cast<uint4*>(buf0 + row_off + (((g * 4 + q) << 4) ^ swz)) = w;
+                                }
+                            }
+                            if constexpr (T::kTwoOut) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    uint4 w;
+                                    w.x = pack_bf16(gl[q * 8 + 0], gl[q * 8 + 1]); w.y = pack_bf16(gl[q * 8 + 2], gl[q * 8 + 3]);
+                                    w.z = pack_bf16(gl[q * 8 + 4], gl[q * 8 + 5]); w.w = pack_bf16(gl[q * 8 + 6], gl[q * 8 + 7]);
+                                    *reinterpret_cast<uint4*>(buf1 + row_off + (((g * 4 + q) << 4) ^ swz)) = w;
+                                }
+                            }
+                        }
+                    } else if (row_in_batch < args.M) {
+                        const long long off = (long long)c.batch * args.bsc + (long long)(args.c_row_offset + row_in_batch) * args.ldc + colg;
+                        const long long off2 = (long long)c.batch * args.bsc2 + (long long)(args.c_row_offset + row_in_batch) * args.ldc2 + colg;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (colg + j >= args.N) continue;
+                            if constexpr (EPI == VB_EPI_ACCUM) {
+                                atomicAdd(reinterpret_cast<float*>(args.C) + off + j, v[j]);
+                            } else if (write_c) {
+                                if constexpr (CDT == VB_F32) reinterpret_cast<float*>(args.C)[off + j] = v[j];
+                                else reinterpret_cast<__nv_bfloat16*>(args.C)[off + j] = __float2bfloat16_rn(v[j]);
+                            }
+                            if constexpr (T::kTwoOut) reinterpret_cast<__nv_bfloat16*>(args.C2)[off2 + j] = __float2bfloat16_rn(gl[j]);
+                        }
+                    }
+                }
+                if (!args.direct) {
+                    fence_proxy_async_smem();  // staging writes (and aux reads) ordered before the async proxy touches smem
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (T::kHasAux) {
+                            // aux buffer consumed: prefetch the aux tile of the next chunk this warp will process
+                            int nu = u, nch = ch + 1;
+                            if (nch >= n_valid_chunks) { nu += gridDim.x; nch = 0; }
+                            if (next_valid(nu, nch)) issue_aux(nu, nch);
+                        }
+                        if constexpr (EPI == VB_EPI_ACCUM) {
+                            tma_reduce_add_3d(&tmC, buf0, col0, row0, c.batch);
+                        } else {
+                            if (write_c) tma_store_3d(&tmC, buf0, col0, row0, c.batch);
+                            if constexpr (T::kTwoOut) tma_store_3d(&tmC2, buf1, col0, row0, c.batch);
+                        }
+                        tma_store_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D map (inner, rows, batch) with a 128-byte-swizzled (box0 x box1 x 1) box.
+int make_tmap_3d(CUtensorMap* m, int dtype, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
+                 uint64_t batch_stride_elems, uint32_t box0, uint32_t box1) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const uint64_t es = (dtype == VB_BF16) ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(VB_ERR_ARG, "tensor base %p not 16-byte aligned", ptr);
+    if ((ld_elems * es) % 16 != 0) return fail(VB_ERR_ARG, "row pitch %llu bytes not a multiple of 16", (unsigned long long)(ld_elems * es));
+    if (d2 > 1 && (batch_stride_elems * es) % 16 != 0) return fail(VB_ERR_ARG, "batch stride not a multiple of 16 bytes");
+    if (box0 * es > 128 || box1 > 256) return fail(VB_ERR_ARG, "bad TMA box %u x %u", box0, box1);
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {ld_elems * es, (d2 > 1 ? batch_stride_elems : d1 * ld_elems) * es};
+    if (strides[1] == 0) strides[1] = strides[0];
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, dtype == VB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(VB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu, pitch %llu B, box %u x %u", (int)r,
+                    (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                    (unsigned long long)strides[0], box0, box1);
+    return VB_OK;
+}
+
+template <int AMAJ, int BMAJ, int EPI, int CDT>
+static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tC2,
+                  const CUtensorMap& tX, const GemmArgs& args, int grid, cudaStream_t stream) {
+    auto kern = gemm_kernel<AMAJ, BMAJ, EPI, CDT>;
+    constexpr uint32_t smem = EpiTraits<EPI>::kSmemBytes;
+    static bool configured = false;  // per instantiation; attribute is per-context, benign to repeat on races
+    if (!configured) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(tA, tB, tC, tC2, tX, args);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+}  // namespace vb
+
+extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
+    using namespace vb;
+    if (!d) return fail(VB_ERR_ARG, "null descriptor");
+    if (int rc = check_arch()) return rc;
+    cudaStream_t stream = as_stream(stream_);
+    VB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->batches >= 1, "bad GEMM dims M=%d N=%d K=%d batches=%d", d->M, d->N, d->K, d->batches);
+    VB_REQUIRE(d->A && d->B && d->C || (d->epilogue == VB_EPI_GELU && d->A && d->B && d->C2), "null operand pointer");
+    VB_REQUIRE(d->a_major == 0 || d->a_major == 1, "bad a_major");
+    VB_REQUIRE(d->b_major == 0 || d->b_major == 1, "bad b_major");
+    VB_REQUIRE(d->c_dtype == VB_BF16 || d->c_dtype == VB_F32, "bad c_dtype");
+    const int split = d->split_k > 1 ? d->split_k : 1;
+    VB_REQUIRE(split == 1 || d->epilogue == VB_EPI_ACCUM, "split_k > 1 requires VB_EPI_ACCUM");
+    VB_REQUIRE(d->epilogue != VB_EPI_ACCUM || d->c_dtype == VB_F32, "VB_EPI_ACCUM requires fp32 C");
+    const bool has_aux = d->epilogue == VB_EPI_RESIDUAL || d->epilogue == VB_EPI_DGELU || d->epilogue == VB_EPI_DRELU;
+    VB_REQUIRE(!has_aux || d->AUX, "epilogue %d needs AUX", d->epilogue);
+    VB_REQUIRE(d->epilogue != VB_EPI_GELU || (d->C2 && d->c_dtype == VB_BF16), "VB_EPI_GELU needs bf16 C2");
+
+    GemmArgs a{};
+    a.M = d->M; a.N = d->N; a.K = d->K; a.batches = d->batches;
+    const int m_blocks = (d->M + BM - 1) / BM;
+    a.n_blocks = (d->N + BN - 1) / BN;
+    a.k_blocks = (d->K + BK - 1) / BK;
+    a.tiles_per_batch = m_blocks * a.n_blocks;
+    a.num_tiles = a.tiles_per_batch * d->batches;
+    a.kb_per_split = (a.k_blocks + split - 1) / split;
+    a.split_k = (a.k_blocks + a.kb_per_split - 1) / a.kb_per_split;  // drop empty splits
+    a.num_units = a.num_tiles * a.split_k;
+    a.c_row_offset = d->c_row_offset;
+    a.aux_bcast = d->aux_batch_broadcast;
+    a.b_batched = d->batch_stride_b != 0;
+    a.direct = d->debug_direct_store;
+    a.bias = d->bias;
+    a.C = d->C; a.C2 = d->C2; a.AUX = d->AUX;
+    a.ldc = d->ldc; a.ldc2 = d->ldc2; a.ldaux = d->ldaux;
+    a.bsc = d->batch_stride_c; a.bsc2 = d->batch_stride_c2; a.bsaux = d->batch_stride_aux;
+    const uint64_t c_rows = d->c_rows > 0 ? d->c_rows : d->M + d->c_row_offset;
+
+    CUtensorMap tA, tB, tC, tC2, tX;
+    int rc;
+    const uint64_t nb = d->batches;
+    if (d->a_major == 0) rc = make_tmap_3d(&tA, VB_BF16, d->A, d->K, d->M, nb, d->lda, d->batch_stride_a, 64, BM);
+    else rc = make_tmap_3d(&tA, VB_BF16, d->A, d->M, d->K, nb, d->lda, d->batch_stride_a, 64, BK);
+    if (rc) return rc;
+    const uint64_t nbb = a.b_batched ? nb : 1;
+    if (d->b_major == 0) rc = make_tmap_3d(&tB, VB_BF16, d->B, d->K, d->N, nbb, d->ldb, d->batch_stride_b, 64, BN);
+    else rc = make_tmap_3d(&tB, VB_BF16, d->B, d->N, d->K, nbb, d->ldb, d->batch_stride_b, 64, BK);
+    if (rc) return rc;
+    const uint32_t cpc = d->c_dtype == VB_BF16 ? 64 : 32;
+    const bool have_c = d->C != nullptr;
+    if (have_c) {
+        rc = make_tmap_3d(&tC, d->c_dtype, d->C, d->N, c_rows, nb, d->ldc, d->batch_stride_c, cpc, 32);
+        if (rc) return rc;
+    }
+    if (d->epilogue == VB_EPI_GELU) {
+        rc = make_tmap_3d(&tC2, VB_BF16, d->C2, d->N, c_rows, nb, d->ldc2, d->batch_stride_c2, cpc, 32);
+        if (rc) return rc;
+        if (!have_c) tC = tC2;
+    } else {
+        tC2 = tC;
+    }
+    if (has_aux) {
+        rc = make_tmap_3d(&tX, d->c_dtype, d->AUX, d->N, c_rows, d->aux_batch_broadcast ? 1 : nb, d->ldaux, d->batch_stride_aux, cpc, 32);
+        if (rc) return rc;
+    } else {
+        tX = tC;
+    }
+
+    int sms = num_sms();
+    if (sms <= 0) return fail(VB_ERR_CUDA, "cannot determine SM count");
+    int grid = d->max_ctas > 0 ? (d->max_ctas < sms ? d->max_ctas : sms) : sms;
+    if (grid > a.num_units) grid = a.num_units;
+
+#define VB_LAUNCH(AM, BMJ, EP, CD) return launch<AM, BMJ, EP, CD>(tA, tB, tC, tC2, tX, a, grid, stream)
+    const int am = d->a_major, bm = d->b_major, ep = d->epilogue, cd = d->c_dtype;
+    if (am == 0 && bm == 0) {
+        if (ep == VB_EPI_STORE && cd == VB_BF16) VB_LAUNCH(0, 0, VB_EPI_STORE, VB_BF16);
+        if (ep == VB_EPI_STORE && cd == VB_F32) VB_LAUNCH(0, 0, VB_EPI_STORE, VB_F32);
+        if (ep == VB_EPI_GELU && cd == VB_BF16) VB_LAUNCH(0, 0, VB_EPI_GELU, VB_BF16);
+        if (ep == VB_EPI_RESIDUAL && cd == VB_F32) VB_LAUNCH(0, 0, VB_EPI_RESIDUAL, VB_F32);
+        if (ep == VB_EPI_RELU && cd == VB_BF16) VB_LAUNCH(0, 0, VB_EPI_RELU, VB_BF16);
+    } else if (am == 0 && bm == 1) {
+        if (ep == VB_EPI_STORE && cd == VB_BF16) VB_LAUNCH(0, 1, VB_EPI_STORE, VB_BF16);
+        if (ep == VB_EPI_STORE && cd == VB_F32) VB_LAUNCH(0, 1, VB_EPI_STORE, VB_F32);
+        if (ep == VB_EPI_DGELU && cd == VB_BF16) VB_LAUNCH(0, 1, VB_EPI_DGELU, VB_BF16);
+        if (ep == VB_EPI_DRELU && cd == VB_BF16) VB_LAUNCH(0, 1, VB_EPI_DRELU, VB_BF16);
+    } else if (am == 1 && bm == 1) {
+        if (ep == VB_EPI_ACCUM && cd == VB_F32) VB_LAUNCH(1, 1, VB_EPI_ACCUM, VB_F32);
+        if (ep == VB_EPI_STORE && cd == VB_F32) VB_LAUNCH(1, 1, VB_EPI_STORE, VB_F32);
+    }
+#undef VB_LAUNCH
+    return fail(VB_ERR_UNSUPPORTED, "no GEMM instantiation for a_major=%d b_major=%d epilogue=%d c_dtype=%d", am, bm, ep, cd);
+}
