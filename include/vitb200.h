@@ -129,6 +129,25 @@ typedef struct VbAttnDesc {
 VB_API int vb_attention_fwd(const VbAttnDesc* desc, void* stream);
 VB_API int vb_attention_bwd(const VbAttnDesc* desc, void* stream);
 
+/* ---- Helper kernels around the encoder (HBM-bound) -----------------------------------------------------------
+ * vb_cast_f32_to_bf16: flat fp32 -> bf16 cast (master parameters -> tensor-core operands), n % 4 == 0.
+ * vb_patchify: images [B,C,H,W] fp32 -> [B, (H/p)(W/p), C*p*p] bf16 with k = c*p*p + i*p + j, the operand of
+ *              conv_proj-as-GEMM (nn.Conv2d(k=s=p) + reshape/permute, vanilla_vit.py:129,196-198).
+ * vb_token_rows: x[b,t,:] = token_t + pos[t] for the n_prefix (1 = cls, 2 = cls+dist) leading rows of the
+ *              fp32 stream [B,S,D] (torch.cat + pos add, vanilla_vit.py:202-203,104).
+ * vb_colsum_bf16: out[c] += sum_r x[r,c] (bias gradients of nn.Linear, autograd of vanilla_vit.py:34,41).
+ * vb_embed_bwd: from dx [B,S,D] fp32: dpos += sum_b dx[b]; dtok_t += sum_b dx[b,t]; dbias += sum_{b,s>=n_prefix} dx[b,s];
+ *              dx_patches_bf16 [B*(S-n_prefix), D] = compact bf16 copy (A operand of the conv_proj wgrad GEMM).
+ *              possum_scratch is [S,D] fp32 scratch. */
+VB_API int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+VB_API int vb_patchify(const float* images, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
+                       void* stream);
+VB_API int vb_token_rows(float* x, const float* tok0, const float* tok1, const float* pos, int32_t B, int32_t S, int32_t D,
+                         int32_t n_prefix, void* stream);
+VB_API int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, float* out_accum, void* stream);
+VB_API int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_patches_bf16, float* dpos, float* dtok0, float* dtok1,
+                        float* dbias, int32_t B, int32_t S, int32_t D, int32_t n_prefix, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,260 @@
+"""CPU oracle: a functional PyTorch-fp32 restatement of the reference's encoder hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package (vitb200/) may import this module; it is used by
+tests/, by __graft_entry__.smoke() as the checker, and by bench.py for the `cpu_baseline` / `--impl reference`
+legs.  It computes with the same ATen CPU operators the reference modules dispatch to (F.linear, F.layer_norm,
+F.gelu, F.scaled_dot_product_attention, F.conv2d), driven by a plain ``state_dict`` with the reference's keys,
+so that its results and its timing are those of the reference's own CPU path.
+
+Parity status: PINNED against the reference itself.  tools/make_golden.py imports the unmodified modules from
+/root/reference (in the build container), runs them on seeded inputs/weights and stores the results under
+tests/golden/; tests/test_oracle.py checks this restatement against those fixtures (and, when /root/reference
+is present, against the live reference).  Exception: the DeiT *model class* lives in timm, which is absent
+ — its block arithmetic is the pinned ViT arithmetic, only key names / token order are restated
+from timm's public semantics ("parity unpinned" for those names).
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------------------------
+# ViT (models/image_classification/vanilla_vit.py)
+# ------------------------------------------------------------------------------------------------------------
+def mha_batch_first(x, in_w, in_b, out_w, out_b, num_heads):
+    """nn.MultiheadAttention(D, H, batch_first=True)(x, x, x, need_weights=False)  — vanilla_vit.py:67,77.
+
+    Packed in-projection (torch/nn/functional.py:5835-5847), per-head softmax(QK^T/sqrt(hd))V via SDPA
+    (functional.py:6676-6682), out-projection (functional.py:6690).
+    """
+    B, S, D = x.shape
+    hd = D // num_heads
+    qkv = F.linear(x, in_w, in_b)
+    q, k, v = qkv.split(D, dim=-1)
+    q = q.view(B, S, num_heads, hd).transpose(1, 2)
+    k = k.view(B, S, num_heads, hd).transpose(1, 2)
+    v = v.view(B, S, num_heads, hd).transpose(1, 2)
+    o = F.scaled_dot_product_attention(q, k, v)
+    o = o.transpose(1, 2).reshape(B, S, D)
+    return F.linear(o, out_w, out_b)
+
+
+def encoder_block(x, sd, prefix, num_heads, eps):
+    """EncoderBlock.forward — vanilla_vit.py:73-83 (pre-norm; dropout p=0)."""
+    h = F.layer_norm(x, (x.shape[-1],), sd[prefix + "ln_1.weight"], sd[prefix + "ln_1.bias"], eps)
+    a = mha_batch_first(h, sd[prefix + "self_attention.in_proj_weight"], sd[prefix + "self_attention.in_proj_bias"],
+                        sd[prefix + "self_attention.out_proj.weight"], sd[prefix + "self_attention.out_proj.bias"], num_heads)
+    x = a + x
+    y = F.layer_norm(x, (x.shape[-1],), sd[prefix + "ln_2.weight"], sd[prefix + "ln_2.bias"], eps)
+    y = F.linear(y, sd[prefix + "mlp.0.weight"], sd[prefix + "mlp.0.bias"])       # MLPBlock: vanilla_vit.py:33-34
+    y = F.gelu(y)                                                                  # nn.GELU() (erf): :50
+    y = F.linear(y, sd[prefix + "mlp.3.weight"], sd[prefix + "mlp.3.bias"])       # :41
+    return x + y
+
+
+def vit_forward_features(sd, images, *, patch_size, num_layers, num_heads, eps=1e-6):
+    """ViT.forward_features + Encoder.forward — vanilla_vit.py:186-207, :102-106."""
+    n = images.shape[0]
+    D = sd["class_token"].shape[-1]
+    x = F.conv2d(images, sd["conv_proj.weight"], sd["conv_proj.bias"], stride=patch_size)   # :196
+    x = x.reshape(n, D, -1).permute(0, 2, 1)                                                   # :197-198
+    x = torch.cat([sd["class_token"].expand(n, -1, -1), x], dim=1)                             # :202-203
+    x = x + sd["encoder.pos_embedding"]                                                        # :104
+    for i in range(num_layers):
+        x = encoder_block(x, sd, f"encoder.layers.encoder_layer_{i}.", num_heads, eps)
+    return F.layer_norm(x, (D,), sd["encoder.ln.weight"], sd["encoder.ln.bias"], eps)         # :106
+
+
+def vit_forward(sd, images, **cfg):
+    """ViT.forward — vanilla_vit.py:209-215."""
+    x = vit_forward_features(sd, images, **cfg)
+    return F.linear(x[:, 0], sd["heads.head.weight"], sd["heads.head.bias"])
+
+
+def vit_param_shapes(image_size, patch_size, num_layers, num_heads, hidden_dim, mlp_dim, num_classes):
+    """state_dict keys/shapes created by ViT.__init__ — vanilla_vit.py:109-151 (== torchvision vit_* keys)."""
+    D, Fd = hidden_dim, mlp_dim
+    S = (image_size // patch_size) ** 2 + 1
+    shapes = {"class_token": (1, 1, D), "conv_proj.weight": (D, 3, patch_size, patch_size), "conv_proj.bias": (D,),
+              "encoder.pos_embedding": (1, S, D)}
+    for i in range(num_layers):
+        p = f"encoder.layers.encoder_layer_{i}."
+        shapes.update({p + "ln_1.weight": (D,), p + "ln_1.bias": (D,),
+                       p + "self_attention.in_proj_weight": (3 * D, D), p + "self_attention.in_proj_bias": (3 * D,),
+                       p + "self_attention.out_proj.weight": (D, D), p + "self_attention.out_proj.bias": (D,),
+                       p + "ln_2.weight": (D,), p + "ln_2.bias": (D,),
+                       p + "mlp.0.weight": (Fd, D), p + "mlp.0.bias": (Fd,),
+                       p + "mlp.3.weight": (D, Fd), p + "mlp.3.bias": (D,)})
+    shapes.update({"encoder.ln.weight": (D,), "encoder.ln.bias": (D,),
+                   "heads.head.weight": (num_classes, D), "heads.head.bias": (num_classes,)})
+    return shapes
+
+
+# ------------------------------------------------------------------------------------------------------------
+# DeiT-style distilled ViT (timm VisionTransformerDistilled as used at deit.py:39-45,65,95-96)
+# ------------------------------------------------------------------------------------------------------------
+def deit_param_shapes(img_size, patch_size, depth, num_heads, embed_dim, mlp_ratio, num_classes):
+    D = embed_dim
+    Fd = int(D * mlp_ratio)
+    N = (img_size // patch_size) ** 2
+    shapes = {"cls_token": (1, 1, D), "dist_token": (1, 1, D), "pos_embed": (1, N + 2, D),
+              "patch_embed.proj.weight": (D, 3, patch_size, patch_size), "patch_embed.proj.bias": (D,)}
+    for i in range(depth):
+        p = f"blocks.{i}."
+        shapes.update({p + "norm1.weight": (D,), p + "norm1.bias": (D,),
+                       p + "attn.qkv.weight": (3 * D, D), p + "attn.qkv.bias": (3 * D,),
+                       p + "attn.proj.weight": (D, D), p + "attn.proj.bias": (D,),
+                       p + "norm2.weight": (D,), p + "norm2.bias": (D,),
+                       p + "mlp.fc1.weight": (Fd, D), p + "mlp.fc1.bias": (Fd,),
+                       p + "mlp.fc2.weight": (D, Fd), p + "mlp.fc2.bias": (D,)})
+    shapes.update({"norm.weight": (D,), "norm.bias": (D,), "head.weight": (num_classes, D), "head.bias": (num_classes,),
+                   "head_dist.weight": (num_classes, D), "head_dist.bias": (num_classes,)})
+    return shapes
+
+
+def deit_forward(sd, images, *, patch_size, depth, num_heads, training, distilled_training, eps=1e-6):
+    """Distilled ViT forward: tokens [cls, dist, patches] + pos_embed, pre-norm blocks (same arithmetic as
+    encoder_block, timm key names), final norm, head(x[:,0]) / head_dist(x[:,1]); tuple iff training and
+    distilled_training (deit.py:45,65,70), else their mean (deit.py:95-96)."""
+    n = images.shape[0]
+    D = sd["cls_token"].shape[-1]
+    x = F.conv2d(images, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch_size)
+    x = x.flatten(2).transpose(1, 2)
+    x = torch.cat([sd["cls_token"].expand(n, -1, -1), sd["dist_token"].expand(n, -1, -1), x], dim=1)
+    x = x + sd["pos_embed"]
+    for i in range(depth):
+        p = f"blocks.{i}."
+        h = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+        a = mha_batch_first(h, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"], sd[p + "attn.proj.weight"],
+                            sd[p + "attn.proj.bias"], num_heads)
+        x = x + a
+        y = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+        y = F.linear(F.gelu(F.linear(y, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])), sd[p + "mlp.fc2.weight"],
+                     sd[p + "mlp.fc2.bias"])
+        x = x + y
+    x = F.layer_norm(x, (D,), sd["norm.weight"], sd["norm.bias"], eps)
+    out = F.linear(x[:, 0], sd["head.weight"], sd["head.bias"])
+    out_dist = F.linear(x[:, 1], sd["head_dist.weight"], sd["head_dist.bias"])
+    if training and distilled_training:
+        return out, out_dist
+    return (out + out_dist) / 2
+
+
+def distillation_loss(outputs, outputs_kd, labels, teacher_logits, distillation_type, alpha, tau):
+    """DistillationLoss.forward — utils/distillation_loss.py:30-75 (base criterion = mean cross-entropy)."""
+    base = F.cross_entropy(outputs, labels)                                        # :43
+    if distillation_type == "none":
+        return base                                                                # :44-45
+    if distillation_type == "soft":                                                # :55-67
+        T = tau
+        kd = F.kl_div(F.log_softmax(outputs_kd / T, dim=1), F.log_softmax(teacher_logits / T, dim=1), reduction="sum",
+                      log_target=True) * (T * T) / outputs_kd.numel()
+    else:                                                                          # hard, :71-72
+        kd = F.cross_entropy(outputs_kd, teacher_logits.argmax(dim=1))
+    return base * (1 - alpha) + kd * alpha                                         # :74
+
+
+# ------------------------------------------------------------------------------------------------------------
+# DETR transformer encoder (models/object_detection/transformer.py:98-115, 192-247)
+# ------------------------------------------------------------------------------------------------------------
+def detr_param_shapes(d_model, dim_feedforward, num_layers, normalize_before):
+    D, Fd = d_model, dim_feedforward
+    shapes = {}
+    for i in range(num_layers):
+        p = f"layers.{i}."
+        shapes.update({p + "self_attn.in_proj_weight": (3 * D, D), p + "self_attn.in_proj_bias": (3 * D,),
+                       p + "self_attn.out_proj.weight": (D, D), p + "self_attn.out_proj.bias": (D,),
+                       p + "linear1.weight": (Fd, D), p + "linear1.bias": (Fd,),
+                       p + "linear2.weight": (D, Fd), p + "linear2.bias": (D,),
+                       p + "norm1.weight": (D,), p + "norm1.bias": (D,), p + "norm2.weight": (D,), p + "norm2.bias": (D,)})
+    if normalize_before:
+        shapes.update({"norm.weight": (D,), "norm.bias": (D,)})
+    return shapes
+
+
+def _detr_self_attn(qk_in, v_in, sd, p, nhead, key_padding_mask):
+    """self_attn(q, k, value=src, key_padding_mask=...)[0] with q = k = src + pos — transformer.py:218-219.
+    q is k but k is not v => three separate projections (torch/nn/functional.py:5866-5873); explicit
+    softmax(QK^T/sqrt(hd) + mask)V (functional.py:6630-6666); sequence-first tensors [S, N, C]."""
+    S, N, D = qk_in.shape
+    hd = D // nhead
+    w, b = sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"]
+    q = F.linear(qk_in, w[:D], b[:D])
+    k = F.linear(qk_in, w[D:2 * D], b[D:2 * D])
+    v = F.linear(v_in, w[2 * D:], b[2 * D:])
+    q = q.view(S, N, nhead, hd).permute(1, 2, 0, 3)
+    k = k.view(S, N, nhead, hd).permute(1, 2, 0, 3)
+    v = v.view(S, N, nhead, hd).permute(1, 2, 0, 3)
+    mask = None
+    if key_padding_mask is not None:
+        mask = torch.zeros(N, 1, 1, S, dtype=q.dtype, device=q.device).masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+    o = o.permute(2, 0, 1, 3).reshape(S, N, D)
+    return F.linear(o, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+
+
+def detr_encoder_forward(sd, src, *, nhead, num_layers, normalize_before=False, activation="relu", src_key_padding_mask=None,
+                         pos=None, eps=1e-5):
+    """TransformerEncoder.forward over TransformerEncoderLayer.forward_post/pre — transformer.py:105-115, 213-241
+    (dropout p=0).  src, pos: [S, N, C]; src_key_padding_mask: [N, S] bool, True = padding."""
+    act = F.relu if activation == "relu" else F.gelu
+    D = src.shape[-1]
+    x = src
+    for i in range(num_layers):
+        p = f"layers.{i}."
+        if not normalize_before:                                                   # forward_post :213-226
+            qk = x if pos is None else x + pos
+            x = x + _detr_self_attn(qk, x, sd, p, nhead, src_key_padding_mask)
+            x = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+            y = F.linear(act(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])), sd[p + "linear2.weight"],
+                         sd[p + "linear2.bias"])
+            x = F.layer_norm(x + y, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+        else:                                                                      # forward_pre :228-241
+            h = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+            qk = h if pos is None else h + pos
+            x = x + _detr_self_attn(qk, h, sd, p, nhead, src_key_padding_mask)
+            h = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+            x = x + F.linear(act(F.linear(h, sd[p + "linear1.weight"], sd[p + "linear1.bias"])), sd[p + "linear2.weight"],
+                             sd[p + "linear2.bias"])
+    if "norm.weight" in sd:                                                        # :112-113
+        x = F.layer_norm(x, (D,), sd["norm.weight"], sd["norm.bias"], eps)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Seeded weights / inputs shared by the golden generator, the tests, smoke() and bench.py
+# ------------------------------------------------------------------------------------------------------------
+def seeded_state_dict(shapes, seed, std=0.02):
+    """Deterministic (CPU generator) N(0, std^2) tensors; LayerNorm weights are 1 + N(0, std^2).
+    A freshly constructed reference ViT has a zero head (vanilla_vit.py:149-151), which makes parity tests
+    vacuous, hence seeded random weights everywhere."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        t = torch.randn(*shp, generator=g, dtype=torch.float32) * std
+        is_norm_w = k.endswith("weight") and any(s in k for s in ("ln_1.", "ln_2.", "ln.", "norm1.", "norm2.", "norm."))
+        if is_norm_w:
+            t = t + 1.0
+        if k.endswith("in_proj_weight") or k.endswith("qkv.weight") or k.endswith(".0.weight") or k.endswith(".3.weight") or \
+                k.endswith("linear1.weight") or k.endswith("linear2.weight") or k.endswith("fc1.weight") or k.endswith("fc2.weight") or \
+                k.endswith("proj.weight") or k.endswith("out_proj.weight"):
+            t = t * (1.0 / std) * math.sqrt(1.0 / shp[-1]) if len(shp) == 2 else t
+        if k.endswith("conv_proj.weight") or k.endswith("patch_embed.proj.weight"):
+            t = t * (1.0 / std) * math.sqrt(1.0 / (shp[1] * shp[2] * shp[3]))
+        if k.endswith("head.weight") or k.endswith("head_dist.weight"):
+            t = t * (1.0 / std) * math.sqrt(1.0 / shp[-1])
+        sd[k] = t
+    return sd
+
+
+def seeded_images(batch, image_size, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(batch, 3, image_size, image_size, generator=g, dtype=torch.float32)
+
+
+def seeded_labels(batch, num_classes, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randint(0, num_classes, (batch,), generator=g)

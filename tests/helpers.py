@@ -1,0 +1,35 @@
+"""Shared helpers for the parity tests: relative-L2 comparison and oracle runs (tests may import oracle/)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import vit_oracle as O  # noqa: E402
+
+
+def rel_l2(a, b):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def oracle_vit_run(cfg, sd, images, labels=None, want="logits", grad_out=None):
+    """Runs the CPU oracle forward (+ backward). Returns (output, loss, grads dict)."""
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    kw = dict(patch_size=cfg["patch_size"], num_layers=cfg["num_layers"], num_heads=cfg["num_heads"])
+    if want == "logits":
+        out = O.vit_forward(sd, images, **kw)
+    else:
+        out = O.vit_forward_features(sd, images, **kw)
+    loss = None
+    if labels is not None:
+        loss = torch.nn.functional.cross_entropy(out, labels)
+        loss.backward()
+    elif grad_out is not None:
+        out.backward(grad_out)
+    grads = {k: v.grad for k, v in sd.items() if v.grad is not None}
+    return out.detach(), (loss.detach() if loss is not None else None), grads

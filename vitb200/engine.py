@@ -1,0 +1,375 @@
+"""Forward/backward engine for the pre-norm ViT / DeiT encoder stack on one B200.
+
+The engine owns (a) a flat fp32 parameter buffer and a flat fp32 gradient buffer that the module's
+``nn.Parameter``s are views of (laid out in gradient-production order so that data-parallel buckets are
+contiguous slices), (b) a bf16 shadow of the parameters for the tensor-core operands, and (c) per-batch-size
+activation workspaces.  It sequences the C-ABI kernels of libvitb200.so on the current CUDA stream; there is no
+PyTorch arithmetic on the path (torch is used for allocation, streams and the autograd hook only).
+
+Reference dataflow being reproduced: ViT.forward_features / Encoder.forward / EncoderBlock.forward
+(vanilla_vit.py:186-207, 102-106, 73-83) and their autograd; SURVEY.md Appendix C lists what is saved.
+"""
+import torch
+
+from . import ops
+
+LAYER_ROLES = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
+_ALIGN = 64  # elements; keeps every parameter 256-byte (fp32) / 128-byte (bf16) aligned for TMA and float4 access
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pick_split_k(tiles, k_blocks, sms):
+    """Split-K factor for a wgrad GEMM: fill a whole number of waves of `sms` CTAs, keep >= 8 k-blocks per unit."""
+    best, best_eff = 1, 0.0
+    for s in range(1, 33):
+        if s > 1 and k_blocks // s < 8:
+            break
+        units = tiles * s
+        eff = units / (-(-units // sms) * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
+
+
+class VitEngine:
+    """Sequences the kernels for `n_prefix` token rows (1 = cls, 2 = cls + dist) + patches through L pre-norm blocks."""
+
+    def __init__(self, *, image_size, patch_size, hidden_dim, num_heads, mlp_dim, num_layers, num_classes, n_prefix, eps,
+                 globals_, layers):
+        """globals_: role -> Parameter for cls, [dist], pos, conv_w, conv_b, lnf_w, lnf_b, head_w, head_b, [headd_w, headd_b];
+        layers: list of dicts role -> Parameter (LAYER_ROLES)."""
+        assert hidden_dim % 128 == 0 and hidden_dim // num_heads == 64, \
+            "vitb200 kernels need hidden_dim % 128 == 0 and head_dim == 64 (true for every reference config)"
+        assert patch_size % 4 == 0 and image_size % patch_size == 0
+        self.image_size, self.p = image_size, patch_size
+        self.D, self.H, self.F, self.L, self.C = hidden_dim, num_heads, mlp_dim, num_layers, num_classes
+        self.n_prefix, self.eps = n_prefix, eps
+        self.P = (image_size // patch_size) ** 2
+        self.S = self.P + n_prefix
+        self.Kp = 3 * patch_size * patch_size
+        self.Kp_ld = _round_up(self.Kp, 8)
+        self.C_ld = _round_up(num_classes, 8)
+        self.g = globals_
+        self.layers = layers
+        self.two_heads = "headd_w" in globals_
+        # gradient-production order: heads + final norm, blocks L-1..0, embedding
+        seg0 = ["head_w", "head_b"] + (["headd_w", "headd_b"] if self.two_heads else []) + ["lnf_w", "lnf_b"]
+        emb = ["pos", "cls"] + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
+        self._order = [(("g", r), globals_[r]) for r in seg0]
+        self.segments = [(0, None)]  # (start offset, end offset) filled below
+        for li in range(num_layers - 1, -1, -1):
+            self._order += [((li, r), layers[li][r]) for r in LAYER_ROLES]
+        self._order += [(("g", r), globals_[r]) for r in emb]
+        self.offsets = {}
+        off = 0
+        seg_bounds = []
+        seg_start = 0
+        count = 0
+        seg_sizes = [len(seg0)] + [len(LAYER_ROLES)] * num_layers + [len(emb)]
+        seg_i = 0
+        for key, p in self._order:
+            self.offsets[key] = off
+            off += _round_up(p.numel(), _ALIGN)
+            count += 1
+            if count == seg_sizes[seg_i]:
+                seg_bounds.append((seg_start, off))
+                seg_start, count, seg_i = off, 0, seg_i + 1
+        self.total = off
+        self.segment_bounds = seg_bounds  # [(start, end)] in elements, index 0 = heads, 1..L = blocks L-1..0, L+1 = embedding
+        self.flat = None
+        self.flat_bf16 = None
+        self.flat_grad = None
+        self._ws = {}
+        self._sms = None
+        self.grad_segment_hook = None  # callable(segment_index) invoked as soon as a segment's gradients are complete
+
+    # ------------------------------------------------------------------ parameters --------------------------------
+    def _params_are_views(self):
+        if self.flat is None:
+            return False
+        base = self.flat.data_ptr()
+        for key, p in self._order:
+            if p.data_ptr() != base + 4 * self.offsets[key] or p.device != self.flat.device:
+                return False
+        return True
+
+    def bind(self, device):
+        """(Re)creates the flat buffers on `device` and re-points every parameter's storage at its slice."""
+        flat = torch.zeros(self.total, device=device, dtype=torch.float32)
+        for key, p in self._order:
+            o = self.offsets[key]
+            with torch.no_grad():
+                flat[o:o + p.numel()].view(p.shape).copy_(p.data.to(device=device, dtype=torch.float32))
+                p.data = flat[o:o + p.numel()].view(p.shape)
+        self.flat = flat
+        self.flat_bf16 = torch.zeros(self.total, device=device, dtype=torch.bfloat16)
+        self.flat_grad = torch.zeros(self.total, device=device, dtype=torch.float32)
+        for key, p in self._order:
+            p.grad = None
+        self._ws.clear()
+        self._sms = torch.cuda.get_device_properties(device).multi_processor_count
+
+    def ensure_bound(self):
+        p0 = self._order[0][1]
+        if not p0.is_cuda:
+            raise RuntimeError("vitb200 runs on a CUDA (sm_100a) device only; move the module to cuda first. "
+                               "There is no CPU fallback.")
+        if not self._params_are_views():
+            self.bind(p0.device)
+
+    def w(self, key):
+        """bf16 shadow of a parameter, as a 2-D matrix."""
+        p = self.layers[key[0]][key[1]] if key[0] != "g" else self.g[key[1]]
+        o = self.offsets[key]
+        v = self.flat_bf16[o:o + p.numel()]
+        return v.view(p.shape[0], -1) if p.dim() >= 2 else v
+
+    def f(self, key):
+        p = self.layers[key[0]][key[1]] if key[0] != "g" else self.g[key[1]]
+        o = self.offsets[key]
+        return self.flat[o:o + p.numel()]
+
+    def gview(self, key):
+        p = self.layers[key[0]][key[1]] if key[0] != "g" else self.g[key[1]]
+        o = self.offsets[key]
+        v = self.flat_grad[o:o + p.numel()]
+        return v.view(p.shape[0], -1) if p.dim() >= 2 else v
+
+    def refresh_bf16(self):
+        ops.cast_bf16(self.flat, self.flat_bf16)
+
+    def prepare_grads(self):
+        """Makes every p.grad a view of the flat gradient buffer (zeroing it if grads were None)."""
+        base = self.flat_grad.data_ptr()
+        need_zero = False
+        foreign = []
+        for key, p in self._order:
+            if p.grad is None:
+                need_zero = True
+            elif p.grad.data_ptr() != base + 4 * self.offsets[key]:
+                foreign.append((key, p, p.grad))
+        if need_zero or foreign:
+            all_none = all(p.grad is None for _, p in self._order)
+            if all_none:
+                self.flat_grad.zero_()
+            else:
+                # keep accumulated values of grads that already are views, zero the slices of the others
+                for key, p in self._order:
+                    if p.grad is None:
+                        o = self.offsets[key]
+                        self.flat_grad[o:o + p.numel()].zero_()
+            for key, p, gr in foreign:
+                o = self.offsets[key]
+                self.flat_grad[o:o + p.numel()].view(p.shape).copy_(gr)
+            for key, p in self._order:
+                o = self.offsets[key]
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    # ------------------------------------------------------------------ workspaces --------------------------------
+    def workspace(self, B, training):
+        key = (B, training)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev = self.flat.device
+        M, D, Fd, S, H = B * self.S, self.D, self.F, self.S, self.H
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *shape, dtype=bf: torch.empty(*shape, device=dev, dtype=dtype)
+        n_sets = self.L if training else 1
+        ws = {"B": B, "M": M}
+        ws["patches"] = torch.zeros(B, self.P, self.Kp_ld, device=dev, dtype=bf)
+        ws["x"] = [e(B, S, D, dtype=f32) for _ in range(self.L + 1 if training else 2)]
+        ws["layer"] = []
+        for _ in range(n_sets):
+            ws["layer"].append({
+                "h1": e(M, D), "qkv": e(M, 3 * D), "o": e(M, D), "lse": e(B, H, S, dtype=f32), "x1": e(B, S, D, dtype=f32),
+                "h2": e(M, D), "a": e(M, Fd) if training else None, "g": e(M, Fd),
+                "mean1": e(M, dtype=f32), "rstd1": e(M, dtype=f32), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32),
+            })
+        ws["y_all"] = None  # allocated on demand (forward_features)
+        ws["y_tok_f32"] = e(B * self.n_prefix, D, dtype=f32)
+        ws["y_tok"] = e(B * self.n_prefix, D)
+        ws["meanf"] = e(M, dtype=f32)
+        ws["rstdf"] = e(M, dtype=f32)
+        ws["logits"] = [torch.zeros(B, self.C_ld, device=dev, dtype=f32) for _ in range(2 if self.two_heads else 1)]
+        if training:
+            ws["d"] = e(B, S, D, dtype=f32)        # fp32 gradient of the residual stream (updated in place)
+            ws["d_bf16"] = e(M, D)                 # its bf16 copy (GEMM operand)
+            ws["dh"] = e(M, D)                     # gradient w.r.t. a LayerNorm output / attention output
+            ws["da"] = e(M, Fd)
+            ws["dqkv"] = e(M, 3 * D)
+            ws["delta"] = e(B, H, S, dtype=f32)
+            ws["dlogits"] = [torch.zeros(B, self.C_ld, device=dev, dtype=bf) for _ in range(2 if self.two_heads else 1)]
+            ws["dy_tok"] = e(B * self.n_prefix, D)
+            ws["possum"] = e(S, D, dtype=f32)
+            ws["dxp"] = e(B * self.P, D)
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward -----------------------------------
+    def _embed(self, ws, images):
+        B = ws["B"]
+        pat = ws["patches"]
+        if self.Kp_ld == self.Kp:
+            ops.patchify(images, pat, self.p)
+        else:  # never hit by the reference configs (3*p*p is a multiple of 8 for p % 4 == 0)
+            raise RuntimeError("patch matrix pitch must be a multiple of 8")
+        x0 = ws["x"][0]
+        pos = self.f(("g", "pos")).view(1, self.S, self.D)
+        ops.gemm(pat, self.w(("g", "conv_w")), x0, epilogue=ops.EPI_RESIDUAL, bias=self.f(("g", "conv_b")), aux=pos,
+                 c_row_offset=self.n_prefix, aux_broadcast=True)
+        ops.token_rows(x0, self.f(("g", "cls")), self.f(("g", "dist")) if self.n_prefix == 2 else None, pos.view(self.S, self.D),
+                       self.n_prefix)
+
+    def _block_fwd(self, li, x_in, x_out, buf, ws, training):
+        B, S, D, H = ws["B"], self.S, self.D, self.H
+        M = ws["M"]
+        xin2, x12, xout2 = x_in.view(M, D), buf["x1"].view(M, D), x_out.view(M, D)
+        ops.layernorm_fwd(xin2, self.f((li, "ln1_w")), self.f((li, "ln1_b")), self.eps, y_bf16=buf["h1"],
+                          mean=buf["mean1"] if training else None, rstd=buf["rstd1"] if training else None)
+        ops.gemm(buf["h1"], self.w((li, "qkv_w")), buf["qkv"], bias=self.f((li, "qkv_b")))
+        qkv = buf["qkv"]
+        ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"] if training else None, B=B, H=H, S=S,
+                          tok_stride=1, batch_stride=S)
+        ops.gemm(buf["o"], self.w((li, "proj_w")), x12, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "proj_b")), aux=xin2)
+        ops.layernorm_fwd(x12, self.f((li, "ln2_w")), self.f((li, "ln2_b")), self.eps, y_bf16=buf["h2"],
+                          mean=buf["mean2"] if training else None, rstd=buf["rstd2"] if training else None)
+        ops.gemm(buf["h2"], self.w((li, "fc1_w")), buf["a"] if training else None, C2=buf["g"], epilogue=ops.EPI_GELU,
+                 bias=self.f((li, "fc1_b")))
+        ops.gemm(buf["g"], self.w((li, "fc2_w")), xout2, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "fc2_b")), aux=x12)
+
+    def forward(self, images, *, training, want):
+        """want: 'logits' (head(s) on the prefix token rows) or 'features' ([B,S,D] fp32 after the final norm).
+        Returns (outputs, ws) where outputs is a list of fp32 tensors (views into the workspace)."""
+        self.ensure_bound()
+        if images.dtype != torch.float32 or not images.is_contiguous():
+            images = images.contiguous().float()
+        B = images.shape[0]
+        ws = self.workspace(B, training)
+        self.refresh_bf16()
+        self._embed(ws, images)
+        xs = ws["x"]
+        for li in range(self.L):
+            buf = ws["layer"][li if training else 0]
+            x_in = xs[li] if training else xs[li & 1]
+            x_out = xs[li + 1] if training else xs[(li + 1) & 1]
+            self._block_fwd(li, x_in, x_out, buf, ws, training)
+        x_last = xs[self.L] if training else xs[self.L & 1]
+        ws["x_last"] = x_last
+        S, D, M = self.S, self.D, ws["M"]
+        if want == "features":
+            if ws["y_all"] is None:
+                ws["y_all"] = torch.empty(B, S, D, device=x_last.device, dtype=torch.float32)
+            ops.layernorm_fwd(x_last.view(M, D), self.f(("g", "lnf_w")), self.f(("g", "lnf_b")), self.eps, y_f32=ws["y_all"].view(M, D),
+                              mean=ws["meanf"] if training else None, rstd=ws["rstdf"] if training else None)
+            return [ws["y_all"]], ws
+        # logits: the final LayerNorm is only needed on the prefix token rows (ViT.forward takes x[:, 0]: vanilla_vit.py:212)
+        outs = []
+        for t in range(self.n_prefix):
+            rows = x_last[:, t, :]                      # [B, D] view with pitch S*D
+            sl = slice(t * B, (t + 1) * B)
+            ops.layernorm_fwd(rows, self.f(("g", "lnf_w")), self.f(("g", "lnf_b")), self.eps, y_bf16=ws["y_tok"][sl],
+                              mean=ws["meanf"][sl] if training else None, rstd=ws["rstdf"][sl] if training else None)
+            hw, hb = ("head_w", "head_b") if t == 0 else ("headd_w", "headd_b")
+            logits = ws["logits"][t][:, :self.C]
+            ops.gemm(ws["y_tok"][sl], self.w(("g", hw)), logits, bias=self.f(("g", hb)))
+            outs.append(logits)
+        return outs, ws
+
+    # ------------------------------------------------------------------ backward ----------------------------------
+    def _wgrad(self, dy, x, key):
+        """dW[key] += dy^T x  with dy [M, N_out], x [M, K_in] (both token-major bf16)."""
+        dW = self.gview(key)
+        n_out, k_in = dW.shape
+        tiles = (-(-n_out // 128)) * (-(-k_in // 256))
+        split = pick_split_k(tiles, -(-dy.shape[0] // 64), self._sms)
+        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split)
+
+    def _seg_done(self, idx):
+        if self.grad_segment_hook is not None:
+            self.grad_segment_hook(idx)
+
+    def backward(self, ws, grads, *, want):
+        """grads: list matching forward outputs (fp32). Accumulates into the flat gradient buffer."""
+        self.prepare_grads()
+        B, S, D, M, L = ws["B"], self.S, self.D, ws["M"], self.L
+        d, d_bf, dh = ws["d"], ws["d_bf16"], ws["dh"]
+        d2 = d.view(M, D)
+        x_last = ws["x"][L]
+        last_b2 = (L - 1, "fc2_b")
+        if want == "features":
+            gy = grads[0]
+            if gy.dtype != torch.float32 or not gy.is_contiguous():
+                gy = gy.contiguous().float()
+            ops.layernorm_bwd(gy.view(M, D), x_last.view(M, D), ws["meanf"], ws["rstdf"], self.f(("g", "lnf_w")), dx=d2, dx_bf16=d_bf,
+                              dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")), dx_colsum=self.gview(last_b2))
+        else:
+            d.zero_()
+            d_bf.zero_()
+            for t in range(self.n_prefix):
+                if grads[t] is None:
+                    continue
+                sl = slice(t * B, (t + 1) * B)
+                hw, hb = ("head_w", "head_b") if t == 0 else ("headd_w", "headd_b")
+                dl = ws["dlogits"][t]
+                gl = grads[t]
+                # fp32 -> bf16 cast of the logits gradient into the padded operand buffer (padding stays zero)
+                tmp = ws["logits"][t]
+                tmp[:, :self.C].copy_(gl)
+                ops.cast_bf16(tmp.view(-1), dl.view(-1))
+                dlv = dl[:, :self.C]
+                ops.gemm(dlv, ws["y_tok"][sl], self.gview(("g", hw)), a_major=1, b_major=1, epilogue=ops.EPI_ACCUM)
+                ops.colsum_bf16(dl, self._padded_bias_grad(hb))
+                ops.gemm(dlv, self.w(("g", hw)), ws["dy_tok"][sl], b_major=1)
+                self._fold_bias_grad(hb)
+                xr = x_last[:, t, :]
+                d_rows = d[:, t, :]
+                db_rows = d_bf.view(B, S, D)[:, t, :]
+                ops.layernorm_bwd(ws["dy_tok"][sl], xr, ws["meanf"][sl], ws["rstdf"][sl], self.f(("g", "lnf_w")), dx=d_rows,
+                                  dx_bf16=db_rows, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
+                                  dx_colsum=self.gview(last_b2))
+        self._seg_done(0)
+        for li in range(L - 1, -1, -1):
+            buf = ws["layer"][li]
+            x_in = ws["x"][li].view(M, D)
+            # ---- MLP ----
+            self._wgrad(d_bf, buf["g"], (li, "fc2_w"))
+            ops.gemm(d_bf, self.w((li, "fc2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"])
+            self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"))
+            ops.colsum_bf16(ws["da"], self.gview((li, "fc1_b")))
+            ops.gemm(ws["da"], self.w((li, "fc1_w")), dh, b_major=1)
+            ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d2, dx=d2, dx_bf16=d_bf,
+                              dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")), dx_colsum=self.gview((li, "proj_b")))
+            # ---- attention ----
+            self._wgrad(d_bf, buf["o"], (li, "proj_w"))
+            ops.gemm(d_bf, self.w((li, "proj_w")), dh, b_major=1)
+            qkv, dqkv = buf["qkv"], ws["dqkv"]
+            ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"], dh, dqkv[:, :D], dqkv[:, D:2 * D],
+                              dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S)
+            self._wgrad(dqkv, buf["h1"], (li, "qkv_w"))
+            ops.colsum_bf16(dqkv, self.gview((li, "qkv_b")))
+            ops.gemm(dqkv, self.w((li, "qkv_w")), dh, b_major=1)
+            prev_b2 = self.gview((li - 1, "fc2_b")) if li > 0 else None
+            ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "ln1_w")), dres=d2, dx=d2, dx_bf16=d_bf if li > 0 else None,
+                              dgamma=self.gview((li, "ln1_w")), dbeta=self.gview((li, "ln1_b")), dx_colsum=prev_b2)
+            self._seg_done(L - li)
+        # ---- embedding ----
+        ops.embed_bwd(d, ws["possum"], ws["dxp"], self.gview(("g", "pos")).view(-1), self.gview(("g", "cls")).view(-1),
+                      self.gview(("g", "dist")).view(-1) if self.n_prefix == 2 else None, self.gview(("g", "conv_b")), self.n_prefix)
+        pat = ws["patches"].view(B * self.P, self.Kp_ld)[:, :self.Kp]
+        self._wgrad(ws["dxp"], pat, ("g", "conv_w"))
+        self._seg_done(L + 1)
+
+    # The head bias has num_classes entries, but the column-sum kernel works on the 8-padded logits-gradient
+    # buffer; sum into a padded scratch and fold the valid part into the gradient.
+    def _padded_bias_grad(self, hb):
+        if not hasattr(self, "_hb_scratch") or self._hb_scratch.device != self.flat.device:
+            self._hb_scratch = torch.zeros(self.C_ld, device=self.flat.device, dtype=torch.float32)
+        self._hb_scratch.zero_()
+        return self._hb_scratch
+
+    def _fold_bias_grad(self, hb):
+        self.gview(("g", hb)).add_(self._hb_scratch[:self.C])

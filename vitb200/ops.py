@@ -73,3 +73,94 @@ def gemm(A, B, C, *, a_major=0, b_major=0, epilogue=EPI_STORE, bias=None, aux=No
     d.debug_direct_store = 1 if direct else 0
     _lib.check(lib.vb_gemm_bf16(ctypes.byref(d), _stream()), "vb_gemm_bf16")
     return out
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, y_bf16=None, y_f32=None, mean=None, rstd=None):
+    """x: fp32 [rows, D] view (unit inner stride). Writes y_bf16 and/or y_f32 (same shape) and optional mean/rstd."""
+    lib = _lib.load()
+    rows, D = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    rc = lib.vb_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                              _p(y_bf16), y_bf16.stride(0) if y_bf16 is not None else 0,
+                              _p(y_f32), y_f32.stride(0) if y_f32 is not None else 0,
+                              _p(mean), _p(rstd), rows, D, float(eps), _stream())
+    _lib.check(rc, "vb_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, dx=None, dx_bf16=None, dgamma=None, dbeta=None, dx_colsum=None):
+    lib = _lib.load()
+    rows, D = x.shape
+    rc = lib.vb_layernorm_bwd(dy.data_ptr(), _dt(dy), dy.stride(0), x.data_ptr(), x.stride(0), mean.data_ptr(), rstd.data_ptr(),
+                              gamma.data_ptr(), _p(dres), dres.stride(0) if dres is not None else 0,
+                              _p(dx), dx.stride(0) if dx is not None else 0,
+                              _p(dx_bf16), dx_bf16.stride(0) if dx_bf16 is not None else 0,
+                              _p(dgamma), _p(dbeta), _p(dx_colsum), rows, D, _stream())
+    _lib.check(rc, "vb_layernorm_bwd")
+
+
+def _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, kpm):
+    d = _lib.VbAttnDesc()
+    d.B, d.H, d.S, d.head_dim = B, H, S, 64
+    d.tok_stride, d.batch_stride = tok_stride, batch_stride
+    d.q, d.k, d.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    d.ldq, d.ldk, d.ldv = q.stride(0), k.stride(0), v.stride(0)
+    d.o, d.ldo = o.data_ptr(), o.stride(0)
+    d.lse = _p(lse)
+    d.key_padding_mask = _p(kpm)
+    return d
+
+
+def attention_fwd(q, k, v, o, lse, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None):
+    """q/k/v/o: bf16 2-D views [tokens, H*64] (any row pitch); lse: fp32 [B,H,S] or None."""
+    lib = _lib.load()
+    d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask)
+    _lib.check(lib.vb_attention_fwd(ctypes.byref(d), _stream()), "vb_attention_fwd")
+
+
+def attention_bwd(q, k, v, o, lse, dout, dq, dk, dv, delta, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None):
+    lib = _lib.load()
+    d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask)
+    d.dout, d.lddo = dout.data_ptr(), dout.stride(0)
+    d.delta = delta.data_ptr()
+    d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    d.lddq, d.lddk, d.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    _lib.check(lib.vb_attention_bwd(ctypes.byref(d), _stream()), "vb_attention_bwd")
+
+
+def cast_bf16(src, dst):
+    lib = _lib.load()
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    _lib.check(lib.vb_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "vb_cast_f32_to_bf16")
+
+
+def patchify(images, out, patch):
+    lib = _lib.load()
+    B, C, H, W = images.shape
+    assert images.dtype == torch.float32 and images.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    _lib.check(lib.vb_patchify(images.data_ptr(), out.data_ptr(), B, C, H, W, patch, _stream()), "vb_patchify")
+
+
+def token_rows(x, tok0, tok1, pos, n_prefix):
+    lib = _lib.load()
+    B, S, D = x.shape
+    assert x.is_contiguous() and pos.is_contiguous()
+    _lib.check(lib.vb_token_rows(x.data_ptr(), tok0.data_ptr(), _p(tok1), pos.data_ptr(), B, S, D, n_prefix, _stream()), "vb_token_rows")
+
+
+def colsum_bf16(x, out_accum):
+    lib = _lib.load()
+    rows, cols = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and out_accum.dtype == torch.float32
+    _lib.check(lib.vb_colsum_bf16(x.data_ptr(), x.stride(0), rows, cols, out_accum.data_ptr(), _stream()), "vb_colsum_bf16")
+
+
+def embed_bwd(dx, possum, dx_patches, dpos, dtok0, dtok1, dbias, n_prefix):
+    lib = _lib.load()
+    B, S, D = dx.shape
+    assert dx.is_contiguous() and dx.dtype == torch.float32
+    _lib.check(lib.vb_embed_bwd(dx.data_ptr(), possum.data_ptr(), _p(dx_patches), _p(dpos), _p(dtok0), _p(dtok1), _p(dbias),
+                                B, S, D, n_prefix, _stream()), "vb_embed_bwd")
