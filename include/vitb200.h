@@ -148,6 +148,21 @@ VB_API int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols,
 VB_API int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_patches_bf16, float* dpos, float* dtok0, float* dtok1,
                         float* dbias, int32_t B, int32_t S, int32_t D, int32_t n_prefix, void* stream);
 
+/* ---- Training-step tail -------------------------------------------------------------------
+ * vb_cross_entropy: mean-reduction softmax cross-entropy (nn.CrossEntropyLoss at vanilla_vit.py:220,237) forward
+ *   and gradient in one pass: *loss_accum += weight * sum_b (lse(z_b) - z_b[y_b]); dz = grad_scale * weight *
+ *   (softmax(z) - onehot(y)) written as bf16 and/or fp32 (pass weight = 1/B for the mean).  labels are int64.
+ *   correct_accum (optional) counts argmax(z) == y.
+ * vb_adam_step: torch.optim.Adam semantics (vanilla_vit.py:221: lr 1e-4, betas .9/.999, eps 1e-8) over flat
+ *   fp32 buffers, n % 4 == 0; gradients are multiplied by grad_scale first; params_bf16 (optional) receives the
+ *   refreshed bf16 shadow used by the GEMMs. */
+VB_API int vb_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t C, float* loss_accum,
+                            float weight, void* dlogits_bf16, int64_t lddz, float* dlogits_f32, int64_t lddzf,
+                            float grad_scale, int32_t* correct_accum, void* stream);
+VB_API int vb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,10 @@ SIGNATURES = {
     "vb_colsum_bf16": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "vb_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                              c_int32, c_int32, c_void_p]),
+    "vb_cross_entropy": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_float, c_void_p, c_int64, c_void_p,
+                                 c_int64, c_float, c_void_p, c_void_p]),
+    "vb_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                             c_float, c_int32, c_float, c_void_p]),
     "vb_attention_fwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),
     "vb_attention_bwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),
     "vb_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
@@ -90,6 +94,10 @@ def load(build_if_missing=True):
 
 
 def check(rc, what):
+    if rc == 0:
+        from . import ops
+        ops.LAUNCHES["n"] += ops._KERNELS_PER_CALL.get(what, 1)
+        return
     if rc != 0:
         msg = load().vb_last_error()
         raise VbError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -71,10 +71,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 }
 
 // Backward. Persistent over rows: warp w of block b walks rows (b * wpb + w), += gridDim.x * wpb, ...; each lane
-// keeps per-column partial sums for dgamma / dbeta / colsum(dx) in registers, reduced across warps in smem and
-// across blocks with one atomicAdd per column per block.
+// keeps per-column partial sums for dgamma / dbeta / colsum(dx) in a warp-private smem slab (registers stay free
+// for two resident blocks per SM = more loads in flight), reduced across warps at the end and across blocks with
+// one atomicAdd per column per block.
 template <int NV, bool DY_BF16>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x,
                                                      long long ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ dres, long long lddres,
                                                      float* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dx_bf16,
@@ -85,16 +86,26 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    float4 ag[NV], ab[NV], ac[NV];
+    float* mine = red + warp * 3 * D;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 g[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + i * 32);
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + i * 32) * 4;
+        *reinterpret_cast<float4*>(mine + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(mine + D + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(mine + 2 * D + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
 
     for (int row = blockIdx.x * wpb + warp; row < rows; row += gridDim.x * wpb) {
         const float mu = mean[row], rs = rstd[row];
-        float4 xh[NV], dyv[NV];
+        float4 xh[NV], dyv[NV], rv[NV];
+        if (dres) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(dres + (long long)row * lddres) + lane + i * 32);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)row * ldx) + lane + i * 32);
@@ -110,38 +121,34 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const float a = dyv[i].x * g[i].x, b = dyv[i].y * g[i].y, c = dyv[i].z * g[i].z, d = dyv[i].w * g[i].w;
-            s1 += (a + b) + (c + d);
-            s2 += (a * xh[i].x + b * xh[i].y) + (c * xh[i].z + d * xh[i].w);
-            ag[i].x += dyv[i].x * xh[i].x; ag[i].y += dyv[i].y * xh[i].y; ag[i].z += dyv[i].z * xh[i].z; ag[i].w += dyv[i].w * xh[i].w;
-            ab[i].x += dyv[i].x; ab[i].y += dyv[i].y; ab[i].z += dyv[i].z; ab[i].w += dyv[i].w;
+            const float4 gi = __ldg(g4 + lane + i * 32);
+            const float a = dyv[i].x * gi.x, b = dyv[i].y * gi.y, cc = dyv[i].z * gi.z, d = dyv[i].w * gi.w;
+            s1 += (a + b) + (cc + d);
+            s2 += (a * xh[i].x + b * xh[i].y) + (cc * xh[i].z + d * xh[i].w);
+            const int c = (lane + i * 32) * 4;
+            float4 ag = *reinterpret_cast<float4*>(mine + c), ab = *reinterpret_cast<float4*>(mine + D + c);
+            ag.x += dyv[i].x * xh[i].x; ag.y += dyv[i].y * xh[i].y; ag.z += dyv[i].z * xh[i].z; ag.w += dyv[i].w * xh[i].w;
+            ab.x += dyv[i].x; ab.y += dyv[i].y; ab.z += dyv[i].z; ab.w += dyv[i].w;
+            *reinterpret_cast<float4*>(mine + c) = ag;
+            *reinterpret_cast<float4*>(mine + D + c) = ab;
         }
         const float m1 = warp_sum(s1) * (1.0f / D), m2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
+            const float4 gi = __ldg(g4 + lane + i * 32);
             float4 o;
-            o.x = rs * (dyv[i].x * g[i].x - m1 - xh[i].x * m2);
-            o.y = rs * (dyv[i].y * g[i].y - m1 - xh[i].y * m2);
-            o.z = rs * (dyv[i].z * g[i].z - m1 - xh[i].z * m2);
-            o.w = rs * (dyv[i].w * g[i].w - m1 - xh[i].w * m2);
-            if (dres) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(dres + (long long)row * lddres) + lane + i * 32);
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-            }
-            ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
+            o.x = rs * (dyv[i].x * gi.x - m1 - xh[i].x * m2) + rv[i].x;
+            o.y = rs * (dyv[i].y * gi.y - m1 - xh[i].y * m2) + rv[i].y;
+            o.z = rs * (dyv[i].z * gi.z - m1 - xh[i].z * m2) + rv[i].z;
+            o.w = rs * (dyv[i].w * gi.w - m1 - xh[i].w * m2) + rv[i].w;
+            float4 ac = *reinterpret_cast<float4*>(mine + 2 * D + (lane + i * 32) * 4);
+            ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+            *reinterpret_cast<float4*>(mine + 2 * D + (lane + i * 32) * 4) = ac;
             if (dx) *reinterpret_cast<float4*>(dx + (long long)row * lddx + (lane + i * 32) * 4) = o;
             if (dx_bf16) *reinterpret_cast<uint2*>(dx_bf16 + (long long)row * lddxb + (lane + i * 32) * 4) = pack4_bf16(o.x, o.y, o.z, o.w);
         }
     }
     // cross-warp reduction of the three column sums
-    float* mine = red + warp * 3 * D;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = (lane + i * 32) * 4;
-        *reinterpret_cast<float4*>(mine + c) = ag[i];
-        *reinterpret_cast<float4*>(mine + D + c) = ab[i];
-        *reinterpret_cast<float4*>(mine + 2 * D + c) = ac[i];
-    }
     __syncthreads();
     for (int idx = threadIdx.x; idx < 3 * D; idx += blockDim.x) {
         float s = 0.f;
@@ -171,7 +178,7 @@ static int ln_bwd_launch(const void* dy, long long lddy, const float* x, long lo
     const size_t smem = size_t(wpb) * 3 * NV * 128 * sizeof(float);
     auto kern = ln_bwd_kernel<NV, DYB>;
     static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
+    if (!configured) {
         VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }

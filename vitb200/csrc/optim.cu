@@ -1,0 +1,108 @@
+// Fused training-step tail: softmax cross-entropy forward+backward on the logits, and a flat multi-tensor Adam
+// that also refreshes the bf16 parameter shadow.  (reference: nn.CrossEntropyLoss + optim.Adam(lr=1e-4)
+// at vanilla_vit.py:220-221,237-239 / base.py:53-57.)
+#include "common.h"
+#include <cuda_bf16.h>
+
+namespace vb {
+
+// one warp per sample: loss_sum += w * (logsumexp(z) - z[y]); dz = scale * w * (softmax(z) - onehot(y)) as bf16 (+ fp32 optional)
+__global__ void ce_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels, int B, int C,
+                          float* __restrict__ loss_accum, float weight, __nv_bfloat16* __restrict__ dz_bf16, long long lddz,
+                          float* __restrict__ dz_f32, long long lddzf, float grad_scale, int* __restrict__ correct_accum) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const float* z = logits + (long long)row * ld;
+    float mx = -INFINITY;
+    int arg = 0;
+    for (int c = lane; c < C; c += 32) {
+        const float v = z[c];
+        if (v > mx) { mx = v; arg = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __expf(z[c] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int y = (int)labels[row];
+    const float lse = mx + __logf(s);
+    if (lane == 0) {
+        atomicAdd(loss_accum, weight * (lse - z[y]));
+        if (correct_accum && arg == y) atomicAdd(correct_accum, 1);
+    }
+    const float inv = 1.f / s;
+    for (int c = lane; c < C; c += 32) {
+        const float g = grad_scale * weight * (__expf(z[c] - mx) * inv - (c == y ? 1.f : 0.f));
+        if (dz_bf16) dz_bf16[(long long)row * lddz + c] = __float2bfloat16_rn(g);
+        if (dz_f32) dz_f32[(long long)row * lddzf + c] = g;
+    }
+}
+
+__global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                            uint2* __restrict__ p_bf16, long long n4, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt, float grad_scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
+        float* pp = reinterpret_cast<float*>(&pv);
+        float* gp = reinterpret_cast<float*>(&gv);
+        float* mp = reinterpret_cast<float*>(&mv);
+        float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float gr = gp[j] * grad_scale + wd * pp[j];
+            mp[j] = b1 * mp[j] + (1.f - b1) * gr;
+            vp[j] = b2 * vp[j] + (1.f - b2) * gr * gr;
+            const float denom = sqrtf(vp[j]) / bc2_sqrt + eps;
+            pp[j] -= (lr / bc1) * (mp[j] / denom);
+        }
+        p[i] = pv; m[i] = mv; v[i] = vv;
+        if (p_bf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(pp[0], pp[1]), hi = __floats2bfloat162_rn(pp[2], pp[3]);
+            uint2 r;
+            r.x = *reinterpret_cast<uint32_t*>(&lo);
+            r.y = *reinterpret_cast<uint32_t*>(&hi);
+            p_bf16[i] = r;
+        }
+    }
+}
+
+}  // namespace vb
+
+extern "C" int vb_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t C, float* loss_accum,
+                                float weight, void* dlogits_bf16, int64_t lddz, float* dlogits_f32, int64_t lddzf, float grad_scale,
+                                int32_t* correct_accum, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(logits && labels && loss_accum && B > 0 && C > 0, "cross_entropy: bad arguments");
+    ce_kernel<<<(B + 7) / 8, 256, 0, as_stream(stream)>>>(logits, ld, reinterpret_cast<const long long*>(labels), B, C, loss_accum, weight,
+                                                          reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), lddz, dlogits_f32, lddzf,
+                                                          grad_scale, correct_accum);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
+                            float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                            void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(params && grads && exp_avg && exp_avg_sq && n >= 0 && n % 4 == 0 && step >= 1, "adam_step: bad arguments");
+    if (n == 0) return VB_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    adam_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads),
+                                                           reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq),
+                                                           reinterpret_cast<uint2*>(params_bf16), n / 4, lr, beta1, beta2, eps,
+                                                           weight_decay, bc1, bc2s, grad_scale);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}

@@ -139,6 +139,10 @@ class VitEngine:
         return v.view(p.shape[0], -1) if p.dim() >= 2 else v
 
     def refresh_bf16(self):
+        # a fused optimizer step (trainer.FusedAdam) leaves the shadow up to date and sets bf16_fresh
+        if getattr(self, "bf16_fresh", False):
+            self.bf16_fresh = False
+            return
         ops.cast_bf16(self.flat, self.flat_bf16)
 
     def prepare_grads(self):
@@ -292,8 +296,9 @@ class VitEngine:
         if self.grad_segment_hook is not None:
             self.grad_segment_hook(idx)
 
-    def backward(self, ws, grads, *, want):
-        """grads: list matching forward outputs (fp32). Accumulates into the flat gradient buffer."""
+    def backward(self, ws, grads, *, want, dlogits_ready=False):
+        """grads: list matching forward outputs (fp32). Accumulates into the flat gradient buffer.
+        dlogits_ready: ws["dlogits"][t] already holds the bf16 logits gradients (fused cross-entropy path)."""
         self.prepare_grads()
         B, S, D, M, L = ws["B"], self.S, self.D, ws["M"], self.L
         d, d_bf, dh = ws["d"], ws["d_bf16"], ws["dh"]
@@ -310,16 +315,16 @@ class VitEngine:
             d.zero_()
             d_bf.zero_()
             for t in range(self.n_prefix):
-                if grads[t] is None:
+                if grads[t] is None and not dlogits_ready:
                     continue
                 sl = slice(t * B, (t + 1) * B)
                 hw, hb = ("head_w", "head_b") if t == 0 else ("headd_w", "headd_b")
                 dl = ws["dlogits"][t]
-                gl = grads[t]
-                # fp32 -> bf16 cast of the logits gradient into the padded operand buffer (padding stays zero)
-                tmp = ws["logits"][t]
-                tmp[:, :self.C].copy_(gl)
-                ops.cast_bf16(tmp.view(-1), dl.view(-1))
+                if not dlogits_ready:
+                    # fp32 -> bf16 cast of the logits gradient into the padded operand buffer (padding stays zero)
+                    tmp = ws["logits"][t]
+                    tmp[:, :self.C].copy_(grads[t])
+                    ops.cast_bf16(tmp.view(-1), dl.view(-1))
                 dlv = dl[:, :self.C]
                 ops.gemm(dlv, ws["y_tok"][sl], self.gview(("g", hw)), a_major=1, b_major=1, epilogue=ops.EPI_ACCUM)
                 ops.colsum_bf16(dl, self._padded_bias_grad(hb))

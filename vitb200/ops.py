@@ -9,6 +9,12 @@ import torch
 from . import _lib
 from ._lib import VbGemmDesc
 
+# kernels launched by libvitb200.so since import (bench.py reports the per-step delta as `gpu_launches`)
+LAUNCHES = {"n": 0}
+_KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 3,
+                     "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
+                     "vb_cross_entropy": 1, "vb_adam_step": 1}
+
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_ACCUM = range(7)
 BF16, F32 = 0, 1
 
@@ -164,3 +170,24 @@ def embed_bwd(dx, possum, dx_patches, dpos, dtok0, dtok1, dbias, n_prefix):
     assert dx.is_contiguous() and dx.dtype == torch.float32
     _lib.check(lib.vb_embed_bwd(dx.data_ptr(), possum.data_ptr(), _p(dx_patches), _p(dpos), _p(dtok0), _p(dtok1), _p(dbias),
                                 B, S, D, n_prefix, _stream()), "vb_embed_bwd")
+
+
+def cross_entropy(logits, labels, loss_accum, *, weight, dlogits_bf16=None, dlogits_f32=None, grad_scale=1.0, correct_accum=None):
+    """logits: fp32 [B, C] view; labels int64 [B]; loss_accum: fp32 scalar tensor that is ADDED to."""
+    lib = _lib.load()
+    B, C = logits.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and labels.dtype == torch.int64 and labels.is_contiguous()
+    rc = lib.vb_cross_entropy(logits.data_ptr(), logits.stride(0), labels.data_ptr(), B, C, loss_accum.data_ptr(), float(weight),
+                              _p(dlogits_bf16), dlogits_bf16.stride(0) if dlogits_bf16 is not None else 0,
+                              _p(dlogits_f32), dlogits_f32.stride(0) if dlogits_f32 is not None else 0,
+                              float(grad_scale), _p(correct_accum), _stream())
+    _lib.check(rc, "vb_cross_entropy")
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, params_bf16, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    lib = _lib.load()
+    n = params.numel()
+    rc = lib.vb_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), _p(params_bf16), n,
+                          float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
+                          _stream())
+    _lib.check(rc, "vb_adam_step")
