@@ -94,16 +94,20 @@ VB_API int vb_gemm_bf16(const VbGemmDesc* desc, void* stream);
 /* ---- LayerNorm over the last dimension of an fp32 [rows, dim] stream -------------------------------------
  * Replaces nn.LayerNorm(eps=1e-6) vanilla_vit.py:66,70,100 (ATen native_layer_norm) and the eps=1e-5 norms of
  * transformer.py:201-202.  dim must be a multiple of 128 and <= 1024.  Row pitches in elements.
- * fwd: y = (x - mean) * rstd * gamma + beta, written as bf16 (y_bf16) and/or fp32 (y_f32); mean/rstd optional.
- * bwd: dx = dres + LN'(dy); dgamma/dbeta/dx_colsum are ACCUMULATED (atomicAdd) and may be NULL;
- *      dx_colsum[c] += sum_rows dx[row, c] (bias gradient of the linear layer feeding this residual stream). */
+ * fwd: y = (x - mean) * rstd * gamma + beta, written as bf16 (y_bf16) and/or fp32 (y_f32); mean/rstd optional;
+ *      y2_bf16 (optional) = bf16(y + add) with add fp32 [rows, dim] (DETR q = k = src + pos, transformer.py:218).
+ * bwd: dx = dres + LN'(dy + dy_add); dy_add (optional) is bf16; dgamma/dbeta/dx_colsum are ACCUMULATED
+ *      (atomicAdd) and may be NULL; dx_colsum[c] += sum_rows dx[row, c] (bias gradient of the linear layer
+ *      feeding this residual stream). */
 VB_API int vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
                             int64_t ldy_bf16, float* y_f32, int64_t ldy_f32, float* mean, float* rstd, int32_t rows,
-                            int32_t dim, float eps, void* stream);
+                            int32_t dim, float eps, const float* add, int64_t ldadd, void* y2_bf16, int64_t ldy2,
+                            void* stream);
 VB_API int vb_layernorm_bwd(const void* dy, int32_t dy_dtype, int64_t lddy, const float* x, int64_t ldx,
                             const float* mean, const float* rstd, const float* gamma, const float* dres, int64_t lddres,
                             float* dx, int64_t lddx, void* dx_bf16, int64_t lddx_bf16, float* dgamma, float* dbeta,
-                            float* dx_colsum, int32_t rows, int32_t dim, void* stream);
+                            float* dx_colsum, int32_t rows, int32_t dim, const void* dy_add_bf16, int64_t lddy_add,
+                            void* stream);
 
 /* ---- Fused multi-head attention, head_dim 64 ---------------------------------------------------------------
  * Replaces F.scaled_dot_product_attention reached from nn.MultiheadAttention at vanilla_vit.py:77
@@ -140,6 +144,10 @@ VB_API int vb_attention_bwd(const VbAttnDesc* desc, void* stream);
  *              dx_patches_bf16 [B*(S-n_prefix), D] = compact bf16 copy (A operand of the conv_proj wgrad GEMM).
  *              possum_scratch is [S,D] fp32 scratch. */
 VB_API int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* out_bf16 = bf16(a + b), b may be NULL (DETR: bf16 operand copies of src and src + pos, transformer.py:218) */
+VB_API int vb_add_cast_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
+/* out = a + b_bf16 (+ c_bf16); accum += b_bf16 if accum != NULL (DETR backward: d_src and d_pos assembly) */
+VB_API int vb_add3(const float* a, const void* b_bf16, const void* c_bf16, float* out, float* accum, int64_t n, void* stream);
 VB_API int vb_patchify(const float* images, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
                        void* stream);
 VB_API int vb_token_rows(float* x, const float* tok0, const float* tok1, const float* pos, int32_t B, int32_t S, int32_t D,

@@ -1,0 +1,81 @@
+"""-m gpu parity tests for the DeiT-style distilled ViT and the DETR transformer encoder against the CPU oracle."""
+import pytest
+import torch
+
+from helpers import O, rel_l2
+
+LOGIT_TOL = 1.5e-2
+GRAD_TOL = 3e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("distill", ["hard", "soft"])
+def test_deit_distilled_training(distill):
+    from vitb200.deit import VisionTransformerDistilled
+    cfg = dict(img_size=32, patch_size=16, depth=3, num_heads=6, embed_dim=384, mlp_ratio=4, num_classes=100)
+    sd = O.seeded_state_dict(O.deit_param_shapes(**cfg), 21)
+    m = VisionTransformerDistilled(drop_rate=0.0, attn_drop_rate=0.0, **cfg)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.set_distilled_training(True)
+    B = 6
+    images, labels = O.seeded_images(B, 32, 22), O.seeded_labels(B, 100, 23)
+    teacher = torch.randn(B, 100, generator=torch.Generator().manual_seed(24))
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ro, rd = O.deit_forward(ref_sd, images, patch_size=16, depth=3, num_heads=6, training=True, distilled_training=True)
+    ref_loss = O.distillation_loss(ro, rd, labels, teacher, distill, 0.5, 5.0)
+    ref_loss.backward()
+    out, out_dist = m(images.cuda())
+    loss = O.distillation_loss(out, out_dist, labels.cuda(), teacher.cuda(), distill, 0.5, 5.0)  # same loss formula on the GPU tensors
+    loss.backward()
+    assert rel_l2(out, ro) < LOGIT_TOL and rel_l2(out_dist, rd) < LOGIT_TOL
+    assert abs(loss.item() - ref_loss.item()) < 1e-2 * max(1.0, abs(ref_loss.item()))
+    worst = max(((rel_l2(p.grad, ref_sd[n].grad), n) for n, p in m.named_parameters()))
+    assert worst[0] < GRAD_TOL, worst
+    # eval: single averaged output (deit.py:95-96)
+    m.eval()
+    with torch.no_grad():
+        avg = m(images.cuda())
+    ref_avg = O.deit_forward(sd, images, patch_size=16, depth=3, num_heads=6, training=False, distilled_training=True)
+    assert avg.shape == (B, 100) and rel_l2(avg, ref_avg) < LOGIT_TOL
+
+
+def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos):
+    from vitb200.detr import TransformerEncoder, TransformerEncoderLayer
+    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, False), 31)
+    enc = TransformerEncoder(TransformerEncoderLayer(d_model, nhead, ffn, 0.0, "relu", False), layers)
+    enc.load_state_dict(sd)
+    enc = enc.cuda().train()
+    g = torch.Generator().manual_seed(32)
+    src = torch.randn(S, N, d_model, generator=g)
+    pos = torch.randn(S, N, d_model, generator=g) if with_pos else None
+    kpm = None
+    if masked:
+        valid = torch.randint(S // 2, S + 1, (N,), generator=g)
+        kpm = torch.arange(S)[None, :] >= valid[:, None]
+    gout = torch.randn(S, N, d_model, generator=g)
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rsrc = src.clone().requires_grad_(True)
+    rpos = pos.clone().requires_grad_(True) if with_pos else None
+    ref = O.detr_encoder_forward(ref_sd, rsrc, nhead=nhead, num_layers=layers, src_key_padding_mask=kpm, pos=rpos)
+    ref.backward(gout)
+    csrc = src.cuda().requires_grad_(True)
+    cpos = pos.cuda().requires_grad_(True) if with_pos else None
+    out = enc(csrc, src_key_padding_mask=kpm.cuda() if masked else None, pos=cpos)
+    out.backward(gout.cuda())
+    assert rel_l2(out, ref) < LOGIT_TOL, rel_l2(out, ref)
+    assert rel_l2(csrc.grad, rsrc.grad) < GRAD_TOL
+    if with_pos:
+        assert rel_l2(cpos.grad, rpos.grad) < GRAD_TOL
+    worst = max(((rel_l2(p.grad, ref_sd[n].grad), n) for n, p in enc.named_parameters()))
+    assert worst[0] < GRAD_TOL, worst
+
+
+@pytest.mark.gpu
+def test_detr_encoder_masked_with_pos():
+    _detr_run(S=300, N=3, d_model=512, nhead=8, ffn=2048, layers=2, masked=True, with_pos=True)
+
+
+@pytest.mark.gpu
+def test_detr_encoder_short_no_mask_no_pos():
+    _detr_run(S=70, N=2, d_model=256, nhead=4, ffn=512, layers=3, masked=False, with_pos=False)

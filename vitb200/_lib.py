@@ -65,10 +65,12 @@ SIGNATURES = {
     "vb_attention_fwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),
     "vb_attention_bwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),
     "vb_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                 c_void_p, c_int32, c_int32, c_float, c_void_p]),
+                                 c_void_p, c_int32, c_int32, c_float, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "vb_layernorm_bwd": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32,
-                                 c_int32, c_void_p]),
+                                 c_int32, c_void_p, c_int64, c_void_p]),
+    "vb_add_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vb_add3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 _lib = None

@@ -418,6 +418,410 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
     store_rows(sQ, warp * 16, dq, p.scale, p.dq, p.lddq, p.tok_stride, row_base, q0, p.S, h);
 }
 
+
+// ==========================================================================================================
+// Short-sequence kernels (S <= 256: every ViT/DeiT config): one CTA per (batch, head), the whole head's Q, K, V
+// (and dO) resident in shared memory, exact 16-row / 8-column tile counts (no 64-granular padding waste), two CTAs
+// per SM so one head's loads overlap the other's math.  Warp w owns 16-row tiles w and w + NW.
+// ==========================================================================================================
+__device__ __forceinline__ void load_rows(uint32_t sbase, const __nv_bfloat16* g, long long ld, long long tok_stride, long long row_base,
+                                          int rows_pad, int S, int h, int nthreads) {
+    for (int c = threadIdx.x; c < rows_pad * 8; c += nthreads) {
+        const int row = c >> 3, ch = c & 7;
+        const bool valid = row < S;
+        const __nv_bfloat16* src = g + (row_base + (long long)(valid ? row : 0) * tok_stride) * ld + h * HD + ch * 8;
+        cp_async16(sbase + tile_off(row, ch), src, valid);
+    }
+}
+
+// 4x4 transpose inside each lane quad: in[j] = this lane's packed column pair of n-tile j; out[i] = column pair i of n-tile (lane & 3).
+__device__ __forceinline__ void quad_transpose(const uint32_t (&in)[4], uint32_t (&out)[4]) {
+    // two butterfly rounds (xor 1, xor 2) with selects only: no divergent branches around the shuffles
+    const bool odd = (threadIdx.x & 1) != 0, hi = (threadIdx.x & 2) != 0;
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? in[0] : in[1], 1);
+    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, odd ? in[2] : in[3], 1);
+    const uint32_t a0 = odd ? r0 : in[0], a1 = odd ? in[1] : r0, a2 = odd ? r1 : in[2], a3 = odd ? in[3] : r1;
+    const uint32_t u0 = __shfl_xor_sync(0xffffffffu, hi ? a0 : a2, 2);
+    const uint32_t u1 = __shfl_xor_sync(0xffffffffu, hi ? a1 : a3, 2);
+    out[0] = hi ? u0 : a0; out[1] = hi ? u1 : a1; out[2] = hi ? a2 : u0; out[3] = hi ? a3 : u1;
+}
+
+// Stores a warp's 16 x 64 accumulator tile (rows row0.., scaled) as bf16 with 16-byte row-contiguous stores.
+__device__ __forceinline__ void store_acc_tile(const float (&acc)[8][4], float mul, __nv_bfloat16* g, long long ld, long long tok_stride,
+                                               long long row_base, int row0, int S, int h) {
+    const int lane = threadIdx.x & 31;
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int s = row0 + r + half * 8;
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+            uint32_t in[4], out[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) in[j] = pack2(acc[grp * 4 + j][half * 2] * mul, acc[grp * 4 + j][half * 2 + 1] * mul);
+            quad_transpose(in, out);
+            if (s < S) {
+                uint4 w = make_uint4(out[0], out[1], out[2], out[3]);
+                *reinterpret_cast<uint4*>(g + (row_base + (long long)s * tok_stride) * ld + h * HD + (grp * 4 + c) * 8) = w;
+            }
+        }
+    }
+}
+
+// Per-lane shared-memory offsets of the ldmatrix patterns, computed once (all row bases used below are multiples
+// of 16, so the XOR swizzle term only depends on the lane and the 16-byte chunk index):
+//   a[i]: A-operand / transposed-B pattern, row (lane & 15), chunk 2*i + (lane >> 4)
+//   b[i]: non-transposed-B pattern, row (lane & 7) + 8 * (lane >> 4), chunk 2*i + ((lane >> 3) & 1)
+struct LaneOff {
+    uint32_t a[4], b[4];
+};
+__device__ __forceinline__ LaneOff make_lane_off() {
+    const int lane = threadIdx.x & 31;
+    LaneOff o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.a[i] = (lane & 15) * 128 + (((i * 2 + (lane >> 4)) ^ (lane & 7)) << 4);
+        o.b[i] = ((lane & 7) + ((lane >> 4) << 3)) * 128 + (((i * 2 + ((lane >> 3) & 1)) ^ (lane & 7)) << 4);
+    }
+    return o;
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// acc[NT][4] (16 x 8*NT) += A(16 rows starting at smem address sA0, k = 64) * T^T, T = rows of a smem matrix [n][64]
+// starting at address sT0.  A fragments are re-read from shared memory per k-step (keeps them out of the register budget).
+template <int NT, bool FULL>
+__device__ __forceinline__ void mma_rows_tileT_impl(float (&acc)[NT][4], uint32_t sA0, uint32_t sT0, int np_count, const LaneOff& off) {
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+        uint32_t a[4];
+        ldsm_x4(sA0 + off.a[kt], a);
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+            if (FULL || np < np_count) {
+                uint32_t b[4];
+                ldsm_x4(sT0 + np * 2048 + off.b[kt], b);
+                mma_bf16(acc[2 * np], a, b[0], b[1]);
+                mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+            }
+        }
+    }
+}
+// Full blocks take a branch-free path (no per-tile predicates => no convergence barriers around ldmatrix/mma).
+template <int NT>
+__device__ __forceinline__ void mma_rows_tileT(float (&acc)[NT][4], uint32_t sA0, uint32_t sT0, int np_count, const LaneOff& off) {
+    if (np_count == NT / 2) mma_rows_tileT_impl<NT, true>(acc, sA0, sT0, np_count, off);
+    else mma_rows_tileT_impl<NT, false>(acc, sA0, sT0, np_count, off);
+}
+
+// acc[8][4] (16 x 64) += P(16 x 16*KQ, accumulator-layout floats p[2*KQ][4]) * T, T = rows of a smem matrix [k][64] from sT0.
+template <int KQ, bool FULL>
+__device__ __forceinline__ void mma_p_rows_impl(float (&acc)[8][4], const float (&p)[2 * KQ][4], uint32_t sT0, int kq_count, const LaneOff& off) {
+#pragma unroll
+    for (int kq = 0; kq < KQ; ++kq) {
+        if (FULL || kq < kq_count) {
+            uint32_t a[4];
+            a[0] = pack2(p[2 * kq][0], p[2 * kq][1]);
+            a[1] = pack2(p[2 * kq][2], p[2 * kq][3]);
+            a[2] = pack2(p[2 * kq + 1][0], p[2 * kq + 1][1]);
+            a[3] = pack2(p[2 * kq + 1][2], p[2 * kq + 1][3]);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b[4];
+                ldsm_x4_t(sT0 + kq * 2048 + off.a[np], b);
+                mma_bf16(acc[2 * np], a, b[0], b[1]);
+                mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+            }
+        }
+    }
+}
+template <int KQ>
+__device__ __forceinline__ void mma_p_rows(float (&acc)[8][4], const float (&p)[2 * KQ][4], uint32_t sT0, int kq_count, const LaneOff& off) {
+    if (kq_count == KQ) mma_p_rows_impl<KQ, true>(acc, p, sT0, kq_count, off);
+    else mma_p_rows_impl<KQ, false>(acc, p, sT0, kq_count, off);
+}
+
+// One block of NP*16 keys of the online-softmax forward for a warp's 16 query rows (compile-time tile counts, so
+// the tail block of a sequence costs only its own tiles).  MASK: apply the key >= S / key-padding mask.
+template <int NP, bool MASK>
+__device__ __forceinline__ void fwd_block(float (&o)[8][4], float& m0, float& m1, float& l0, float& l1, uint32_t sA0, uint32_t sK0,
+                                          uint32_t sV0, int k0, int S, int b, const uint8_t* kpm, float c, const LaneOff& off) {
+    const int lane = threadIdx.x & 31;
+    float s[2 * NP][4];
+#pragma unroll
+    for (int i = 0; i < 2 * NP; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    mma_rows_tileT_impl<2 * NP, true>(s, sA0, sK0, NP, off);
+    if (MASK) {
+        const int kbase = k0 + (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 2 * NP; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = kbase + nt * 8 + e;
+                bool dead = key >= S;
+                if (!dead && kpm) dead = kpm[(long long)b * S + key] != 0;
+                if (dead) { s[nt][e] = -INFINITY; s[nt][e + 2] = -INFINITY; }
+            }
+        }
+    }
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NP; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float ms0 = (mx0 == -INFINITY) ? 0.f : mx0, ms1 = (mx1 == -INFINITY) ? 0.f : mx1;
+    const float a0 = ex2((m0 - ms0) * c), a1 = ex2((m1 - ms1) * c);
+    const float n0 = -ms0 * c, n1 = -ms1 * c;
+    m0 = mx0; m1 = mx1;
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NP; ++nt) {
+        s[nt][0] = ex2(fmaf(s[nt][0], c, n0)); s[nt][1] = ex2(fmaf(s[nt][1], c, n0));
+        s[nt][2] = ex2(fmaf(s[nt][2], c, n1)); s[nt][3] = ex2(fmaf(s[nt][3], c, n1));
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= a0; o[nt][1] *= a0; o[nt][2] *= a1; o[nt][3] *= a1; }
+    mma_p_rows_impl<NP, true>(o, s, sV0, NP, off);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 2) attn_fwd_short_kernel(const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int S = p.S;
+    const int n_mt = (S + 15) >> 4, rows_pad = n_mt * 16;
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + rows_pad * 128;
+    uint8_t* sV = sK + rows_pad * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const long long row_base = (long long)b * p.batch_stride;
+    load_rows(smem_addr(sQ), p.q, p.ldq, p.tok_stride, row_base, rows_pad, S, h, NW * 32);
+    load_rows(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, rows_pad, S, h, NW * 32);
+    load_rows(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, rows_pad, S, h, NW * 32);
+    cp_async_commit();
+    const LaneOff off = make_lane_off();
+    cp_async_wait<0>();
+    __syncthreads();
+    const uint32_t aQ = smem_addr(sQ), aK = smem_addr(sK), aV = smem_addr(sV);
+    const int n_nt = (S + 7) >> 3;  // valid 8-key tiles
+    const float c = p.scale_log2;
+
+    for (int mt = warp; mt < n_mt; mt += NW) {
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max in raw-score units
+        const int n_full = p.kpm ? 0 : (S >> 6);                     // 64-key blocks that need no masking at all
+        int k0 = 0;
+        for (; k0 < n_full * 64; k0 += 64)
+            fwd_block<4, false>(o, m0, m1, l0, l1, aQ + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, c, off);
+        for (; k0 < S; k0 += 64) {                                   // tail (or key-padding-masked) blocks
+            const int pairs = (min(8, n_nt - (k0 >> 3)) + 1) >> 1;
+            if (pairs == 4) fwd_block<4, true>(o, m0, m1, l0, l1, aQ + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, c, off);
+            else if (pairs == 3) fwd_block<3, true>(o, m0, m1, l0, l1, aQ + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, c, off);
+            else if (pairs == 2) fwd_block<2, true>(o, m0, m1, l0, l1, aQ + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, c, off);
+            else fwd_block<1, true>(o, m0, m1, l0, l1, aQ + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, c, off);
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= inv0; o[nt][1] *= inv0; o[nt][2] *= inv1; o[nt][3] *= inv1; }
+        if (p.lse && (lane & 3) == 0) {
+            const int r0 = mt * 16 + (lane >> 2);
+            float* lse = p.lse + ((long long)b * p.H + h) * S;
+            if (r0 < S) lse[r0] = m0 * c + log2f(l0);
+            if (r0 + 8 < S) lse[r0 + 8] = m1 * c + log2f(l1);
+        }
+        store_acc_tile(o, 1.0f, p.o, p.ldo, p.tok_stride, row_base, mt * 16, S, h);
+    }
+}
+
+// Phase-A block: 16 keys (this warp) x NP*16 queries.  lse = +inf beyond S makes P vanish there; kill0/1 zero dead keys.
+template <int NP>
+__device__ __forceinline__ void bwd_a_block(float (&dk)[8][4], float (&dv)[8][4], uint32_t sK0, uint32_t sV0, uint32_t sQ0, uint32_t sdO0,
+                                            const float* lse_q, const float* delta_q, float kill0, float kill1, float c, const LaneOff& off) {
+    const int lane = threadIdx.x & 31;
+    float st[2 * NP][4], dpt[2 * NP][4];
+#pragma unroll
+    for (int i = 0; i < 2 * NP; ++i) { st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f; dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f; }
+    mma_rows_tileT_impl<2 * NP, true>(st, sK0, sQ0, NP, off);     // S^T[key, q]
+    mma_rows_tileT_impl<2 * NP, true>(dpt, sV0, sdO0, NP, off);   // dP^T[key, q]
+    const float* lq = lse_q + (lane & 3) * 2;
+    const float* dq_ = delta_q + (lane & 3) * 2;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NP; ++nt) {
+        const float2 l2 = *reinterpret_cast<const float2*>(lq + nt * 8);
+        const float2 d2 = *reinterpret_cast<const float2*>(dq_ + nt * 8);
+        const float p00 = ex2(fmaf(st[nt][0], c, -l2.x)) * kill0, p01 = ex2(fmaf(st[nt][1], c, -l2.y)) * kill0;
+        const float p10 = ex2(fmaf(st[nt][2], c, -l2.x)) * kill1, p11 = ex2(fmaf(st[nt][3], c, -l2.y)) * kill1;
+        st[nt][0] = p00; st[nt][1] = p01; st[nt][2] = p10; st[nt][3] = p11;
+        dpt[nt][0] = p00 * (dpt[nt][0] - d2.x); dpt[nt][1] = p01 * (dpt[nt][1] - d2.y);
+        dpt[nt][2] = p10 * (dpt[nt][2] - d2.x); dpt[nt][3] = p11 * (dpt[nt][3] - d2.y);
+    }
+    mma_p_rows_impl<NP, true>(dv, st, sdO0, NP, off);   // dV += P^T dO
+    mma_p_rows_impl<NP, true>(dk, dpt, sQ0, NP, off);   // dK += dS^T Q
+}
+
+// Phase-B block: 16 queries (this warp) x NP*16 keys.
+template <int NP, bool MASK>
+__device__ __forceinline__ void bwd_b_block(float (&dq)[8][4], uint32_t sQ0, uint32_t sdO0, uint32_t sK0, uint32_t sV0, int k0, int S, int b,
+                                            const uint8_t* kpm, float nl0, float nl1, float dl0, float dl1, float c, const LaneOff& off) {
+    const int lane = threadIdx.x & 31;
+    float s[2 * NP][4], dp[2 * NP][4];
+#pragma unroll
+    for (int i = 0; i < 2 * NP; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+    mma_rows_tileT_impl<2 * NP, true>(s, sQ0, sK0, NP, off);      // S[q, key]
+    mma_rows_tileT_impl<2 * NP, true>(dp, sdO0, sV0, NP, off);    // dP[q, key]
+    if (MASK) {
+        const int kbase = k0 + (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 2 * NP; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = kbase + nt * 8 + e;
+                bool dead = key >= S;
+                if (!dead && kpm) dead = kpm[(long long)b * S + key] != 0;
+                if (dead) { s[nt][e] = -INFINITY; s[nt][e + 2] = -INFINITY; }
+            }
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2 * NP; ++nt) {
+        const float p00 = ex2(fmaf(s[nt][0], c, nl0)), p01 = ex2(fmaf(s[nt][1], c, nl0));
+        const float p10 = ex2(fmaf(s[nt][2], c, nl1)), p11 = ex2(fmaf(s[nt][3], c, nl1));
+        dp[nt][0] = p00 * (dp[nt][0] - dl0); dp[nt][1] = p01 * (dp[nt][1] - dl0);
+        dp[nt][2] = p10 * (dp[nt][2] - dl1); dp[nt][3] = p11 * (dp[nt][3] - dl1);
+    }
+    mma_p_rows_impl<NP, true>(dq, dp, sK0, NP, off);   // dQ += dS K
+}
+
+// Backward, whole head per CTA.  Phase A: warp owns 16 keys -> dK, dV (loops over 32-query blocks).
+// Phase B: warp owns 16 queries -> dQ (loops over 32-key blocks).  delta = rowsum(dO o O) is computed in-kernel.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 2) attn_bwd_short_kernel(const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int S = p.S;
+    const int n_mt = (S + 15) >> 4, rows_pad = n_mt * 16;
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + rows_pad * 128;
+    uint8_t* sV = sK + rows_pad * 128;
+    uint8_t* sdO = sV + rows_pad * 128;
+    float* sLse = reinterpret_cast<float*>(sdO + rows_pad * 128);   // [rows_pad + 32], entries >= S hold +inf (=> P = 0)
+    float* sDelta = sLse + rows_pad + 32;                           // [rows_pad + 32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const long long row_base = (long long)b * p.batch_stride;
+    load_rows(smem_addr(sQ), p.q, p.ldq, p.tok_stride, row_base, rows_pad, S, h, NW * 32);
+    load_rows(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, rows_pad, S, h, NW * 32);
+    load_rows(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, rows_pad, S, h, NW * 32);
+    load_rows(smem_addr(sdO), p.dout, p.lddo, p.tok_stride, row_base, rows_pad, S, h, NW * 32);
+    cp_async_commit();
+    for (int r = threadIdx.x; r < rows_pad + 32; r += NW * 32) sLse[r] = r < S ? p.lse[((long long)b * p.H + h) * S + r] : INFINITY;
+    const LaneOff off = make_lane_off();
+    cp_async_wait<0>();
+    __syncthreads();
+    // delta[r] = sum_d dO[r,d] * O[r,d]  (dO from smem, O from global)
+    for (int r = threadIdx.x; r < rows_pad + 32; r += NW * 32) {
+        float acc = 0.f;
+        if (r < S) {
+            const __nv_bfloat16* orow = p.o + (row_base + (long long)r * p.tok_stride) * p.ldo + h * HD;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint4 ov = *reinterpret_cast<const uint4*>(orow + ch * 8);
+                const uint4 dv = *reinterpret_cast<const uint4*>(sdO + tile_off(r, ch));
+                const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    acc += __uint_as_float(oo[j] << 16) * __uint_as_float(dd[j] << 16) +
+                           __uint_as_float(oo[j] & 0xFFFF0000u) * __uint_as_float(dd[j] & 0xFFFF0000u);
+            }
+        }
+        sDelta[r] = acc;
+    }
+    __syncthreads();
+    const uint32_t aQ = smem_addr(sQ), aK = smem_addr(sK), aV = smem_addr(sV), adO = smem_addr(sdO);
+    const int n_nt = (S + 7) >> 3;
+    const float c = p.scale_log2;
+
+    // ---------------- phase A: dK, dV ----------------
+    for (int mt = warp; mt < n_mt; mt += NW) {
+        float dk[8][4], dv[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+        const int key0 = mt * 16 + (lane >> 2), key1 = key0 + 8;
+        bool dead0 = key0 >= S, dead1 = key1 >= S;
+        if (p.kpm) {
+            if (!dead0) dead0 = p.kpm[(long long)b * S + key0] != 0;
+            if (!dead1) dead1 = p.kpm[(long long)b * S + key1] != 0;
+        }
+        const float kill0 = dead0 ? 0.f : 1.f, kill1 = dead1 ? 0.f : 1.f;
+        for (int q0 = 0; q0 < S; q0 += 32) {
+            const int pairs = (min(4, n_nt - (q0 >> 3)) + 1) >> 1;
+            if (pairs == 2) bwd_a_block<2>(dk, dv, aK + mt * 2048, aV + mt * 2048, aQ + q0 * 128, adO + q0 * 128, sLse + q0, sDelta + q0, kill0, kill1, c, off);
+            else bwd_a_block<1>(dk, dv, aK + mt * 2048, aV + mt * 2048, aQ + q0 * 128, adO + q0 * 128, sLse + q0, sDelta + q0, kill0, kill1, c, off);
+        }
+        store_acc_tile(dk, p.scale, p.dk, p.lddk, p.tok_stride, row_base, mt * 16, S, h);
+        store_acc_tile(dv, 1.0f, p.dv, p.lddv, p.tok_stride, row_base, mt * 16, S, h);
+    }
+    // ---------------- phase B: dQ ----------------
+    for (int mt = warp; mt < n_mt; mt += NW) {
+        float dq[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+        const int r0 = mt * 16 + (lane >> 2), r1 = r0 + 8;
+        // rows >= S carry lse = +inf => P = 0 => dQ = 0 (and are never stored)
+        const float nl0 = -sLse[r0], nl1 = -sLse[r1], dl0 = sDelta[r0], dl1 = sDelta[r1];
+        const int n_full = p.kpm ? 0 : (S >> 5);
+        int k0 = 0;
+        for (; k0 < n_full * 32; k0 += 32)
+            bwd_b_block<2, false>(dq, aQ + mt * 2048, adO + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, nl0, nl1, dl0, dl1, c, off);
+        for (; k0 < S; k0 += 32) {
+            const int pairs = (min(4, n_nt - (k0 >> 3)) + 1) >> 1;
+            if (pairs == 2) bwd_b_block<2, true>(dq, aQ + mt * 2048, adO + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, nl0, nl1, dl0, dl1, c, off);
+            else bwd_b_block<1, true>(dq, aQ + mt * 2048, adO + mt * 2048, aK + k0 * 128, aV + k0 * 128, k0, S, b, p.kpm, nl0, nl1, dl0, dl1, c, off);
+        }
+        store_acc_tile(dq, p.scale, p.dq, p.lddq, p.tok_stride, row_base, mt * 16, S, h);
+    }
+}
+
+template <int NW>
+static int launch_short_fwd(const AttnParams& p, cudaStream_t st) {
+    const int rows_pad = ((p.S + 15) / 16) * 16;
+    const int smem = 3 * rows_pad * 128;
+    auto kern = attn_fwd_short_kernel<NW>;
+    static int configured = 0;
+    if (configured < smem) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    kern<<<dim3(p.H, p.B), NW * 32, smem, st>>>(p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+template <int NW>
+static int launch_short_bwd(const AttnParams& p, cudaStream_t st) {
+    const int rows_pad = ((p.S + 15) / 16) * 16;
+    const int smem = 4 * rows_pad * 128 + 2 * (rows_pad + 32) * (int)sizeof(float);
+    auto kern = attn_bwd_short_kernel<NW>;
+    static int configured = 0;
+    if (configured < smem) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    kern<<<dim3(p.H, p.B), NW * 32, smem, st>>>(p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
 static int check_common(const VbAttnDesc* d) {
     VB_REQUIRE(d != nullptr, "attention: null descriptor");
     VB_REQUIRE(d->head_dim == 64, "attention: head_dim %d unsupported (every reference config has 64)", d->head_dim);
@@ -452,6 +856,14 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (int rc = check_arch()) return rc;
     if (int rc = check_common(d)) return rc;
     const AttnParams p = to_params(d);
+    if (d->S <= 256) {
+        const int n_mt = (d->S + 15) / 16;
+        cudaStream_t st = as_stream(stream);
+        if (n_mt <= 6) return launch_short_fwd<3>(p, st);
+        if (n_mt <= 10) return launch_short_fwd<5>(p, st);
+        if (n_mt <= 14) return launch_short_fwd<7>(p, st);
+        return launch_short_fwd<8>(p, st);
+    }
     const int smem = 5 * TILE_BYTES;
     static bool configured = false;
     if (!configured) {
@@ -472,6 +884,13 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     VB_REQUIRE(d->lddo % 8 == 0 && d->lddq % 8 == 0 && d->lddk % 8 == 0 && d->lddv % 8 == 0, "attention_bwd: row pitches must be multiples of 8");
     const AttnParams p = to_params(d);
     cudaStream_t st = as_stream(stream);
+    if (d->S <= 256) {
+        const int n_mt = (d->S + 15) / 16;
+        if (n_mt <= 6) return launch_short_bwd<3>(p, st);
+        if (n_mt <= 10) return launch_short_bwd<5>(p, st);
+        if (n_mt <= 14) return launch_short_bwd<7>(p, st);
+        return launch_short_bwd<8>(p, st);
+    }
     const int smem = 6 * TILE_BYTES + 4 * TILE * (int)sizeof(float);
     static bool configured = false;
     if (!configured) {

@@ -124,6 +124,33 @@ __global__ void embed_bwd_finalize_kernel(const float* __restrict__ possum, floa
     if (dbias) dbias[c] += bsum;
 }
 
+// ---- out_bf16 = bf16(a + b) (b optional): DETR q = k = src + pos operand and the bf16 copy of src -------------
+__global__ void add_cast_kernel(const float4* __restrict__ a, const float4* __restrict__ b, uint2* __restrict__ out, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = __ldg(a + i);
+        if (b) { const float4 w = __ldg(b + i); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+        out[i] = pack4(v.x, v.y, v.z, v.w);
+    }
+}
+// ---- out_f32 = a_f32 + b_bf16 (+ c_bf16);  accum_f32 += b_bf16 (optional): DETR d_src / d_pos assembly ---------
+__global__ void add3_kernel(const float4* __restrict__ a, const uint2* __restrict__ b, const uint2* __restrict__ c, float4* __restrict__ out,
+                            float4* __restrict__ accum, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = __ldg(a + i);
+        const uint2 w = __ldg(b + i);
+        const float4 bv = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                                      __uint_as_float(w.y & 0xFFFF0000u));
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        if (c) {
+            const uint2 u = __ldg(c + i);
+            v.x += __uint_as_float(u.x << 16); v.y += __uint_as_float(u.x & 0xFFFF0000u);
+            v.z += __uint_as_float(u.y << 16); v.w += __uint_as_float(u.y & 0xFFFF0000u);
+        }
+        out[i] = v;
+        if (accum) { float4 t = accum[i]; t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w; accum[i] = t; }
+    }
+}
+
 static int grid_for(long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = (long long)num_sms() * 8;
@@ -204,6 +231,29 @@ extern "C" int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_pat
                                                                 D, n_prefix, bpc);
     VB_CUDA_CHECK(cudaGetLastError());
     embed_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, st>>>(possum_scratch, dpos, dtok0, dtok1, dbias, S, D, n_prefix);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_add_cast_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(a && out_bf16 && n >= 0 && n % 4 == 0, "add_cast: n=%lld must be a multiple of 4", (long long)n);
+    if (n == 0) return VB_OK;
+    add_cast_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                                         reinterpret_cast<uint2*>(out_bf16), n / 4);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_add3(const float* a, const void* b_bf16, const void* c_bf16, float* out, float* accum, int64_t n, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(a && b_bf16 && out && n >= 0 && n % 4 == 0, "add3: n=%lld must be a multiple of 4", (long long)n);
+    if (n == 0) return VB_OK;
+    add3_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const uint2*>(b_bf16),
+                                                                     reinterpret_cast<const uint2*>(c_bf16), reinterpret_cast<float4*>(out),
+                                                                     reinterpret_cast<float4*>(accum), n / 4);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

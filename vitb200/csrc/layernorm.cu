@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_bf16,
                                                      long long ldyb, float* __restrict__ y_f32, long long ldyf,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
-                                                     float eps) {
+                                                     float eps, const float* __restrict__ add, long long ldadd,
+                                                     __nv_bfloat16* __restrict__ y2_bf16, long long ldy2) {
     constexpr int D = NV * 128;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -67,6 +68,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
         if (y_bf16) *reinterpret_cast<uint2*>(y_bf16 + (long long)row * ldyb + (lane + i * 32) * 4) = pack4_bf16(o.x, o.y, o.z, o.w);
         if (y_f32) *reinterpret_cast<float4*>(y_f32 + (long long)row * ldyf + (lane + i * 32) * 4) = o;
+        if (y2_bf16) {  // second bf16 output y + add (DETR: q = k = src + pos, transformer.py:218)
+            const float4 a = __ldg(reinterpret_cast<const float4*>(add + (long long)row * ldadd) + lane + i * 32);
+            *reinterpret_cast<uint2*>(y2_bf16 + (long long)row * ldy2 + (lane + i * 32) * 4) = pack4_bf16(o.x + a.x, o.y + a.y, o.z + a.z, o.w + a.w);
+        }
     }
 }
 
@@ -80,7 +85,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const void* __restrict__
                                                      const float* __restrict__ gamma, const float* __restrict__ dres, long long lddres,
                                                      float* __restrict__ dx, long long lddx, __nv_bfloat16* __restrict__ dx_bf16,
                                                      long long lddxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     float* __restrict__ dx_colsum, int rows) {
+                                                     float* __restrict__ dx_colsum, int rows,
+                                                     const __nv_bfloat16* __restrict__ dy_add, long long lddya) {
     constexpr int D = NV * 128;
     extern __shared__ float red[];  // [warps][3][D]
     const int lane = threadIdx.x & 31;
@@ -116,6 +122,11 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const void* __restrict__
                                      __uint_as_float(w.y & 0xFFFF0000u));
             } else {
                 dyv[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (long long)row * lddy) + lane + i * 32);
+            }
+            if (dy_add) {  // post-norm blocks: the gradient reaching a LayerNorm output is a sum of two streams
+                const uint2 w = __ldg(reinterpret_cast<const uint2*>(dy_add + (long long)row * lddya) + lane + i * 32);
+                dyv[i].x += __uint_as_float(w.x << 16); dyv[i].y += __uint_as_float(w.x & 0xFFFF0000u);
+                dyv[i].z += __uint_as_float(w.y << 16); dyv[i].w += __uint_as_float(w.y & 0xFFFF0000u);
             }
         }
         float s1 = 0.f, s2 = 0.f;
@@ -162,10 +173,12 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const void* __restrict__
 
 template <int NV>
 static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, const float* beta, void* y_bf16, long long ldyb,
-                         float* y_f32, long long ldyf, float* mean, float* rstd, int rows, float eps, cudaStream_t st) {
+                         float* y_f32, long long ldyf, float* mean, float* rstd, int rows, float eps, const float* add,
+                         long long ldadd, void* y2, long long ldy2, cudaStream_t st) {
     const int wpb = 8;
     ln_fwd_kernel<NV><<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, ldx, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), ldyb,
-                                                                  y_f32, ldyf, mean, rstd, rows, eps);
+                                                                  y_f32, ldyf, mean, rstd, rows, eps, add, ldadd,
+                                                                  reinterpret_cast<__nv_bfloat16*>(y2), ldy2);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }
@@ -173,7 +186,8 @@ static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, cons
 template <int NV, bool DYB>
 static int ln_bwd_launch(const void* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd,
                          const float* gamma, const float* dres, long long lddres, float* dx, long long lddx, void* dxb,
-                         long long lddxb, float* dgamma, float* dbeta, float* colsum, int rows, cudaStream_t st) {
+                         long long lddxb, float* dgamma, float* dbeta, float* colsum, int rows, const void* dy_add, long long lddya,
+                         cudaStream_t st) {
     const int wpb = 8;
     const size_t smem = size_t(wpb) * 3 * NV * 128 * sizeof(float);
     auto kern = ln_bwd_kernel<NV, DYB>;
@@ -187,7 +201,8 @@ static int ln_bwd_launch(const void* dy, long long lddy, const float* x, long lo
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     kern<<<grid, wpb * 32, smem, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx,
-                                       reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta, colsum, rows);
+                                       reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta, colsum, rows,
+                                       reinterpret_cast<const __nv_bfloat16*>(dy_add), lddya);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }
@@ -196,16 +211,17 @@ static int ln_bwd_launch(const void* dy, long long lddy, const float* x, long lo
 
 extern "C" int vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16, int64_t ldy_bf16,
                                 float* y_f32, int64_t ldy_f32, float* mean, float* rstd, int32_t rows, int32_t dim, float eps,
-                                void* stream) {
+                                const float* add, int64_t ldadd, void* y2_bf16, int64_t ldy2, void* stream) {
     using namespace vb;
     if (int rc = check_arch()) return rc;
     VB_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
+    VB_REQUIRE((y2_bf16 == nullptr) || (add != nullptr && ldadd % 4 == 0 && ldy2 % 4 == 0), "layernorm_fwd: y2 needs `add` and 4-aligned pitches");
     VB_REQUIRE(rows >= 0 && dim > 0 && dim % 128 == 0 && dim <= 1024, "layernorm_fwd: dim %d must be a multiple of 128 and <= 1024", dim);
     VB_REQUIRE(ldx % 4 == 0 && ldy_bf16 % 4 == 0 && ldy_f32 % 4 == 0, "layernorm_fwd: row pitches must be multiples of 4 elements");
     if (rows == 0) return VB_OK;
     cudaStream_t st = as_stream(stream);
     switch (dim / 128) {
-#define VB_CASE(NV) case NV: return ln_fwd_launch<NV>(x, ldx, gamma, beta, y_bf16, ldy_bf16, y_f32, ldy_f32, mean, rstd, rows, eps, st);
+#define VB_CASE(NV) case NV: return ln_fwd_launch<NV>(x, ldx, gamma, beta, y_bf16, ldy_bf16, y_f32, ldy_f32, mean, rstd, rows, eps, add, ldadd, y2_bf16, ldy2, st);
         VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8)
 #undef VB_CASE
     }
@@ -215,13 +231,14 @@ extern "C" int vb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma,
 extern "C" int vb_layernorm_bwd(const void* dy, int32_t dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* mean,
                                 const float* rstd, const float* gamma, const float* dres, int64_t lddres, float* dx, int64_t lddx,
                                 void* dx_bf16, int64_t lddx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int32_t rows,
-                                int32_t dim, void* stream) {
+                                int32_t dim, const void* dy_add_bf16, int64_t lddy_add, void* stream) {
     using namespace vb;
     if (int rc = check_arch()) return rc;
     VB_REQUIRE(dy && x && mean && rstd && gamma && (dx || dx_bf16), "layernorm_bwd: null pointer");
     VB_REQUIRE(rows >= 0 && dim > 0 && dim % 128 == 0 && dim <= 1024, "layernorm_bwd: dim %d must be a multiple of 128 and <= 1024", dim);
     VB_REQUIRE(dy_dtype == VB_BF16 || dy_dtype == VB_F32, "layernorm_bwd: bad dy dtype");
-    VB_REQUIRE(lddy % 4 == 0 && ldx % 4 == 0 && lddres % 4 == 0 && lddx % 4 == 0 && lddx_bf16 % 4 == 0, "layernorm_bwd: pitches must be multiples of 4");
+    VB_REQUIRE(lddy % 4 == 0 && ldx % 4 == 0 && lddres % 4 == 0 && lddx % 4 == 0 && lddx_bf16 % 4 == 0 && lddy_add % 4 == 0,
+               "layernorm_bwd: pitches must be multiples of 4");
     if (rows == 0) return VB_OK;
     cudaStream_t st = as_stream(stream);
     switch (dim / 128) {
@@ -229,9 +246,9 @@ extern "C" int vb_layernorm_bwd(const void* dy, int32_t dy_dtype, int64_t lddy, 
     case NV:                                                                                                                     \
         if (dy_dtype == VB_BF16)                                                                                                 \
             return ln_bwd_launch<NV, true>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx_bf16, lddx_bf16, dgamma, \
-                                           dbeta, dx_colsum, rows, st);                                                          \
+                                           dbeta, dx_colsum, rows, dy_add_bf16, lddy_add, st);                                   \
         return ln_bwd_launch<NV, false>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx_bf16, lddx_bf16, dgamma,    \
-                                        dbeta, dx_colsum, rows, st);
+                                        dbeta, dx_colsum, rows, dy_add_bf16, lddy_add, st);
         VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8)
 #undef VB_CASE
     }

@@ -1,0 +1,277 @@
+"""Drop-in DETR transformer encoder (models/object_detection/transformer.py: TransformerEncoderLayer :192-247,
+TransformerEncoder :98-115) on the hand-written sm_100a kernels.
+
+Same constructors, ``forward(src, src_mask=None, src_key_padding_mask=None, pos=None)`` signature, sequence-first
+[S, N, C] tensors and state_dict keys (``layers.{i}.self_attn.in_proj_weight`` ...).  The post-norm path
+(``normalize_before=False``, the reference default: transformer.py:27-28) is implemented; ``q = k = src + pos``,
+``v = src`` (transformer.py:218-219), boolean key-padding mask, ReLU (or GELU) feed-forward, LayerNorm eps 1e-5.
+The layer objects are parameter containers: the stack is executed by the enclosing ``TransformerEncoder``.
+"""
+import copy
+
+import torch
+from torch import nn
+
+from . import ops
+from .engine import FlatParams
+from .vit import _EncoderFn  # noqa: F401  (same single-node autograd pattern)
+
+DETR_ROLES = ("norm2_w", "norm2_b", "lin2_w", "lin2_b", "lin1_w", "lin1_b", "norm1_w", "norm1_b", "out_w", "out_b", "in_w", "in_b")
+
+
+class TransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward, dropout, activation, normalize_before):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        if activation not in ("relu", "gelu"):
+            raise RuntimeError(F"activation should be relu/gelu, not {activation}.")
+        self.activation_name = activation
+        self.normalize_before = normalize_before
+        self.d_model, self.nhead, self.dim_feedforward, self.dropout_p = d_model, nhead, dim_feedforward, dropout
+
+    def roles(self):
+        return {"norm2_w": self.norm2.weight, "norm2_b": self.norm2.bias, "lin2_w": self.linear2.weight, "lin2_b": self.linear2.bias,
+                "lin1_w": self.linear1.weight, "lin1_b": self.linear1.bias, "norm1_w": self.norm1.weight, "norm1_b": self.norm1.bias,
+                "out_w": self.self_attn.out_proj.weight, "out_b": self.self_attn.out_proj.bias,
+                "in_w": self.self_attn.in_proj_weight, "in_b": self.self_attn.in_proj_bias}
+
+    def forward(self, src, src_mask=None, src_key_padding_mask=None, pos=None):
+        # a single layer is a one-layer stack
+        enc = self.__dict__.get("_solo")
+        if enc is None:
+            enc = TransformerEncoder.__new__(TransformerEncoder)
+            nn.Module.__init__(enc)
+            enc.layers = nn.ModuleList([self])
+            enc.num_layers, enc.norm = 1, None
+            enc.__dict__["_engine"] = None
+            self.__dict__["_solo"] = enc
+        return enc(src, mask=src_mask, src_key_padding_mask=src_key_padding_mask, pos=pos)
+
+    def __deepcopy__(self, memo):
+        solo = self.__dict__.pop("_solo", None)
+        try:
+            new = self.__class__.__new__(self.__class__)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        finally:
+            if solo is not None:
+                self.__dict__["_solo"] = solo
+        return new
+
+
+class DetrEngine(FlatParams):
+    def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5):
+        assert d_model % 128 == 0 and d_model // nhead == 64, "vitb200 kernels need d_model % 128 == 0 and head_dim == 64"
+        self.D, self.H, self.F, self.L, self.eps = d_model, nhead, dim_feedforward, len(layers), eps
+        self.act = activation
+        self.has_norm = norm is not None
+        self._order = []
+        seg = []
+        if self.has_norm:
+            self._order += [(("g", "norm_w"), norm.weight), (("g", "norm_b"), norm.bias)]
+            seg.append(2)
+        for li in range(self.L - 1, -1, -1):
+            r = layers[li].roles()
+            self._order += [((li, k), r[k]) for k in DETR_ROLES]
+            seg.append(len(DETR_ROLES))
+        self._layout(seg)
+
+    def workspace(self, S, N, training):
+        key = (S, N, training)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev, D, Fd, M = self.flat.device, self.D, self.F, S * N
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *shape, dtype=bf: torch.empty(*shape, device=dev, dtype=dtype)
+        ws = {"S": S, "N": N, "M": M, "layer": []}
+        for _ in range(self.L if training else 1):
+            ws["layer"].append({"x_bf": e(M, D), "qk_bf": e(M, D), "qkb": e(M, 2 * D), "vb": e(M, D), "o": e(M, D),
+                                "lse": e(N, self.H, S, dtype=f32), "x1pre": e(M, D, dtype=f32), "x1": e(M, D, dtype=f32),
+                                "x1_bf": e(M, D), "a": e(M, Fd), "x2pre": e(M, D, dtype=f32), "mean1": e(M, dtype=f32),
+                                "rstd1": e(M, dtype=f32), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32)})
+        ws["x"] = [e(M, D, dtype=f32) for _ in range(2)]
+        ws["meanf"], ws["rstdf"] = e(M, dtype=f32), e(M, dtype=f32)
+        ws["y"] = e(M, D, dtype=f32)
+        if training:
+            ws["dA"], ws["dB"] = e(M, D, dtype=f32), e(M, D, dtype=f32)
+            ws["dA_bf"], ws["dB_bf"] = e(M, D), e(M, D)
+            ws["dh"], ws["dh2"] = e(M, D), e(M, D)
+            ws["da"] = e(M, Fd)
+            ws["dqk"], ws["dv"] = e(M, 2 * D), e(M, D)
+            ws["delta"] = e(N, self.H, S, dtype=f32)
+            ws["dpos"] = e(M, D, dtype=f32)
+        self._ws[key] = ws
+        return ws
+
+    def forward(self, src, pos, kpm, training):
+        self.ensure_bound()
+        S, N, D = src.shape
+        ws = self.workspace(S, N, training)
+        self.refresh_bf16()
+        M, H = ws["M"], self.H
+        src2 = src.contiguous().float().view(M, D)
+        pos2 = pos.contiguous().float().view(M, D) if pos is not None else None
+        ws["pos"], ws["kpm"] = pos2, kpm
+        x = src2
+        epi_act = ops.EPI_RELU if self.act == "relu" else ops.EPI_GELU
+        for li in range(self.L):
+            buf = ws["layer"][li if training else 0]
+            if li == 0:
+                ops.add_cast_bf16(x, None, buf["x_bf"])
+                ops.add_cast_bf16(x, pos2, buf["qk_bf"])
+            in_w, in_b = self.w((li, "in_w")), self.f((li, "in_b"))
+            ops.gemm(buf["qk_bf"], in_w[:2 * D], buf["qkb"], bias=in_b[:2 * D])
+            ops.gemm(buf["x_bf"], in_w[2 * D:], buf["vb"], bias=in_b[2 * D:])
+            ops.attention_fwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"] if training else None, B=N, H=H, S=S,
+                              tok_stride=N, batch_stride=1, key_padding_mask=kpm)
+            ops.gemm(buf["o"], self.w((li, "out_w")), buf["x1pre"], epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "out_b")), aux=x)
+            ops.layernorm_fwd(buf["x1pre"], self.f((li, "norm1_w")), self.f((li, "norm1_b")), self.eps, y_bf16=buf["x1_bf"], y_f32=buf["x1"],
+                              mean=buf["mean1"], rstd=buf["rstd1"])
+            if self.act == "relu":
+                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], epilogue=ops.EPI_RELU, bias=self.f((li, "lin1_b")))
+                act_out = buf["a"]
+            else:
+                if "g" not in buf:
+                    buf["g"] = torch.empty_like(buf["a"])
+                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], C2=buf["g"], epilogue=ops.EPI_GELU, bias=self.f((li, "lin1_b")))
+                act_out = buf["g"]
+            ops.gemm(act_out, self.w((li, "lin2_w")), buf["x2pre"], epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "lin2_b")), aux=buf["x1"])
+            x_next = ws["x"][li & 1]
+            last = li == self.L - 1
+            nbuf = None if last else ws["layer"][(li + 1) if training else 0]
+            # the next layer's operands come out of this LayerNorm directly: bf16(x) for v, bf16(x + pos) for q = k
+            if last:
+                ops.layernorm_fwd(buf["x2pre"], self.f((li, "norm2_w")), self.f((li, "norm2_b")), self.eps, y_f32=x_next,
+                                  mean=buf["mean2"], rstd=buf["rstd2"])
+            elif pos2 is not None:
+                ops.layernorm_fwd(buf["x2pre"], self.f((li, "norm2_w")), self.f((li, "norm2_b")), self.eps, y_f32=x_next,
+                                  y_bf16=nbuf["x_bf"], mean=buf["mean2"], rstd=buf["rstd2"], add=pos2, y2_bf16=nbuf["qk_bf"])
+            else:
+                ops.layernorm_fwd(buf["x2pre"], self.f((li, "norm2_w")), self.f((li, "norm2_b")), self.eps, y_f32=x_next,
+                                  y_bf16=nbuf["x_bf"], mean=buf["mean2"], rstd=buf["rstd2"])
+                ops.add_cast_bf16(x_next, None, nbuf["qk_bf"])
+            x = x_next
+        if self.has_norm:
+            ops.layernorm_fwd(x, self.f(("g", "norm_w")), self.f(("g", "norm_b")), self.eps, y_f32=ws["y"], mean=ws["meanf"], rstd=ws["rstdf"])
+            ws["x_last"] = x
+            return ws["y"].view(S, N, D), ws
+        return x.view(S, N, D), ws
+
+    def backward(self, ws, grad_out):
+        self.prepare_grads()
+        S, N, M, D, H = ws["S"], ws["N"], ws["M"], self.D, self.H
+        dA, dB, dA_bf, dB_bf, dh, dh2 = ws["dA"], ws["dB"], ws["dA_bf"], ws["dB_bf"], ws["dh"], ws["dh2"]
+        g = grad_out.contiguous().float().view(M, D)
+        pos2, kpm = ws["pos"], ws["kpm"]
+        dpos = None
+        if pos2 is not None:
+            dpos = ws["dpos"]
+            dpos.zero_()
+        seg = 0
+        if self.has_norm:
+            ops.layernorm_bwd(g, ws["x_last"], ws["meanf"], ws["rstdf"], self.f(("g", "norm_w")), dx=dA, dgamma=self.gview(("g", "norm_w")),
+                              dbeta=self.gview(("g", "norm_b")))
+            self._seg_done(seg)
+            seg += 1
+            g = dA
+        for li in range(self.L - 1, -1, -1):
+            buf = ws["layer"][li]
+            # norm2: gradient w.r.t. x2pre = x1 + linear2(act(linear1(x1)))
+            ops.layernorm_bwd(g, buf["x2pre"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dx=dB, dx_bf16=dB_bf,
+                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")), dx_colsum=self.gview((li, "lin2_b")))
+            act_out = buf["a"] if self.act == "relu" else buf["g"]
+            self._wgrad(dB_bf, act_out, (li, "lin2_w"))
+            if self.act == "relu":
+                ops.gemm(dB_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU, aux=buf["a"])
+            else:
+                ops.gemm(dB_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"])
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
+            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
+            # norm1: its output x1 received dB (residual) + dh (through the FFN); input is x1pre = src + out_proj(attn)
+            ops.layernorm_bwd(dB, buf["x1pre"], buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dx=dA, dx_bf16=dA_bf,
+                              dgamma=self.gview((li, "norm1_w")), dbeta=self.gview((li, "norm1_b")), dx_colsum=self.gview((li, "out_b")),
+                              dy_add=dh)
+            self._wgrad(dA_bf, buf["o"], (li, "out_w"))
+            ops.gemm(dA_bf, self.w((li, "out_w")), dh, b_major=1)      # dO
+            dqk, dv = ws["dqk"], ws["dv"]
+            ops.attention_bwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"], dh, dqk[:, :D], dqk[:, D:], dv,
+                              ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm)
+            in_w = self.w((li, "in_w"))
+            self._wgrad(dqk, buf["qk_bf"], (li, "in_w"), rows=(0, 2 * D))
+            self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
+            gb = self.gview((li, "in_b"))
+            ops.colsum_bf16(dqk, gb[:2 * D])
+            ops.colsum_bf16(dv, gb[2 * D:])
+            ops.gemm(dqk, in_w[:2 * D], dh, b_major=1)                 # d(src + pos) through q and k
+            ops.gemm(dv, in_w[2 * D:], dh2, b_major=1)                 # d src through v
+            # d src = dA (residual around attention) + dh + dh2; d pos += dh
+            ops.add3(dA, dh, dh2, dB, dpos)
+            g = dB
+            # ping-pong: next iteration's norm2 backward reads g (= dB) and writes dB again -> swap roles
+            dA, dB = dB, dA
+            dA_bf, dB_bf = dB_bf, dA_bf
+            self._seg_done(seg)
+            seg += 1
+        return g.view(S, N, D), (dpos.view(S, N, D) if dpos is not None else None)
+
+
+class _DetrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, kpm, src, pos, *params):
+        out, ws = engine.forward(src, pos, kpm, training=True)
+        ctx.engine, ctx.ws, ctx.n_params, ctx.has_pos = engine, ws, len(params), pos is not None
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dsrc, dpos = ctx.engine.backward(ctx.ws, grad_out)
+        return (None, None, dsrc.clone(), dpos.clone() if (ctx.has_pos and ctx.needs_input_grad[3]) else None) + (None,) * ctx.n_params
+
+
+class TransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers, norm=None):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.__dict__["_engine"] = None
+
+    def _get_engine(self):
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            l0 = self.layers[0]
+            eng = DetrEngine(list(self.layers), self.norm, l0.d_model, l0.nhead, l0.dim_feedforward, l0.activation_name,
+                             eps=float(l0.norm1.eps))
+            self.__dict__["_engine"] = eng
+        return eng
+
+    def forward(self, src, mask=None, src_key_padding_mask=None, pos=None):
+        l0 = self.layers[0]
+        if l0.normalize_before:
+            raise NotImplementedError("vitb200: the pre-norm DETR encoder path (normalize_before=True, transformer.py:228-241) is not "
+                                      "implemented yet; the reference default is post-norm")
+        if mask is not None:
+            raise NotImplementedError("vitb200: src_mask (attn_mask) is not supported; DETR passes None (transformer.py:59)")
+        if self.training and l0.dropout_p > 0:
+            raise NotImplementedError("vitb200: dropout > 0 in train() mode is not implemented in the fused kernels yet; "
+                                      "construct the layer with dropout=0.0 or call .eval()")
+        eng = self._get_engine()
+        kpm = None
+        if src_key_padding_mask is not None:
+            kpm = src_key_padding_mask.to(device=src.device, dtype=torch.uint8).contiguous()
+        params = [p for _, p in eng._order]
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or src.requires_grad)
+        if needs_grad:
+            return _DetrFn.apply(eng, kpm, src, pos, *params)
+        out, _ = eng.forward(src, pos, kpm, training=False)
+        return out.clone()

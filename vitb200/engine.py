@@ -34,59 +34,32 @@ def pick_split_k(tiles, k_blocks, sms):
     return best
 
 
-class VitEngine:
-    """Sequences the kernels for `n_prefix` token rows (1 = cls, 2 = cls + dist) + patches through L pre-norm blocks."""
+class FlatParams:
+    """Flat fp32 parameter / gradient buffers (+ bf16 shadow) that a module's nn.Parameters are views of.
 
-    def __init__(self, *, image_size, patch_size, hidden_dim, num_heads, mlp_dim, num_layers, num_classes, n_prefix, eps,
-                 globals_, layers):
-        """globals_: role -> Parameter for cls, [dist], pos, conv_w, conv_b, lnf_w, lnf_b, head_w, head_b, [headd_w, headd_b];
-        layers: list of dicts role -> Parameter (LAYER_ROLES)."""
-        assert hidden_dim % 128 == 0 and hidden_dim // num_heads == 64, \
-            "vitb200 kernels need hidden_dim % 128 == 0 and head_dim == 64 (true for every reference config)"
-        assert patch_size % 4 == 0 and image_size % patch_size == 0
-        self.image_size, self.p = image_size, patch_size
-        self.D, self.H, self.F, self.L, self.C = hidden_dim, num_heads, mlp_dim, num_layers, num_classes
-        self.n_prefix, self.eps = n_prefix, eps
-        self.P = (image_size // patch_size) ** 2
-        self.S = self.P + n_prefix
-        self.Kp = 3 * patch_size * patch_size
-        self.Kp_ld = _round_up(self.Kp, 8)
-        self.C_ld = _round_up(num_classes, 8)
-        self.g = globals_
-        self.layers = layers
-        self.two_heads = "headd_w" in globals_
-        # gradient-production order: heads + final norm, blocks L-1..0, embedding
-        seg0 = ["head_w", "head_b"] + (["headd_w", "headd_b"] if self.two_heads else []) + ["lnf_w", "lnf_b"]
-        emb = ["pos", "cls"] + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
-        self._order = [(("g", r), globals_[r]) for r in seg0]
-        self.segments = [(0, None)]  # (start offset, end offset) filled below
-        for li in range(num_layers - 1, -1, -1):
-            self._order += [((li, r), layers[li][r]) for r in LAYER_ROLES]
-        self._order += [(("g", r), globals_[r]) for r in emb]
+    Subclasses fill ``self._order`` (list of (key, Parameter) in gradient-production order) and call
+    ``_layout(segment_sizes)``."""
+
+    def _layout(self, seg_sizes):
         self.offsets = {}
-        off = 0
+        off, seg_start, count, seg_i = 0, 0, 0, 0
         seg_bounds = []
-        seg_start = 0
-        count = 0
-        seg_sizes = [len(seg0)] + [len(LAYER_ROLES)] * num_layers + [len(emb)]
-        seg_i = 0
+        self._by_key = {}
         for key, p in self._order:
             self.offsets[key] = off
+            self._by_key[key] = p
             off += _round_up(p.numel(), _ALIGN)
             count += 1
             if count == seg_sizes[seg_i]:
                 seg_bounds.append((seg_start, off))
                 seg_start, count, seg_i = off, 0, seg_i + 1
         self.total = off
-        self.segment_bounds = seg_bounds  # [(start, end)] in elements, index 0 = heads, 1..L = blocks L-1..0, L+1 = embedding
-        self.flat = None
-        self.flat_bf16 = None
-        self.flat_grad = None
+        self.segment_bounds = seg_bounds
+        self.flat = self.flat_bf16 = self.flat_grad = None
         self._ws = {}
         self._sms = None
         self.grad_segment_hook = None  # callable(segment_index) invoked as soon as a segment's gradients are complete
 
-    # ------------------------------------------------------------------ parameters --------------------------------
     def _params_are_views(self):
         if self.flat is None:
             return False
@@ -110,6 +83,7 @@ class VitEngine:
         for key, p in self._order:
             p.grad = None
         self._ws.clear()
+        self.bf16_fresh = False
         self._sms = torch.cuda.get_device_properties(device).multi_processor_count
 
     def ensure_bound(self):
@@ -122,18 +96,18 @@ class VitEngine:
 
     def w(self, key):
         """bf16 shadow of a parameter, as a 2-D matrix."""
-        p = self.layers[key[0]][key[1]] if key[0] != "g" else self.g[key[1]]
+        p = self._by_key[key]
         o = self.offsets[key]
         v = self.flat_bf16[o:o + p.numel()]
         return v.view(p.shape[0], -1) if p.dim() >= 2 else v
 
     def f(self, key):
-        p = self.layers[key[0]][key[1]] if key[0] != "g" else self.g[key[1]]
+        p = self._by_key[key]
         o = self.offsets[key]
         return self.flat[o:o + p.numel()]
 
     def gview(self, key):
-        p = self.layers[key[0]][key[1]] if key[0] != "g" else self.g[key[1]]
+        p = self._by_key[key]
         o = self.offsets[key]
         v = self.flat_grad[o:o + p.numel()]
         return v.view(p.shape[0], -1) if p.dim() >= 2 else v
@@ -171,6 +145,51 @@ class VitEngine:
             for key, p in self._order:
                 o = self.offsets[key]
                 p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    def _wgrad(self, dy, x, key, rows=None):
+        """dW[key] (or its first `rows` rows / a row slice) += dy^T x  with dy [M, N_out], x [M, K_in] (token-major bf16)."""
+        dW = self.gview(key)
+        if rows is not None:
+            dW = dW[rows[0]:rows[1]]
+        n_out, k_in = dW.shape
+        tiles = (-(-n_out // 128)) * (-(-k_in // 256))
+        split = pick_split_k(tiles, -(-dy.shape[0] // 64), self._sms)
+        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split)
+
+    def _seg_done(self, idx):
+        if self.grad_segment_hook is not None:
+            self.grad_segment_hook(idx)
+
+
+class VitEngine(FlatParams):
+    """Sequences the kernels for `n_prefix` token rows (1 = cls, 2 = cls + dist) + patches through L pre-norm blocks."""
+
+    def __init__(self, *, image_size, patch_size, hidden_dim, num_heads, mlp_dim, num_layers, num_classes, n_prefix, eps,
+                 globals_, layers):
+        """globals_: role -> Parameter for cls, [dist], pos, conv_w, conv_b, lnf_w, lnf_b, head_w, head_b, [headd_w, headd_b];
+        layers: list of dicts role -> Parameter (LAYER_ROLES)."""
+        assert hidden_dim % 128 == 0 and hidden_dim // num_heads == 64, \
+            "vitb200 kernels need hidden_dim % 128 == 0 and head_dim == 64 (true for every reference config)"
+        assert patch_size % 4 == 0 and image_size % patch_size == 0
+        self.image_size, self.p = image_size, patch_size
+        self.D, self.H, self.F, self.L, self.C = hidden_dim, num_heads, mlp_dim, num_layers, num_classes
+        self.n_prefix, self.eps = n_prefix, eps
+        self.P = (image_size // patch_size) ** 2
+        self.S = self.P + n_prefix
+        self.Kp = 3 * patch_size * patch_size
+        self.Kp_ld = _round_up(self.Kp, 8)
+        self.C_ld = _round_up(num_classes, 8)
+        self.g = globals_
+        self.layers = layers
+        self.two_heads = "headd_w" in globals_
+        # gradient-production order: heads + final norm, blocks L-1..0, embedding
+        seg0 = ["head_w", "head_b"] + (["headd_w", "headd_b"] if self.two_heads else []) + ["lnf_w", "lnf_b"]
+        emb = ["pos", "cls"] + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
+        self._order = [(("g", r), globals_[r]) for r in seg0]
+        for li in range(num_layers - 1, -1, -1):
+            self._order += [((li, r), layers[li][r]) for r in LAYER_ROLES]
+        self._order += [(("g", r), globals_[r]) for r in emb]
+        self._layout([len(seg0)] + [len(LAYER_ROLES)] * num_layers + [len(emb)])
 
     # ------------------------------------------------------------------ workspaces --------------------------------
     def workspace(self, B, training):
@@ -284,18 +303,6 @@ class VitEngine:
         return outs, ws
 
     # ------------------------------------------------------------------ backward ----------------------------------
-    def _wgrad(self, dy, x, key):
-        """dW[key] += dy^T x  with dy [M, N_out], x [M, K_in] (both token-major bf16)."""
-        dW = self.gview(key)
-        n_out, k_in = dW.shape
-        tiles = (-(-n_out // 128)) * (-(-k_in // 256))
-        split = pick_split_k(tiles, -(-dy.shape[0] // 64), self._sms)
-        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split)
-
-    def _seg_done(self, idx):
-        if self.grad_segment_hook is not None:
-            self.grad_segment_hook(idx)
-
     def backward(self, ws, grads, *, want, dlogits_ready=False):
         """grads: list matching forward outputs (fp32). Accumulates into the flat gradient buffer.
         dlogits_ready: ws["dlogits"][t] already holds the bf16 logits gradients (fused cross-entropy path)."""

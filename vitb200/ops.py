@@ -13,7 +13,7 @@ from ._lib import VbGemmDesc
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 3,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
-                     "vb_cross_entropy": 1, "vb_adam_step": 1}
+                     "vb_cross_entropy": 1, "vb_adam_step": 1, "vb_add_cast_bf16": 1, "vb_add3": 1}
 
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_ACCUM = range(7)
 BF16, F32 = 0, 1
@@ -85,7 +85,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def layernorm_fwd(x, gamma, beta, eps, *, y_bf16=None, y_f32=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps, *, y_bf16=None, y_f32=None, mean=None, rstd=None, add=None, y2_bf16=None):
     """x: fp32 [rows, D] view (unit inner stride). Writes y_bf16 and/or y_f32 (same shape) and optional mean/rstd."""
     lib = _lib.load()
     rows, D = x.shape
@@ -93,18 +93,21 @@ def layernorm_fwd(x, gamma, beta, eps, *, y_bf16=None, y_f32=None, mean=None, rs
     rc = lib.vb_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
                               _p(y_bf16), y_bf16.stride(0) if y_bf16 is not None else 0,
                               _p(y_f32), y_f32.stride(0) if y_f32 is not None else 0,
-                              _p(mean), _p(rstd), rows, D, float(eps), _stream())
+                              _p(mean), _p(rstd), rows, D, float(eps), _p(add), add.stride(0) if add is not None else 0,
+                              _p(y2_bf16), y2_bf16.stride(0) if y2_bf16 is not None else 0, _stream())
     _lib.check(rc, "vb_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, dx=None, dx_bf16=None, dgamma=None, dbeta=None, dx_colsum=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, dx=None, dx_bf16=None, dgamma=None, dbeta=None, dx_colsum=None,
+                  dy_add=None):
     lib = _lib.load()
     rows, D = x.shape
     rc = lib.vb_layernorm_bwd(dy.data_ptr(), _dt(dy), dy.stride(0), x.data_ptr(), x.stride(0), mean.data_ptr(), rstd.data_ptr(),
                               gamma.data_ptr(), _p(dres), dres.stride(0) if dres is not None else 0,
                               _p(dx), dx.stride(0) if dx is not None else 0,
                               _p(dx_bf16), dx_bf16.stride(0) if dx_bf16 is not None else 0,
-                              _p(dgamma), _p(dbeta), _p(dx_colsum), rows, D, _stream())
+                              _p(dgamma), _p(dbeta), _p(dx_colsum), rows, D, _p(dy_add),
+                              dy_add.stride(0) if dy_add is not None else 0, _stream())
     _lib.check(rc, "vb_layernorm_bwd")
 
 
@@ -191,3 +194,16 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, params_bf16, *, lr, beta1, bet
                           float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
                           _stream())
     _lib.check(rc, "vb_adam_step")
+
+
+def add_cast_bf16(a, b, out):
+    """out_bf16 = bf16(a + b); a, b fp32 contiguous (b may be None)."""
+    lib = _lib.load()
+    assert a.is_contiguous() and out.is_contiguous() and (b is None or b.is_contiguous())
+    _lib.check(lib.vb_add_cast_bf16(a.data_ptr(), _p(b), out.data_ptr(), a.numel(), _stream()), "vb_add_cast_bf16")
+
+
+def add3(a, b_bf16, c_bf16, out, accum=None):
+    """out = a + b (+ c); accum += b (optional). a/out/accum fp32, b/c bf16, all contiguous."""
+    lib = _lib.load()
+    _lib.check(lib.vb_add3(a.data_ptr(), b_bf16.data_ptr(), _p(c_bf16), out.data_ptr(), _p(accum), a.numel(), _stream()), "vb_add3")
