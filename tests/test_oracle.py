@@ -1,0 +1,156 @@
+"""CPU tests: the oracle restatement against the golden fixtures generated from the unmodified reference
+(tools/make_golden.py), and — when /root/reference is present (build container only) — against the live reference."""
+import math
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from helpers import O, rel_l2
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF = os.environ.get("VITB200_REFERENCE", "/root/reference")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["vit_tiny_b4.pt", "vit_b16x2_b2.pt"])
+def test_oracle_vit_matches_reference_golden(name):
+    gd = load(name)
+    cfg, batch, seed = gd["cfg"], gd["batch"], gd["seed"]
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.vit_param_shapes(**cfg), seed).items()}
+    images, labels = O.seeded_images(batch, cfg["image_size"], seed + 1), O.seeded_labels(batch, cfg["num_classes"], seed + 2)
+    kw = dict(patch_size=cfg["patch_size"], num_layers=cfg["num_layers"], num_heads=cfg["num_heads"])
+    logits = O.vit_forward(sd, images, **kw)
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    assert rel_l2(logits, gd["logits"]) < 1e-5
+    assert abs(loss.item() - gd["loss"]) < 1e-5
+    feats = O.vit_forward_features(sd, images, **kw).detach()
+    assert rel_l2(feats[:, 0], gd["features_cls"]) < 1e-5
+    assert abs(feats.norm().item() - gd["features_norm"]) < 1e-3 * gd["features_norm"]
+    for k, n in gd["grad_norms"].items():
+        assert abs(sd[k].grad.norm().item() - n) <= 1e-4 * max(n, 1e-6), k
+    for k, g in gd["grads_small"].items():
+        assert rel_l2(sd[k].grad, g) < 1e-4, k
+
+
+def test_oracle_detr_matches_reference_golden():
+    gd = load("detr_enc_d256.pt")
+    d, h, ffn, L, S, N, seed = gd["d_model"], gd["nhead"], gd["ffn"], gd["layers"], gd["S"], gd["N"], gd["seed"]
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.detr_param_shapes(d, ffn, L, False), seed).items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    src = torch.randn(S, N, d, generator=g, requires_grad=True)
+    pos = torch.randn(S, N, d, generator=g, requires_grad=True)
+    valid = torch.randint(S // 2, S + 1, (N,), generator=g)
+    kpm = torch.arange(S)[None, :] >= valid[:, None]
+    gout = torch.randn(S, N, d, generator=g)
+    out = O.detr_encoder_forward(sd, src, nhead=h, num_layers=L, src_key_padding_mask=kpm, pos=pos)
+    out.backward(gout)
+    assert rel_l2(out, gd["out"]) < 1e-5
+    assert abs(src.grad.norm().item() - gd["dsrc_norm"]) < 1e-4 * gd["dsrc_norm"]
+    assert abs(pos.grad.norm().item() - gd["dpos_norm"]) < 1e-4 * gd["dpos_norm"]
+    assert rel_l2(src.grad[0], gd["dsrc_row0"]) < 1e-4
+    for k, n in gd["grad_norms"].items():
+        assert abs(sd[k].grad.norm().item() - n) <= 1e-4 * max(n, 1e-6), k
+    for k, gr in gd["grads_small"].items():
+        assert rel_l2(sd[k].grad, gr) < 1e-4, k
+
+
+def test_oracle_distillation_loss_matches_reference_golden():
+    gd = load("distill_loss.pt")
+    g = torch.Generator().manual_seed(gd["seed"])
+    B, C = 16, 100
+    out, kd = torch.randn(B, C, generator=g), torch.randn(B, C, generator=g)
+    labels = torch.randint(0, C, (B,), generator=g)
+    W = torch.randn(3 * 8 * 8, C, generator=g) * 0.05
+    inputs = torch.randn(B, 3, 8, 8, generator=g)
+    teacher = inputs.flatten(1) @ W
+    for kind in ("none", "soft", "hard"):
+        v = O.distillation_loss(out, kd, labels, teacher, kind, 0.5, 5.0).item()
+        assert abs(v - gd[kind]) < 1e-5, (kind, v, gd[kind])
+
+
+def test_known_answers_from_reference_init():
+    """KAT-1/3/4: zero head => logits 0 and loss ln(C); key sets and parameter counts."""
+    gd = load("kat.pt")
+    assert gd["tiny_fresh_logits_absmax"] == 0.0
+    assert abs(gd["tiny_fresh_loss"] - math.log(10.0)) < 1e-6
+    a = gd["tiny_args"]
+    shapes = O.vit_param_shapes(a["image_size"], a["patch_size"], a["num_layers"], a["num_heads"], a["hidden_dim"], a["mlp_dim"],
+                                a["num_classes"])
+    assert list(shapes.keys()) == gd["tiny_keys"]
+    assert sum(math.prod(s) for s in shapes.values()) == gd["tiny_params"] == 3722250
+    b16 = O.vit_param_shapes(224, 16, 12, 12, 768, 3072, 1000)
+    assert list(b16.keys()) == gd["b16_keys"] and len(b16) == 152
+    assert sum(math.prod(s) for s in b16.values()) == gd["b16_params"] == 86567656
+
+
+def test_dropin_module_contract_and_seed_parity():
+    """The drop-in ViT has the reference's keys/shapes/attributes and (KAT-5) the same seed gives the same init."""
+    from vitb200.vit import ViT
+    gd = load("kat.pt")
+    a = gd["tiny_args"]
+    torch.manual_seed(gd["init_seed"])
+    m = ViT(**a)
+    sd = m.state_dict()
+    assert list(sd.keys()) == gd["tiny_keys"]
+    for k, (s1, s2) in gd["tiny_init_checksums"].items():
+        assert abs(sd[k].double().sum().item() - s1) < 1e-9 + 1e-12 * abs(s1), k
+        assert abs(sd[k].double().abs().sum().item() - s2) < 1e-9 + 1e-12 * abs(s2), k
+    for attr in ("image_size", "patch_size", "hidden_dim", "mlp_dim", "attention_dropout", "dropout", "num_classes", "norm_layer",
+                 "num_patches", "num_layers", "num_heads", "device", "conv_proj", "class_token", "encoder", "heads"):
+        assert hasattr(m, attr), attr
+    with pytest.raises(Exception):
+        ViT(33, 4, 1, 4, 256, 512, 0.0, 0.0, 10)       # image_size % patch_size != 0 (vanilla_vit.py:115)
+    b = ViT(224, 16, 12, 12, 768, 3072, 0.0, 0.0, 1000)
+    assert list(b.state_dict().keys()) == gd["b16_keys"]
+    # no CPU fallback: running on CPU must fail loudly
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 32, 32))
+
+
+def test_deit_and_detr_module_keys():
+    from vitb200.deit import VisionTransformerDistilled
+    from vitb200.detr import TransformerEncoder, TransformerEncoderLayer
+    d = VisionTransformerDistilled(img_size=32, patch_size=16, depth=2, num_heads=6, embed_dim=384, mlp_ratio=4.0, drop_rate=0.0,
+                                   attn_drop_rate=0.0, num_classes=100)
+    sh = O.deit_param_shapes(32, 16, 2, 6, 384, 4.0, 100)
+    assert set(sh) == set(d.state_dict().keys())
+    assert all(tuple(d.state_dict()[k].shape) == tuple(v) for k, v in sh.items())
+    enc = TransformerEncoder(TransformerEncoderLayer(512, 8, 2048, 0.1, "relu", False), 6)
+    sh = O.detr_param_shapes(512, 2048, 6, False)
+    assert set(sh) == set(enc.state_dict().keys())
+    assert enc.layers[0] is not enc.layers[1] and enc.layers[0].linear1.weight is not enc.layers[1].linear1.weight
+    with pytest.raises(RuntimeError):
+        TransformerEncoderLayer(512, 8, 2048, 0.1, "swish", False)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree not present (GPU box)")
+def test_oracle_against_live_reference():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for name in ("pycocotools", "pycocotools.coco"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pycocotools.coco"].COCO = object
+    sys.modules["pycocotools"].coco = sys.modules["pycocotools.coco"]
+    from models.image_classification.vanilla_vit import ViT as RefViT
+    cfg = dict(image_size=32, patch_size=4, num_layers=3, num_heads=4, hidden_dim=256, mlp_dim=512, num_classes=10)
+    sd = O.seeded_state_dict(O.vit_param_shapes(**cfg), 7)
+    m = RefViT(32, 4, 3, 4, 256, 512, 0.0, 0.0, 10)
+    m.load_state_dict(sd)
+    x = O.seeded_images(5, 32, 8)
+    y = O.seeded_labels(5, 10, 9)
+    ref = m(x)
+    torch.nn.functional.cross_entropy(ref, y).backward()
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.vit_forward(osd, x, patch_size=4, num_layers=3, num_heads=4)
+    torch.nn.functional.cross_entropy(out, y).backward()
+    assert rel_l2(out, ref) < 1e-5
+    for n, p in m.named_parameters():
+        assert rel_l2(osd[n].grad, p.grad) < 1e-4, n

@@ -1,0 +1,124 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (imported from /root/reference, build container
+only) on seeded inputs and weights.  The fixtures pin the CPU oracle (oracle/vit_oracle.py) and, through it, the
+CUDA path.  Re-run:  python tools/make_golden.py
+"""
+import math
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("VITB200_REFERENCE", "/root/reference")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+for name in ("pycocotools", "pycocotools.coco"):      # utils/load_data.py:6 imports it at module top
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["pycocotools.coco"].COCO = object
+sys.modules["pycocotools"].coco = sys.modules["pycocotools.coco"]
+
+import torch  # noqa: E402
+
+from models.image_classification.vanilla_vit import ViT as RefViT  # noqa: E402
+from models.object_detection.transformer import TransformerEncoder as RefEnc, TransformerEncoderLayer as RefLayer  # noqa: E402
+from utils.distillation_loss import DistillationLoss as RefDistill  # noqa: E402
+from utils.args import get_args  # noqa: E402
+
+from oracle import vit_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+SMALL = 4096
+
+
+def grads_summary(named_params):
+    norms, full = {}, {}
+    for n, p in named_params:
+        norms[n] = p.grad.norm().item()
+        if p.grad.numel() <= SMALL:
+            full[n] = p.grad.clone()
+    return norms, full
+
+
+def vit_case(name, cfg, batch, seed):
+    m = RefViT(cfg["image_size"], cfg["patch_size"], cfg["num_layers"], cfg["num_heads"], cfg["hidden_dim"], cfg["mlp_dim"], 0.0, 0.0,
+               cfg["num_classes"])
+    sd = O.seeded_state_dict(O.vit_param_shapes(**cfg), seed)
+    m.load_state_dict(sd)
+    m.train()
+    images, labels = O.seeded_images(batch, cfg["image_size"], seed + 1), O.seeded_labels(batch, cfg["num_classes"], seed + 2)
+    logits = m(images)
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    with torch.no_grad():
+        feats = m.forward_features(images)
+    norms, full = grads_summary(m.named_parameters())
+    torch.save({"cfg": cfg, "batch": batch, "seed": seed, "logits": logits.detach(), "loss": loss.item(),
+                "features_cls": feats[:, 0].clone(), "features_norm": feats.norm().item(), "grad_norms": norms, "grads_small": full},
+               os.path.join(OUT, name))
+    print(name, "loss", loss.item())
+
+
+def detr_case(name, d_model, nhead, ffn, layers, S, N, seed):
+    enc = RefEnc(RefLayer(d_model, nhead, ffn, 0.0, "relu", False), layers)
+    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, False), seed)
+    enc.load_state_dict(sd)
+    enc.train()
+    g = torch.Generator().manual_seed(seed + 1)
+    src = torch.randn(S, N, d_model, generator=g, requires_grad=True)
+    pos = torch.randn(S, N, d_model, generator=g, requires_grad=True)
+    valid = torch.randint(S // 2, S + 1, (N,), generator=g)
+    kpm = torch.arange(S)[None, :] >= valid[:, None]
+    gout = torch.randn(S, N, d_model, generator=g)
+    out = enc(src, src_key_padding_mask=kpm, pos=pos)
+    out.backward(gout)
+    norms, full = grads_summary(enc.named_parameters())
+    torch.save({"d_model": d_model, "nhead": nhead, "ffn": ffn, "layers": layers, "S": S, "N": N, "seed": seed, "out": out.detach(),
+                "dsrc_norm": src.grad.norm().item(), "dpos_norm": pos.grad.norm().item(), "dsrc_row0": src.grad[0].clone(),
+                "grad_norms": norms, "grads_small": full}, os.path.join(OUT, name))
+    print(name, "out norm", out.norm().item())
+
+
+def distill_case(name, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, C = 16, 100
+    out, kd = torch.randn(B, C, generator=g), torch.randn(B, C, generator=g)
+    labels = torch.randint(0, C, (B,), generator=g)
+    W = torch.randn(3 * 8 * 8, C, generator=g) * 0.05
+    teacher = lambda x: x.flatten(1) @ W
+    inputs = torch.randn(B, 3, 8, 8, generator=g)
+    res = {"seed": seed}
+    for kind in ("none", "soft", "hard"):
+        crit = RefDistill(torch.nn.CrossEntropyLoss(), teacher, kind, 0.5, 5.0)
+        res[kind] = crit(inputs, (out, kd), labels).item()
+    torch.save(res, os.path.join(OUT, name))
+    print(name, res)
+
+
+def kat_case(name):
+    torch.manual_seed(123)
+    args = dict(get_args("vit_tiny_cifar10"))
+    m = RefViT(**args)
+    init_sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.eval()
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    logits = m(x)
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.tensor([0, 1, 2, 3]))
+    b16 = RefViT(224, 16, 12, 12, 768, 3072, 0.0, 0.0, 1000)
+    res = {"tiny_args": args, "tiny_keys": list(init_sd.keys()), "tiny_params": sum(p.numel() for p in m.parameters()),
+           "tiny_fresh_logits_absmax": logits.abs().max().item(), "tiny_fresh_loss": loss.item(), "ln10": math.log(10.0),
+           "b16_keys": list(b16.state_dict().keys()), "b16_params": sum(p.numel() for p in b16.parameters()),
+           "tiny_init_checksums": {k: (v.double().sum().item(), v.double().abs().sum().item()) for k, v in init_sd.items()},
+           "init_seed": 123}
+    torch.save(res, os.path.join(OUT, name))
+    print(name, res["tiny_params"], res["b16_params"], res["tiny_fresh_loss"])
+
+
+if __name__ == "__main__":
+    TINY = dict(image_size=32, patch_size=4, num_layers=7, num_heads=4, hidden_dim=256, mlp_dim=512, num_classes=10)
+    B16_2L = dict(image_size=224, patch_size=16, num_layers=2, num_heads=12, hidden_dim=768, mlp_dim=3072, num_classes=1000)
+    vit_case("vit_tiny_b4.pt", TINY, 4, 101)
+    vit_case("vit_b16x2_b2.pt", B16_2L, 2, 111)
+    detr_case("detr_enc_d256.pt", 256, 4, 512, 2, 70, 2, 121)
+    distill_case("distill_loss.pt", 131)
+    kat_case("kat.pt")
