@@ -71,8 +71,12 @@ def case(name, M, N, K, a_major, b_major, epi, cdt, *, bias=False, split=1, dire
     errs = [rel(o, r) for o, r in zip(outs, refs)]
     nan = any(torch.isnan(o.float()).any().item() for o in outs)
     pad_ok = True
-    if ldc > N:
-        pad = Cfull[:, N:]
+    # TMA stores clip at 16-byte granularity: columns beyond round_up(N * elem_size, 16) must stay untouched
+    # (the engine always allocates row pitches that are multiples of 16 bytes, so the clipped tail is padding).
+    es = 2 if cdt == ops.BF16 else 4
+    n_clip = (N * es + 15) // 16 * 16 // es
+    if ldc > n_clip:
+        pad = Cfull[:, n_clip:]
         pad_ok = bool(torch.isnan(pad.float()).all().item())
     ok = (not nan) and all(e < tol for e in errs) and pad_ok
     print(f"{'OK  ' if ok else 'FAIL'} {name:34s} M={M:6d} N={N:5d} K={K:5d} maj=({a_major},{b_major}) epi={epi} cdt={cdt} "
@@ -137,8 +141,7 @@ def perf(M, N, K, a_major, b_major, epi, cdt, split=1, iters=20, name=""):
     print(f"PERF {name:22s} M={M} N={N} K={K} maj=({a_major},{b_major}) epi={epi} split={split}: {ms:.3f} ms {tf:7.1f} TF/s | cuBLAS {ms2:.3f} ms {tf2:7.1f} TF/s", flush=True)
 
 
-def main():
-    print(torch.cuda.get_device_name(0), flush=True)
+def correctness():
     ok = True
     for direct in (True, False):
         ok &= case("single tile 1 k-block", 128, 256, 64, 0, 0, ops.EPI_STORE, ops.BF16, direct=direct)
@@ -158,6 +161,12 @@ def main():
         ok &= case("wgrad split 4", 1000, 768, 4000, 1, 1, ops.EPI_ACCUM, ops.F32, split=4, direct=direct)
         ok &= case("many tiles (persistence)", 20000, 768, 768, 0, 0, ops.EPI_STORE, ops.BF16, bias=True, direct=direct)
         ok &= batched_case(direct)
+    return ok
+
+
+def main():
+    print(torch.cuda.get_device_name(0), flush=True)
+    ok = correctness()
     print("ALL OK" if ok else "SOME FAILED", flush=True)
     if "--perf" in sys.argv:
         M = 256 * 197

@@ -1,0 +1,87 @@
+"""Installs the B200 classes behind the reference's own import paths, so the reference's unmodified training loops,
+``DistillationLoss`` and notebook drive the hand-written kernels.
+
+    import vitb200.dropin as dropin
+    dropin.install("/path/to/vision-transformers")          # the reference checkout
+    from models.image_classification.vanilla_vit import ViT  # now the sm_100a implementation
+    model = ViT(**get_args("vit_tiny_cifar10")); model.train_model(model, train_loader, test_loader, 50, val_loader)
+
+What is rebound:
+  models.image_classification.vanilla_vit.{ViT, Encoder, EncoderBlock, MLPBlock, MLP}   (vanilla_vit.py:22-215)
+  models.object_detection.transformer.{TransformerEncoderLayer, TransformerEncoder}      (transformer.py:98-115,192-247)
+  timm.models.deit.VisionTransformerDistilled (a shim module, since timm is what deit.py:4 imports)
+The rebound ``ViT`` subclasses the reference's ``BaseTransformer`` (base.py:12) and borrows the reference's
+``ViT.train_model`` function object (vanilla_vit.py:217), so the training loop that runs is the reference's own code.
+Nothing is copied from the reference tree.
+"""
+import importlib
+import sys
+import types
+
+
+def _stub(name, **attrs):
+    mod = sys.modules.get(name)
+    if mod is None:
+        mod = types.ModuleType(name)
+        sys.modules[name] = mod
+    for k, v in attrs.items():
+        setattr(mod, k, v)
+    return mod
+
+
+def install(reference_root, stub_missing=True):
+    """Returns a dict of the rebound classes."""
+    from . import deit as our_deit
+    from . import detr as our_detr
+    from . import vit as our_vit
+
+    if reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    sys.dont_write_bytecode = True
+    if stub_missing:
+        try:
+            importlib.import_module("pycocotools.coco")
+        except Exception:   # utils/load_data.py:6 imports pycocotools at module top; only the COCO loader needs it
+            _stub("pycocotools")
+            _stub("pycocotools.coco", COCO=object)
+            sys.modules["pycocotools"].coco = sys.modules["pycocotools.coco"]
+    ref_vit = importlib.import_module("models.image_classification.vanilla_vit")
+    ref_base = importlib.import_module("models.image_classification.base")
+    ref_tr = importlib.import_module("models.object_detection.transformer")
+
+    ref_train_model = ref_vit.ViT.__dict__.get("train_model")
+
+    class ViT(our_vit.ViT, ref_base.BaseTransformer):
+        __doc__ = our_vit.ViT.__doc__
+
+    if ref_train_model is not None:
+        ViT.train_model = ref_train_model
+    ViT.__module__ = ref_vit.__name__
+    ViT.__qualname__ = "ViT"
+    ref_vit.ViT = ViT
+    ref_vit.Encoder = our_vit.Encoder
+    ref_vit.EncoderBlock = our_vit.EncoderBlock
+    ref_vit.MLPBlock = our_vit.MLPBlock
+    ref_vit.MLP = our_vit.MLP
+    ref_tr.TransformerEncoderLayer = our_detr.TransformerEncoderLayer
+    ref_tr.TransformerEncoder = our_detr.TransformerEncoder
+
+    # timm shim for models/image_classification/deit.py:4-5
+    have_timm = True
+    try:
+        importlib.import_module("timm.models.deit")
+    except Exception:
+        have_timm = False
+    if have_timm:
+        sys.modules["timm.models.deit"].VisionTransformerDistilled = our_deit.VisionTransformerDistilled
+    elif stub_missing:
+        def create_model(name, *a, **k):
+            raise RuntimeError(f"timm is not installed: cannot create teacher model '{name}'; pass your own teacher nn.Module "
+                               "to utils.distillation_loss.DistillationLoss")
+        _stub("timm")
+        _stub("timm.models", create_model=create_model)
+        _stub("timm.models.deit", VisionTransformerDistilled=our_deit.VisionTransformerDistilled)
+        sys.modules["timm"].models = sys.modules["timm.models"]
+        sys.modules["timm.models"].deit = sys.modules["timm.models.deit"]
+    return {"ViT": ViT, "TransformerEncoder": our_detr.TransformerEncoder, "TransformerEncoderLayer": our_detr.TransformerEncoderLayer,
+            "VisionTransformerDistilled": our_deit.VisionTransformerDistilled}
