@@ -163,13 +163,14 @@ VB_API int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_patches
  *   correct_accum (optional) counts argmax(z) == y.
  * vb_adam_step: torch.optim.Adam semantics (vanilla_vit.py:221: lr 1e-4, betas .9/.999, eps 1e-8) over flat
  *   fp32 buffers, n % 4 == 0; gradients are multiplied by grad_scale first; params_bf16 (optional) receives the
- *   refreshed bf16 shadow used by the GEMMs. */
+ *   refreshed bf16 shadow used by the GEMMs.  If step_counter_dev != NULL the step number lives on the device
+ *   (incremented by the call), so that a whole training step can be replayed from one CUDA graph. */
 VB_API int vb_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t C, float* loss_accum,
                             float weight, void* dlogits_bf16, int64_t lddz, float* dlogits_f32, int64_t lddzf,
                             float grad_scale, int32_t* correct_accum, void* stream);
 VB_API int vb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
-                        void* stream);
+                        int32_t* step_counter_dev, void* stream);
 
 #ifdef __cplusplus
 }

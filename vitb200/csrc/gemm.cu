@@ -2,9 +2,11 @@
 //
 //   C[M,N] = epilogue( A[M,K] * B[N,K]^T )     bf16 operands, fp32 accumulation in TMEM.
 //
-// One CTA per SM loops over 128x256 output tiles (or (tile, k-split) units).  Roles:
-//   warp 0      TMA producer: fills a 3/4-stage ring of {A 128x64, B 256x64} bf16 tiles (128B swizzle)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma 128x256x16 into one of two TMEM accumulators
+// One CTA per SM; with CG = 2 (default) the two CTAs of a cluster pair share 256x256 output tiles: each CTA loads its
+// own 128 rows of A and HALF of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) that reads both
+// CTAs' shared memory, halving the per-SM shared-memory traffic of the B operand.  Roles per CTA:
+//   warp 0      TMA producer: fills a 4-6-stage ring of {A 128x64, B (256/CG)x64} bf16 tiles (128B swizzle)
+//   warp 1      MMA issuer (leader CTA): one thread issues tcgen05.mma into one of two TMEM accumulators
 //   warp 2      TMEM allocator (512 columns = 2 x 256 fp32 accumulator columns)
 //   warps 4-11  epilogue: tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store / reduce-add,
 //               overlapping the MMA of the next tile (double-buffered accumulator)
@@ -14,6 +16,7 @@
 // Replaces the cuBLASLt calls behind nn.Linear / F.linear on the reference path
 // (vanilla_vit.py:33-42,77-79,212-213; torch/nn/functional.py:5835-5847,6690) and their autograd formulas.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -41,30 +44,45 @@ struct GemmArgs {
     long long ldc, ldc2, ldaux, bsc, bsc2, bsaux;
 };
 
-template <int EPI>
+template <int EPI, int CG>
 struct EpiTraits {
     static constexpr bool kHasAux = (EPI == VB_EPI_RESIDUAL || EPI == VB_EPI_DGELU || EPI == VB_EPI_DRELU);
     static constexpr bool kTwoOut = (EPI == VB_EPI_GELU);
-    static constexpr uint32_t kBufsPerWarp = (kHasAux || kTwoOut) ? 2 : 1;
-    static constexpr uint32_t kStages = (kBufsPerWarp == 2) ? 3 : 4;
-    static constexpr uint32_t kSmemBytes =
-        kStages * (A_STAGE_BYTES + B_STAGE_BYTES) + kEpiWarps * kBufsPerWarp * EPI_BUF_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+    // staging buffers per epilogue warp: [aux-in] + out0 + out1 (out1 = second output for GELU, else double buffer)
+    static constexpr uint32_t kBufsPerWarp = (kHasAux ? 1 : 0) + 2;
+    static constexpr uint32_t kBStageBytes = B_STAGE_BYTES / CG;
+    static constexpr uint32_t kStageBytes = A_STAGE_BYTES + kBStageBytes;
+    static constexpr uint32_t kEpiBytes = kEpiWarps * kBufsPerWarp * EPI_BUF_BYTES;
+    static constexpr uint32_t kBudget = 232448 - 1024 /*align*/ - 256 /*barriers*/;
+    static constexpr uint32_t kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
+    static constexpr uint32_t kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 1024;
 };
 
 // Exact-erf GELU via the Abramowitz-Stegun 7.1.26 rational approximation of erf (|abs err| < 1.5e-7, far below
 // bf16 resolution): Phi(z) = 1 - q for z >= 0, q for z < 0, with q = 0.5 * poly(t) * exp(-z^2/2),
 // t = 1 / (1 + 0.2316419 |z|).  One MUFU.RCP + one MUFU.EX2 + ~10 FMAs per element instead of erff()'s
 // two divergent polynomial branches; the derivative shares the exponential.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void phi_parts(float z, float& cdf, float& e) {
-    const float az = fabsf(z);
-    const float t = __fdividef(1.0f, fmaf(0.2316419f, az, 1.0f));
-    e = exp2f(-0.72134752044448170f * z * z);  // exp(-z^2 / 2)
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float q = 0.5f * poly * t * e;
-    cdf = z >= 0.f ? 1.0f - q : q;
+    const float t = fast_rcp(fmaf(0.2316419f, fabsf(z), 1.0f));
+    e = fast_ex2((z * -0.72134752044448170f) * z);  // exp(-z^2 / 2)
+    float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);   // coefficients pre-multiplied by 0.5
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    const float q = (poly * t) * e;                  // = 1 - Phi(|z|)
+    // Phi(z) = 0.5 + sign(z) * (0.5 - q)
+    cdf = 0.5f + __uint_as_float(__float_as_uint(0.5f - q) ^ (__float_as_uint(z) & 0x80000000u));
 }
 __device__ __forceinline__ float gelu_erf(float x) {
     float cdf, e;
@@ -87,27 +105,34 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 struct UnitCoord {
     int m_blk, n_blk, batch, kb0, kb1;
 };
-__device__ __forceinline__ UnitCoord decode_unit(const GemmArgs& a, int u) {
+// Units enumerate (k-split, batch, m-group, n-block) with n fastest; an m-group is CG consecutive 128-row blocks and
+// CTA `rank` of the pair owns block m_group * CG + rank.
+template <int CG>
+__device__ __forceinline__ UnitCoord decode_unit(const GemmArgs& a, int u, int rank) {
     UnitCoord c;
     const int s = u / a.num_tiles;
     const int t = u - s * a.num_tiles;
     c.batch = t / a.tiles_per_batch;
     const int r = t - c.batch * a.tiles_per_batch;
-    c.m_blk = r / a.n_blocks;
-    c.n_blk = r - c.m_blk * a.n_blocks;
+    const int mg = r / a.n_blocks;
+    c.m_blk = mg * CG + rank;
+    c.n_blk = r - mg * a.n_blocks;
     c.kb0 = s * a.kb_per_split;
     c.kb1 = min(c.kb0 + a.kb_per_split, a.k_blocks);
     return c;
 }
 
-template <int AMAJ, int BMAJ, int EPI, int CDT>
+template <int AMAJ, int BMAJ, int EPI, int CDT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
             const __grid_constant__ CUtensorMap tmAux, const GemmArgs args) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
-    using T = EpiTraits<EPI>;
+    using T = EpiTraits<EPI, CG>;
     constexpr uint32_t kStages = T::kStages;
+    constexpr uint32_t kBStage = T::kBStageBytes;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0;
+    const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;
     constexpr uint32_t CPC = (CDT == VB_BF16) ? 64 : 32;  // columns per 128-byte store chunk
     constexpr uint32_t kChunks = 128 / CPC;               // chunks per epilogue warp per tile
 
@@ -115,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
-    uint8_t* smem_epi = smem_b + kStages * B_STAGE_BYTES;
+    uint8_t* smem_epi = smem_b + kStages * kBStage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * T::kBufsPerWarp * EPI_BUF_BYTES);
     uint64_t* full_bar = bars;                      // [kStages]
     uint64_t* empty_bar = bars + kStages;           // [kStages]
@@ -141,14 +166,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], kEpiWarps);
+            mbar_init(&tmem_empty_bar[i], kEpiWarps * CG);   // (leader's copy) every epilogue warp of the pair arrives
         }
         for (uint32_t i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
         fence_barrier_init();
     }
-    if (warp_idx == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+    if (warp_idx == 2) {
+        if (CG == 2) tmem_alloc_2sm<kTmemCols>(tmem_ptr_smem);
+        else tmem_alloc<kTmemCols>(tmem_ptr_smem);
+    }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -156,27 +185,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int u = blockIdx.x; u < args.num_units; u += gridDim.x) {
-                const UnitCoord c = decode_unit(args, u);
+            for (int u = unit0; u < args.num_units; u += unit_stride) {
+                const UnitCoord c = decode_unit<CG>(args, u, rank);
                 const int bb = args.b_batched ? c.batch : 0;
+                const int n_row0 = c.n_blk * BN + rank * (BN / CG);   // this CTA's share of the B tile
                 for (int kb = c.kb0; kb < c.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-                    uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
-                    if (AMAJ == 0) {
-                        tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, c.m_blk * BM, c.batch);
-                    } else {
+                    uint8_t* sb = smem_b + stage * kBStage;
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes);
+                        if (AMAJ == 0) {
+                            tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, c.m_blk * BM, c.batch);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < int(BM / 64); ++j)
-                            tma_load_3d(sa + j * (BK * 128), &tmA, &full_bar[stage], c.m_blk * BM + j * 64, kb * BK, c.batch);
-                    }
-                    if (BMAJ == 0) {
-                        tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, c.n_blk * BN, bb);
-                    } else {
+                            for (int j = 0; j < int(BM / 64); ++j)
+                                tma_load_3d(sa + j * (BK * 128), &tmA, &full_bar[stage], c.m_blk * BM + j * 64, kb * BK, c.batch);
+                        }
+                        if (BMAJ == 0) {
+                            tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, n_row0, bb);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < int(BN / 64); ++j)
-                            tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[stage], c.n_blk * BN + j * 64, kb * BK, bb);
+                            for (int j = 0; j < int(BN / 64); ++j)
+                                tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[stage], n_row0 + j * 64, kb * BK, bb);
+                        }
+                    } else {
+                        // both CTAs' loads complete on the LEADER's full barrier; the leader expects both halves
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * T::kStageBytes);
+                        if (AMAJ == 0) {
+                            tma_load_3d_2sm(sa, &tmA, fb, kb * BK, c.m_blk * BM, c.batch);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < int(BM / 64); ++j)
+                                tma_load_3d_2sm(sa + j * (BK * 128), &tmA, fb, c.m_blk * BM + j * 64, kb * BK, c.batch);
+                        }
+                        if (BMAJ == 0) {
+                            tma_load_3d_2sm(sb, &tmB, fb, kb * BK, n_row0, bb);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < int(BN / CG / 64); ++j)
+                                tma_load_3d_2sm(sb + j * (BK * 128), &tmB, fb, n_row0 + j * 64, kb * BK, bb);
+                        }
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -184,8 +234,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else if (warp_idx == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMAJ, BMAJ);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, AMAJ, BMAJ);
             // K-major SW128: 8-row groups 1024 B apart (SBO); MN-major SW128: 64-wide MN atoms BK*128 B apart
             // (LBO) and 8-deep K groups 1024 B apart (SBO).
             constexpr uint64_t a_base = (AMAJ == 0) ? umma_smem_desc_base(0, 1024) : umma_smem_desc_base(BK * 128, 1024);
@@ -193,8 +243,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             constexpr uint32_t a_kstep = (AMAJ == 0) ? UK * 2 : UK * 128;
             constexpr uint32_t b_kstep = (BMAJ == 0) ? UK * 2 : UK * 128;
             uint32_t stage = 0, phase = 0, it = 0;
-            for (int u = blockIdx.x; u < args.num_units; u += gridDim.x, ++it) {
-                const UnitCoord c = decode_unit(args, u);
+            for (int u = unit0; u < args.num_units; u += unit_stride, ++it) {
+                const UnitCoord c = decode_unit<CG>(args, u, 0);
                 const uint32_t as = it & 1, ap = (it >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[as], ap ^ 1);
                 tcgen05_fence_after();
@@ -203,17 +253,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * kBStage);
 #pragma unroll
                     for (uint32_t k = 0; k < BK / UK; ++k) {
                         const uint64_t ad = umma_smem_desc(a_base, sa + k * a_kstep);
                         const uint64_t bd = umma_smem_desc(b_base, sb + k * b_kstep);
-                        umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > c.kb0 || k > 0) ? 1u : 0u);
+                        if (CG == 2) umma_bf16_ss_2sm(d_tmem, ad, bd, idesc, (kb > c.kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > c.kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    // frees the smem slot (in both CTAs of the pair) once these MMAs retire
+                    if (CG == 2) umma_commit_2sm(&empty_bar[stage], 0x3);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[as]);     // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps of both CTAs
+                if (CG == 2) umma_commit_2sm(&tmem_full_bar[as], 0x3);
+                else umma_commit(&tmem_full_bar[as]);
             }
         }
     } else if (warp_idx >= kFirstEpiWarp) {
@@ -221,8 +276,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t ew = warp_idx - kFirstEpiWarp;
         const uint32_t quad = warp_idx & 3;   // TMEM lane quadrant this warp may access
         const uint32_t half = ew >> 2;        // which 128-column half of the tile
-        uint8_t* buf0 = smem_epi + ew * T::kBufsPerWarp * EPI_BUF_BYTES;
-        uint8_t* buf1 = buf0 + EPI_BUF_BYTES;  // aux-in or second output (only if kBufsPerWarp == 2)
+        uint8_t* wbuf = smem_epi + ew * T::kBufsPerWarp * EPI_BUF_BYTES;
+        uint8_t* buf_aux = wbuf;                                        // aux-in (only if kHasAux)
+        uint8_t* buf_o0 = wbuf + (T::kHasAux ? EPI_BUF_BYTES : 0);      // output staging 0
+        uint8_t* buf_o1 = buf_o0 + EPI_BUF_BYTES;                       // staging 1: GELU's second output, else double buffer
+        uint32_t chunk_count = 0;                                       // running count of stored chunks (selects the out buffer)
+        const uint32_t tmem_empty_remote = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0;
         const uint32_t swz = (lane & 7) << 4;
         const uint32_t row_off = lane * 128;
         uint32_t aux_phase = 0;
@@ -231,33 +290,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         auto next_valid = [&](int& u, int& ch) -> bool {
             while (u < args.num_units) {
                 if (ch < int(kChunks)) {
-                    const UnitCoord c = decode_unit(args, u);
+                    const UnitCoord c = decode_unit<CG>(args, u, rank);
                     const int col0 = c.n_blk * BN + half * 128 + ch * CPC;
                     if (col0 < args.N) return true;
                 }
-                u += gridDim.x;
+                u += unit_stride;
                 ch = 0;
             }
             return false;
         };
         auto issue_aux = [&](int u, int ch) {
-            const UnitCoord c = decode_unit(args, u);
+            const UnitCoord c = decode_unit<CG>(args, u, rank);
             const int col0 = c.n_blk * BN + half * 128 + ch * CPC;
             const int row0 = args.c_row_offset + c.m_blk * BM + quad * 32;
             mbar_arrive_expect_tx(&aux_bar[ew], EPI_BUF_BYTES);
-            tma_load_3d(buf1, &tmAux, &aux_bar[ew], col0, row0, args.aux_bcast ? 0 : c.batch);
+            tma_load_3d(buf_aux, &tmAux, &aux_bar[ew], col0, row0, args.aux_bcast ? 0 : c.batch);
         };
 
         if constexpr (T::kHasAux) {
             if (!args.direct && lane == 0) {
-                int u = blockIdx.x, ch = 0;
+                int u = unit0, ch = 0;
                 if (next_valid(u, ch)) issue_aux(u, ch);
             }
         }
 
         uint32_t it = 0;
-        for (int u = blockIdx.x; u < args.num_units; u += gridDim.x, ++it) {
-            const UnitCoord c = decode_unit(args, u);
+        auto release_tmem = [&](uint32_t as) {
+            if (CG == 2 && rank != 0) mbar_arrive_cluster(tmem_empty_remote + as * 8);
+            else mbar_arrive(&tmem_empty_bar[as]);
+        };
+        for (int u = unit0; u < args.num_units; u += unit_stride, ++it) {
+            const UnitCoord c = decode_unit<CG>(args, u, rank);
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             mbar_wait(&tmem_full_bar[as], ap);
             tcgen05_fence_after();
@@ -272,7 +335,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (n_valid_chunks == 0) {
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                if (lane == 0) release_tmem(as);
                 continue;
             }
 
@@ -285,6 +348,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 const bool write_c = (EPI != VB_EPI_GELU) || args.C != nullptr;
+                uint8_t* obuf = (T::kTwoOut || (chunk_count & 1) == 0) ? buf_o0 : buf_o1;
 #pragma unroll
                 for (int g = 0; g < int(CPC / 32); ++g) {
                     const int colg = col0 + g * 32;
@@ -296,7 +360,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         // all TMEM reads of this tile by this warp are done -> hand the accumulator back
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                        if (lane == 0) release_tmem(as);
                     }
                     float v[32];
 #pragma unroll
@@ -322,14 +386,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if constexpr (CDT == VB_F32) {
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) {
-                                    const uint4 w = *reinterpret_cast<const uint4*>(buf1 + row_off + ((q << 4) ^ swz));
+                                    const uint4 w = *reinterpret_cast<const uint4*>(buf_aux + row_off + ((q << 4) ^ swz));
                                     x[q * 4 + 0] = __uint_as_float(w.x); x[q * 4 + 1] = __uint_as_float(w.y);
                                     x[q * 4 + 2] = __uint_as_float(w.z); x[q * 4 + 3] = __uint_as_float(w.w);
                                 }
                             } else {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
-                                    const uint4 w = *reinterpret_cast<const uint4*>(buf1 + row_off + ((((g * 4 + q)) << 4) ^ swz));
+                                    const uint4 w = *reinterpret_cast<const uint4*>(buf_aux + row_off + ((((g * 4 + q)) << 4) ^ swz));
                                     x[q * 8 + 0] = bf16_lo(w.x); x[q * 8 + 1] = bf16_hi(w.x);
                                     x[q * 8 + 2] = bf16_lo(w.y); x[q * 8 + 3] = bf16_hi(w.y);
                                     x[q * 8 + 4] = bf16_lo(w.z); x[q * 8 + 5] = bf16_hi(w.z);
@@ -360,7 +424,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     // ---- registers -> swizzled staging buffer (or straight to global on the bring-up path) ----
                     if (!args.direct) {
                         if (g == 0) {
-                            if (lane == 0) tma_store_wait_read<0>();  // previous TMA store out of buf0/buf1 has drained
+                            // GELU: both buffers belong to the previous chunk's store -> wait for all; otherwise the two
+                            // buffers alternate, so only the store issued two chunks ago has to have drained
+                            if (lane == 0) {
+                                if (T::kTwoOut) tma_store_wait_read<0>();
+                                else tma_store_wait_read<1>();
+                            }
                             __syncwarp();
                         }
                         if constexpr (CDT == VB_F32) {
@@ -370,7 +439,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     uint4 w;
                                     w.x = __float_as_uint(v[q * 4 + 0]); w.y = __float_as_uint(v[q * 4 + 1]);
                                     w.z = __float_as_uint(v[q * 4 + 2]); w.w = __float_as_uint(v[q * 4 + 3]);
-                                    *reinterpret_cast<uint4*>(buf0 + row_off + ((q << 4) ^ swz)) = w;
+                                    *reinterpret_cast<uint4*>(obuf + row_off + ((q << 4) ^ swz)) = w;
                                 }
                             }
                         } else {
@@ -380,7 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     uint4 w;
                                     w.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
                                     w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-                                    *reinterpret_cast<uint4*>(buf0 + row_off + (((g * 4 + q) << 4) ^ swz)) = w;
+                                    *reinterpret_cast<uint4*>(obuf + row_off + (((g * 4 + q) << 4) ^ swz)) = w;
                                 }
                             }
                             if constexpr (T::kTwoOut) {
@@ -389,7 +458,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     uint4 w;
                                     w.x = pack_bf16(gl[q * 8 + 0], gl[q * 8 + 1]); w.y = pack_bf16(gl[q * 8 + 2], gl[q * 8 + 3]);
                                     w.z = pack_bf16(gl[q * 8 + 4], gl[q * 8 + 5]); w.w = pack_bf16(gl[q * 8 + 6], gl[q * 8 + 7]);
-                                    *reinterpret_cast<uint4*>(buf1 + row_off + (((g * 4 + q) << 4) ^ swz)) = w;
+                                    *reinterpret_cast<uint4*>(buf_o1 + row_off + (((g * 4 + q) << 4) ^ swz)) = w;
                                 }
                             }
                         }
@@ -416,17 +485,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if constexpr (T::kHasAux) {
                             // aux buffer consumed: prefetch the aux tile of the next chunk this warp will process
                             int nu = u, nch = ch + 1;
-                            if (nch >= n_valid_chunks) { nu += gridDim.x; nch = 0; }
+                            if (nch >= n_valid_chunks) { nu += unit_stride; nch = 0; }
                             if (next_valid(nu, nch)) issue_aux(nu, nch);
                         }
                         if constexpr (EPI == VB_EPI_ACCUM) {
-                            tma_reduce_add_3d(&tmC, buf0, col0, row0, c.batch);
+                            tma_reduce_add_3d(&tmC, obuf, col0, row0, c.batch);
                         } else {
-                            if (write_c) tma_store_3d(&tmC, buf0, col0, row0, c.batch);
-                            if constexpr (T::kTwoOut) tma_store_3d(&tmC2, buf1, col0, row0, c.batch);
+                            if (write_c) tma_store_3d(&tmC, obuf, col0, row0, c.batch);
+                            if constexpr (T::kTwoOut) tma_store_3d(&tmC2, buf_o1, col0, row0, c.batch);
                         }
                         tma_store_commit();
                     }
+                    ++chunk_count;
                 }
             }
         }
@@ -434,10 +504,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer may still be reading our smem / signalling our barriers
+    else __syncthreads();
     if (warp_idx == 2) {
         tcgen05_fence_after();
-        tmem_dealloc<kTmemCols>(tmem_base);
+        if (CG == 2) tmem_dealloc_2sm<kTmemCols>(tmem_base);
+        else tmem_dealloc<kTmemCols>(tmem_base);
     }
 #endif
 }
@@ -486,19 +558,40 @@ int make_tmap_3d(CUtensorMap* m, int dtype, const void* ptr, uint64_t d0, uint64
     return VB_OK;
 }
 
-template <int AMAJ, int BMAJ, int EPI, int CDT>
+template <int AMAJ, int BMAJ, int EPI, int CDT, int CG>
 static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tC2,
                   const CUtensorMap& tX, const GemmArgs& args, int grid, cudaStream_t stream) {
-    auto kern = gemm_kernel<AMAJ, BMAJ, EPI, CDT>;
-    constexpr uint32_t smem = EpiTraits<EPI>::kSmemBytes;
+    auto kern = gemm_kernel<AMAJ, BMAJ, EPI, CDT, CG>;
+    constexpr uint32_t smem = EpiTraits<EPI, CG>::kSmemBytes;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool configured = false;  // per instantiation; attribute is per-context, benign to repeat on races
     if (!configured) {
         VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    kern<<<grid, kThreads, smem, stream>>>(tA, tB, tC, tC2, tX, args);
-    VB_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tA, tB, tC, tC2, tX, args));
     return VB_OK;
+}
+
+static int default_cta_group() {
+    static int cg = 0;
+    if (cg == 0) {
+        const char* e = getenv("VITB200_GEMM_CTA_GROUP");
+        cg = (e && e[0] == '1') ? 1 : 2;
+    }
+    return cg;
 }
 
 }  // namespace vb
@@ -520,9 +613,10 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     VB_REQUIRE(!has_aux || d->AUX, "epilogue %d needs AUX", d->epilogue);
     VB_REQUIRE(d->epilogue != VB_EPI_GELU || (d->C2 && d->c_dtype == VB_BF16), "VB_EPI_GELU needs bf16 C2");
 
+    const int cg = default_cta_group();
     GemmArgs a{};
     a.M = d->M; a.N = d->N; a.K = d->K; a.batches = d->batches;
-    const int m_blocks = (d->M + BM - 1) / BM;
+    const int m_blocks = ((d->M + BM - 1) / BM + cg - 1) / cg;   // m-groups of `cg` 128-row blocks
     a.n_blocks = (d->N + BN - 1) / BN;
     a.k_blocks = (d->K + BK - 1) / BK;
     a.tiles_per_batch = m_blocks * a.n_blocks;
@@ -547,7 +641,7 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     else rc = make_tmap_3d(&tA, VB_BF16, d->A, d->M, d->K, nb, d->lda, d->batch_stride_a, 64, BK);
     if (rc) return rc;
     const uint64_t nbb = a.b_batched ? nb : 1;
-    if (d->b_major == 0) rc = make_tmap_3d(&tB, VB_BF16, d->B, d->K, d->N, nbb, d->ldb, d->batch_stride_b, 64, BN);
+    if (d->b_major == 0) rc = make_tmap_3d(&tB, VB_BF16, d->B, d->K, d->N, nbb, d->ldb, d->batch_stride_b, 64, BN / cg);
     else rc = make_tmap_3d(&tB, VB_BF16, d->B, d->N, d->K, nbb, d->ldb, d->batch_stride_b, 64, BK);
     if (rc) return rc;
     const uint32_t cpc = d->c_dtype == VB_BF16 ? 64 : 32;
@@ -573,9 +667,15 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     int sms = num_sms();
     if (sms <= 0) return fail(VB_ERR_CUDA, "cannot determine SM count");
     int grid = d->max_ctas > 0 ? (d->max_ctas < sms ? d->max_ctas : sms) : sms;
-    if (grid > a.num_units) grid = a.num_units;
+    if (grid > a.num_units * cg) grid = a.num_units * cg;
+    grid -= grid % cg;
+    if (grid < cg) grid = cg;
 
-#define VB_LAUNCH(AM, BMJ, EP, CD) return launch<AM, BMJ, EP, CD>(tA, tB, tC, tC2, tX, a, grid, stream)
+#define VB_LAUNCH(AM, BMJ, EP, CD)                                                              \
+    do {                                                                                        \
+        if (cg == 2) return launch<AM, BMJ, EP, CD, 2>(tA, tB, tC, tC2, tX, a, grid, stream);   \
+        return launch<AM, BMJ, EP, CD, 1>(tA, tB, tC, tC2, tX, a, grid, stream);                \
+    } while (0)
     const int am = d->a_major, bm = d->b_major, ep = d->epilogue, cd = d->c_dtype;
     if (am == 0 && bm == 0) {
         if (ep == VB_EPI_STORE && cd == VB_BF16) VB_LAUNCH(0, 0, VB_EPI_STORE, VB_BF16);

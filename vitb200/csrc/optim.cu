@@ -44,9 +44,16 @@ __global__ void ce_kernel(const float* __restrict__ logits, long long ld, const 
     }
 }
 
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+
 __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                             uint2* __restrict__ p_bf16, long long n4, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt, float grad_scale) {
+                            float bc1, float bc2_sqrt, float grad_scale, const int* __restrict__ step_dev) {
+    if (step_dev) {  // device-side step counter: lets the whole training step live in one CUDA graph
+        const float t = (float)(*step_dev);
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
         float* pp = reinterpret_cast<float*>(&pv);
@@ -89,10 +96,15 @@ extern "C" int vb_cross_entropy(const float* logits, int64_t ld, const int64_t* 
 
 extern "C" int vb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
                             float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
-                            void* stream) {
+                            int32_t* step_counter_dev, void* stream) {
     using namespace vb;
     if (int rc = check_arch()) return rc;
-    VB_REQUIRE(params && grads && exp_avg && exp_avg_sq && n >= 0 && n % 4 == 0 && step >= 1, "adam_step: bad arguments");
+    VB_REQUIRE(params && grads && exp_avg && exp_avg_sq && n >= 0 && n % 4 == 0 && (step >= 1 || step_counter_dev), "adam_step: bad arguments");
+    if (step_counter_dev) {
+        step_inc_kernel<<<1, 1, 0, as_stream(stream)>>>(step_counter_dev);
+        VB_CUDA_CHECK(cudaGetLastError());
+        if (step < 1) step = 1;
+    }
     if (n == 0) return VB_OK;
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
@@ -102,7 +114,7 @@ extern "C" int vb_adam_step(float* params, const float* grads, float* exp_avg, f
     adam_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads),
                                                            reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq),
                                                            reinterpret_cast<uint2*>(params_bf16), n / 4, lr, beta1, beta2, eps,
-                                                           weight_decay, bc1, bc2s, grad_scale);
+                                                           weight_decay, bc1, bc2s, grad_scale, step_counter_dev);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

@@ -152,8 +152,9 @@ class FlatParams:
         if rows is not None:
             dW = dW[rows[0]:rows[1]]
         n_out, k_in = dW.shape
-        tiles = (-(-n_out // 128)) * (-(-k_in // 256))
-        split = pick_split_k(tiles, -(-dy.shape[0] // 64), self._sms)
+        # work units are 256x256 tiles owned by CTA pairs (cta_group::2): sms // 2 pairs run concurrently
+        tiles = (-(-(-(-n_out // 128)) // 2)) * (-(-k_in // 256))
+        split = pick_split_k(tiles, -(-dy.shape[0] // 64), max(1, self._sms // 2))
         ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split)
 
     def _seg_done(self, idx):

@@ -13,7 +13,7 @@ from ._lib import VbGemmDesc
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 3,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
-                     "vb_cross_entropy": 1, "vb_adam_step": 1, "vb_add_cast_bf16": 1, "vb_add3": 1}
+                     "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1}
 
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_ACCUM = range(7)
 BF16, F32 = 0, 1
@@ -187,12 +187,14 @@ def cross_entropy(logits, labels, loss_accum, *, weight, dlogits_bf16=None, dlog
     _lib.check(rc, "vb_cross_entropy")
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, params_bf16, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def adam_step(params, grads, exp_avg, exp_avg_sq, params_bf16, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+              step_counter=None):
+    """step_counter: optional int32 device tensor holding the step number (incremented by the call; CUDA-graph friendly)."""
     lib = _lib.load()
     n = params.numel()
     rc = lib.vb_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), _p(params_bf16), n,
                           float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
-                          _stream())
+                          _p(step_counter), _stream())
     _lib.check(rc, "vb_adam_step")
 
 

@@ -1,5 +1,5 @@
 """Sync-free training step for the drop-in models: fused cross-entropy, in-engine backward, optional data-parallel
-gradient all-reduce overlapped with backward, fused flat Adam (+ bf16 parameter refresh).
+gradient all-reduce overlapped with backward, fused flat Adam (+ bf16 parameter refresh), replayed from one CUDA graph.
 
 This is the B200-native equivalent of the reference's hot loop body (base.py:51-57 == vanilla_vit.py:233-239:
 ``zero_grad -> model(images) -> CrossEntropyLoss -> backward -> Adam.step``) without its two ``.item()`` host syncs
@@ -16,9 +16,17 @@ class FusedAdam:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.engine = model._get_engine()
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.step_count = 0
         self.exp_avg = None
         self.exp_avg_sq = None
+        self.step_counter = None   # int32 device tensor: the step number lives on the GPU (graph-replayable)
+
+    def _ensure_state(self):
+        eng = self.engine
+        eng.ensure_bound()
+        if self.exp_avg is None or self.exp_avg.device != eng.flat.device or self.exp_avg.numel() != eng.total:
+            self.exp_avg = torch.zeros_like(eng.flat)
+            self.exp_avg_sq = torch.zeros_like(eng.flat)
+            self.step_counter = torch.zeros(1, device=eng.flat.device, dtype=torch.int32)
 
     def zero_grad(self, set_to_none=False):
         eng = self.engine
@@ -28,40 +36,50 @@ class FusedAdam:
 
     def step(self, grad_scale=1.0):
         eng = self.engine
-        if self.exp_avg is None or self.exp_avg.device != eng.flat.device or self.exp_avg.numel() != eng.total:
-            self.exp_avg = torch.zeros_like(eng.flat)
-            self.exp_avg_sq = torch.zeros_like(eng.flat)
-        self.step_count += 1
+        self._ensure_state()
         ops.adam_step(eng.flat, eng.flat_grad, self.exp_avg, self.exp_avg_sq, eng.flat_bf16, lr=self.lr, beta1=self.betas[0],
-                      beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self.step_count, grad_scale=grad_scale)
+                      beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=0, grad_scale=grad_scale,
+                      step_counter=self.step_counter)
         eng.bf16_fresh = True
 
 
 class Trainer:
-    """``loss = trainer.step(images, labels)``; images/labels may live on the host (pinned) or on the device."""
+    """``loss = trainer.step(images, labels)``; images/labels may live on the host (pinned) or on the device.
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, reducer=None):
+    The first step for a given batch shape runs eagerly (allocations, kernel attribute setup), the second is captured
+    into a CUDA graph, later steps copy the batch into the graph's static input buffers and replay it.  Call
+    ``invalidate()`` after changing parameters from outside (load_state_dict, manual edits) so the bf16 shadow is
+    refreshed."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, reducer=None, use_cuda_graph=True):
         self.model = model
         self.engine = model._get_engine()
         self.opt = FusedAdam(model, lr, betas, eps, weight_decay)
         self.reducer = reducer
+        self.use_cuda_graph = use_cuda_graph
         self._loss = None
         self._correct = None
+        self._graphs = {}   # batch shape -> (graph, static_images, static_labels)
+        self._eager_done = set()
         if reducer is not None:
             reducer.attach(self.engine)
 
-    def step(self, images, labels):
+    def invalidate(self):
+        self.engine.bf16_fresh = False
+        self._graphs.clear()
+        self._eager_done.clear()
+
+    @property
+    def correct_count(self):
+        """int32 device tensor: number of argmax-correct samples in the last step (no host sync)."""
+        return self._correct
+
+    def _step_body(self, images, labels):
         eng = self.engine
-        if not images.is_cuda:
-            images = images.cuda(non_blocking=True)
-        if not labels.is_cuda:
-            labels = labels.cuda(non_blocking=True)
-        eng.ensure_bound()
-        if self._loss is None or self._loss.device != eng.flat.device:
-            self._loss = torch.zeros(1, device=eng.flat.device, dtype=torch.float32)
-            self._correct = torch.zeros(1, device=eng.flat.device, dtype=torch.int32)
+        n0 = ops.LAUNCHES["n"]
         self.opt.zero_grad()
         self._loss.zero_()
+        self._correct.zero_()
         outs, ws = eng.forward(images, training=True, want="logits")
         B = images.shape[0]
         world = self.reducer.world_size if self.reducer is not None else 1
@@ -73,4 +91,44 @@ class Trainer:
         if self.reducer is not None:
             self.reducer.finish_step()
         self.opt.step()
+        self.launches_per_step = ops.LAUNCHES["n"] - n0   # libvitb200 kernels per step (graph replays launch the same set)
+
+    def step(self, images, labels):
+        eng = self.engine
+        eng.ensure_bound()
+        dev = eng.flat.device
+        self.opt._ensure_state()
+        if self._loss is None or self._loss.device != dev:
+            self._loss = torch.zeros(1, device=dev, dtype=torch.float32)
+            self._correct = torch.zeros(1, device=dev, dtype=torch.int32)
+        key = (tuple(images.shape), str(images.dtype))
+        if not self.use_cuda_graph:
+            if not images.is_cuda:
+                images = images.to(dev, non_blocking=True)
+            if not labels.is_cuda:
+                labels = labels.to(dev, non_blocking=True)
+            self._step_body(images.float() if images.dtype != torch.float32 else images, labels)
+            return self._loss
+        entry = self._graphs.get(key)
+        if entry is None:
+            s_img = torch.empty(images.shape, device=dev, dtype=torch.float32)
+            s_lab = torch.empty(labels.shape, device=dev, dtype=torch.int64)
+            s_img.copy_(images, non_blocking=True)
+            s_lab.copy_(labels, non_blocking=True)
+            if key not in self._eager_done:
+                self._eager_done.add(key)          # first step: eager (lazy allocations, cudaFuncSetAttribute, NCCL init)
+                self._step_body(s_img, s_lab)
+                return self._loss
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step_body(s_img, s_lab)
+            entry = (graph, s_img, s_lab)
+            self._graphs[key] = entry
+            graph.replay()
+            return self._loss
+        graph, s_img, s_lab = entry
+        s_img.copy_(images, non_blocking=True)
+        s_lab.copy_(labels, non_blocking=True)
+        graph.replay()
         return self._loss
