@@ -131,6 +131,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)   # a hung rank prints where it is stuck instead of burning the time limit
     import torch
     import torch.distributed as dist
     from vitb200 import ops
@@ -144,6 +146,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     reducer = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("VITB200_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=dev)
         from vitb200.dp import GradReducer
         reducer = GradReducer()
@@ -239,7 +244,7 @@ def main():
 
     # ---------------- roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch of one step ----------
     roofline = None
-    if rank == 0:
+    if True:  # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports
         peak, peak_sus, hbm, src = measured_peaks()
         rec = []
         orig = ops.gemm
@@ -259,7 +264,7 @@ def main():
         trainer.use_cuda_graph = False      # one eager step so that every GEMM launch can be bracketed by events
         trainer.step(images, labels)
         torch.cuda.synchronize()
-        trainer.use_cuda_graph = True
+        trainer.use_cuda_graph = (not args.no_graph) and reducer is None
         ops.gemm = orig
         gemm_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
         gemm_flops = sum(f for _, _, f in rec)
@@ -293,6 +298,7 @@ def main():
                 "final_loss": final_loss, "gpu_launches": launches, "clocks": sampler.summary(), "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -56,7 +56,8 @@ class Trainer:
         self.engine = model._get_engine()
         self.opt = FusedAdam(model, lr, betas, eps, weight_decay)
         self.reducer = reducer
-        self.use_cuda_graph = use_cuda_graph
+        # NCCL collectives on a side stream are launched eagerly (not captured): the graph path is single-GPU only
+        self.use_cuda_graph = use_cuda_graph and reducer is None
         self._loss = None
         self._correct = None
         self._graphs = {}   # batch shape -> (graph, static_images, static_labels)
