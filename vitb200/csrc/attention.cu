@@ -822,6 +822,8 @@ static int launch_short_bwd(const AttnParams& p, cudaStream_t st) {
     return VB_OK;
 }
 
+int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream);   // attention_tc.cu (tcgen05 path, S <= 256)
+
 static int check_common(const VbAttnDesc* d) {
     VB_REQUIRE(d != nullptr, "attention: null descriptor");
     VB_REQUIRE(d->head_dim == 64, "attention: head_dim %d unsupported (every reference config has 64)", d->head_dim);
@@ -857,6 +859,8 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (int rc = check_common(d)) return rc;
     const AttnParams p = to_params(d);
     if (d->S <= 256) {
+        const int tc = attention_fwd_tc(d, as_stream(stream));
+        if (tc <= 0) return tc;   // launched (0) or failed with an error (< 0); 1 = shape not handled there
         const int n_mt = (d->S + 15) / 16;
         cudaStream_t st = as_stream(stream);
         if (n_mt <= 6) return launch_short_fwd<3>(p, st);
