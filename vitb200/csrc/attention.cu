@@ -9,6 +9,7 @@
 // head-major copy is ever made; O is written token-major, ready to be the A operand of the out-proj GEMM.
 // Token row index = b * batch_stride + s * tok_stride (batch-first ViT: (S,1); sequence-first DETR: (1,N)).
 #include "common.h"
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 namespace vb {
@@ -823,6 +824,7 @@ static int launch_short_bwd(const AttnParams& p, cudaStream_t st) {
 }
 
 int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream);   // attention_tc.cu (tcgen05 path, S <= 256)
+int attention_bwd_tc(const VbAttnDesc* d, cudaStream_t stream);
 
 static int check_common(const VbAttnDesc* d) {
     VB_REQUIRE(d != nullptr, "attention: null descriptor");
@@ -888,6 +890,14 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     VB_REQUIRE(d->lddo % 8 == 0 && d->lddq % 8 == 0 && d->lddk % 8 == 0 && d->lddv % 8 == 0, "attention_bwd: row pitches must be multiples of 8");
     const AttnParams p = to_params(d);
     cudaStream_t st = as_stream(stream);
+    const char* tc_env = getenv("VITB200_ATTN_TC_BWD");
+    if (d->S <= 256 && d->tok_stride == 1 && !(tc_env && tc_env[0] == '0')) {
+        const long long nw = (long long)d->B * d->S * d->H;
+        attn_delta_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, st>>>(p);
+        VB_CUDA_CHECK(cudaGetLastError());
+        const int tc = attention_bwd_tc(d, st);
+        if (tc <= 0) return tc;
+    }
     if (d->S <= 256) {
         const int n_mt = (d->S + 15) / 16;
         if (n_mt <= 6) return launch_short_bwd<3>(p, st);
