@@ -891,7 +891,9 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     const AttnParams p = to_params(d);
     cudaStream_t st = as_stream(stream);
     const char* tc_env = getenv("VITB200_ATTN_TC_BWD");
-    if (d->S <= 256 && d->tok_stride == 1 && !(tc_env && tc_env[0] == '0')) {
+    // The tcgen05 backward (attention_tc.cu) is numerically validated but, being latency-bound on its TMEM slot
+    // hand-offs, not yet faster than the mma.sync kernel below: opt-in with VITB200_ATTN_TC_BWD=1.
+    if (d->S <= 256 && d->tok_stride == 1 && tc_env && tc_env[0] == '1') {
         const long long nw = (long long)d->B * d->S * d->H;
         attn_delta_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, st>>>(p);
         VB_CUDA_CHECK(cudaGetLastError());
