@@ -228,6 +228,8 @@ class VitEngine(FlatParams):
             ws["delta"] = e(B, H, S, dtype=f32)
             ws["dlogits"] = [torch.zeros(B, self.C_ld, device=dev, dtype=bf) for _ in range(2 if self.two_heads else 1)]
             ws["dy_tok"] = e(B * self.n_prefix, D)
+            ws["dh_cls"] = e(B, D)
+            ws["stat_cls"] = [e(B, dtype=f32), e(B, dtype=f32)]
             ws["possum"] = e(S, D, dtype=f32)
             ws["dxp"] = e(B * self.P, D)
         self._ws[key] = ws
@@ -348,17 +350,38 @@ class VitEngine(FlatParams):
         for li in range(L - 1, -1, -1):
             buf = ws["layer"][li]
             x_in = ws["x"][li].view(M, D)
-            # ---- MLP ----
-            self._wgrad(d_bf, buf["g"], (li, "fc2_w"))
-            ops.gemm(d_bf, self.w((li, "fc2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"])
-            self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"))
-            ops.colsum_bf16(ws["da"], self.gview((li, "fc1_b")))
-            ops.gemm(ws["da"], self.w((li, "fc1_w")), dh, b_major=1)
-            ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d2, dx=d2, dx_bf16=d_bf,
-                              dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")), dx_colsum=self.gview((li, "proj_b")))
-            # ---- attention ----
-            self._wgrad(d_bf, buf["o"], (li, "proj_w"))
-            ops.gemm(d_bf, self.w((li, "proj_w")), dh, b_major=1)
+            if li == L - 1 and want == "logits" and self.n_prefix == 1:
+                # ViT.forward only consumes x[:, 0] (vanilla_vit.py:212): the gradient entering the last block is non-zero
+                # on the class-token rows only, so its MLP / out-proj backward runs on B rows instead of B*S.  The rows are
+                # addressed in place through strided views (row pitch S * width); nothing is gathered.
+                Fd = self.F
+                d_c = d_bf.view(B, S, D)[:, 0, :]
+                da_c, dh_c = ws["da"][:B], ws["dh_cls"]
+                self._wgrad(d_c, buf["g"].view(B, S, Fd)[:, 0, :], (li, "fc2_w"))
+                ops.gemm(d_c, self.w((li, "fc2_w")), da_c, b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"].view(B, S, Fd)[:, 0, :])
+                self._wgrad(da_c, buf["h2"].view(B, S, D)[:, 0, :], (li, "fc1_w"))
+                ops.colsum_bf16(da_c, self.gview((li, "fc1_b")))
+                ops.gemm(da_c, self.w((li, "fc1_w")), dh_c, b_major=1)
+                ws["stat_cls"][0].copy_(buf["mean2"].view(B, S)[:, 0])
+                ws["stat_cls"][1].copy_(buf["rstd2"].view(B, S)[:, 0])
+                ops.layernorm_bwd(dh_c, buf["x1"][:, 0, :], ws["stat_cls"][0], ws["stat_cls"][1], self.f((li, "ln2_w")), dres=d[:, 0, :],
+                                  dx=d[:, 0, :], dx_bf16=d_c, dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")),
+                                  dx_colsum=self.gview((li, "proj_b")))
+                self._wgrad(d_c, buf["o"].view(B, S, D)[:, 0, :], (li, "proj_w"))
+                dh.zero_()
+                ops.gemm(d_c, self.w((li, "proj_w")), dh.view(B, S, D)[:, 0, :], b_major=1)
+            else:
+                # ---- MLP ----
+                self._wgrad(d_bf, buf["g"], (li, "fc2_w"))
+                ops.gemm(d_bf, self.w((li, "fc2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"])
+                self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"))
+                ops.colsum_bf16(ws["da"], self.gview((li, "fc1_b")))
+                ops.gemm(ws["da"], self.w((li, "fc1_w")), dh, b_major=1)
+                ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d2, dx=d2, dx_bf16=d_bf,
+                                  dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")), dx_colsum=self.gview((li, "proj_b")))
+                # ---- attention ----
+                self._wgrad(d_bf, buf["o"], (li, "proj_w"))
+                ops.gemm(d_bf, self.w((li, "proj_w")), dh, b_major=1)
             qkv, dqkv = buf["qkv"], ws["dqkv"]
             ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"], dh, dqkv[:, :D], dqkv[:, D:2 * D],
                               dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S)
