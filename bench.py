@@ -73,7 +73,8 @@ class ClockSampler(threading.Thread):
 
 
 def oracle_cpu_step_rate(batch, steps, warmup, threads=None):
-    """The reference's CPU path (oracle port): fp32 forward + cross-entropy + backward of ViT-B/16; images/sec."""
+    """The reference's CPU path (oracle port): fp32 zero_grad + forward + cross-entropy + backward + Adam of ViT-B/16
+    (the loop body of vanilla_vit.py:235-239); images/sec."""
     import torch
     from oracle import vit_oracle as O
     if threads:
@@ -83,13 +84,14 @@ def oracle_cpu_step_rate(batch, steps, warmup, threads=None):
     images = O.seeded_images(batch, CFG["image_size"], 1)
     labels = O.seeded_labels(batch, CFG["num_classes"], 2)
     kw = dict(patch_size=CFG["patch_size"], num_layers=CFG["num_layers"], num_heads=CFG["num_heads"])
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-4)      # vanilla_vit.py:221
     times = []
     for i in range(warmup + steps):
-        for v in sd.values():
-            v.grad = None
         t0 = time.perf_counter()
+        opt.zero_grad()
         loss = torch.nn.functional.cross_entropy(O.vit_forward(sd, images, **kw), labels)
         loss.backward()
+        opt.step()
         t1 = time.perf_counter()
         if i >= warmup:
             times.append(t1 - t0)
@@ -105,7 +107,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 5))
     warmup = 1
     ips, dt, cores = oracle_cpu_step_rate(batch, steps, warmup)
-    sample = f"{steps} timed fwd+bwd steps of batch {batch} (fp32, PyTorch CPU ops the reference dispatches to), {warmup} warm-up"
+    sample = f"{steps} timed fwd+CE+bwd+Adam steps of batch {batch} (fp32, PyTorch CPU ops the reference dispatches to), {warmup} warm-up"
     line = {"impl": "reference", "metric": "ViT-B/16 train images/sec", "value": ips, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -269,8 +271,19 @@ def main():
         gemm_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
         gemm_flops = sum(f for _, _, f in rec)
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
+        # DRAM traffic per launch from the committed ncu --set full capture of the six representative ViT-B launches
+        # (profiles/r1_gemm_ncu.json; each shape occurs 12x per step, the wgrad shape stands for the 4 wgrad GEMMs per layer)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_gemm_ncu.json")) as fh:
+                prof = json.load(fh)
+            traffic = sum(p["dram_bytes"] for p in prof) / len(prof)
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "vb::gemm_kernel (tcgen05, all launches of one step)", "achieved": achieved,
-                    "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus, "traffic": None,
+                    "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus, "traffic": traffic,
+                    "traffic_note": "mean dram read+write bytes per launch over the 6 profiled ViT-B/16 GEMM shapes (ncu --set full, "
+                                    "profiles/r1_gemm_ncu_summary.txt); algorithmic bytes of the same launches are within 0.82-1.02x",
                     "peak_kind": f"bf16_tflops_sustained ({src}); burst peak {peak}", "frac_of_burst": achieved / peak,
                     "launches_per_step": len(rec), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / K),
                     "algorithmic_gflop_per_launch_avg": gemm_flops / len(rec) / 1e9}
@@ -280,7 +293,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ips, dt, cores = oracle_cpu_step_rate(8, 2, 1)
         cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
-               "sample": "2 timed fwd+bwd steps of batch 8 after 1 warm-up, fp32 oracle (PyTorch CPU ops the reference dispatches to)"}
+               "sample": "2 timed fwd+CE+bwd+Adam steps of batch 8 after 1 warm-up, fp32 oracle (PyTorch CPU ops the reference dispatches to)"}
 
     if rank == 0:
         step_tflops = value / world * TRAIN_GFLOP_PER_IMAGE / 1e3

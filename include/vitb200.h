@@ -60,10 +60,10 @@ VB_API int vb_sm_count(int device);          /* number of SMs, or a negative err
  */
 enum {
     VB_EPI_STORE = 0,    /* C = acc + bias                                                */
-    VB_EPI_GELU = 1,     /* C = acc + bias (pre-activation, optional), C2 = gelu_erf(C)   */
+    VB_EPI_GELU = 1,     /* x = acc + bias; C2 = gelu_erf(x); C (optional) = gelu_erf'(x)  */
     VB_EPI_RESIDUAL = 2, /* C = acc + bias + AUX                                          */
     VB_EPI_RELU = 3,     /* C = max(acc + bias, 0)                                        */
-    VB_EPI_DGELU = 4,    /* C = acc * gelu_erf'(AUX)        (AUX = saved pre-activation)  */
+    VB_EPI_DGELU = 4,    /* C = acc * AUX                   (AUX = gelu'(x) saved by VB_EPI_GELU) */
     VB_EPI_DRELU = 5,    /* C = AUX > 0 ? acc : 0           (AUX = saved relu output)     */
     VB_EPI_ACCUM = 6     /* C += acc  (fp32 C, TMA reduce-add; used by wgrad and split-K) */
 };

@@ -48,7 +48,7 @@ def case(name, M, N, K, a_major, b_major, epi, cdt, *, bias=False, split=1, dire
         refs = [ref]
     elif epi == ops.EPI_GELU:
         C2 = torch.full((M, ldc), float("nan"), device=dev, dtype=odt)[:, :N]
-        refs = [ref, gelu(ref)]
+        refs = [dgelu(ref), gelu(ref)]
     elif epi == ops.EPI_RESIDUAL:
         aux = torch.randn(M, ldc, device=dev, dtype=odt)[:, :N]
         refs = [ref + aux.float()]
@@ -56,7 +56,7 @@ def case(name, M, N, K, a_major, b_major, epi, cdt, *, bias=False, split=1, dire
         refs = [torch.relu(ref)]
     elif epi == ops.EPI_DGELU:
         aux = torch.randn(M, ldc, device=dev).to(odt)[:, :N]
-        refs = [ref * dgelu(aux.float())]
+        refs = [ref * aux.float()]
     elif epi == ops.EPI_DRELU:
         aux = torch.randn(M, ldc, device=dev).to(odt)[:, :N]
         refs = [torch.where(aux.float() > 0, ref, torch.zeros_like(ref))]

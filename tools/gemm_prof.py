@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vitb200 import ops
 torch.manual_seed(0)
-M = 64 * 197
+M = int(os.environ.get("VB_PROF_B", "256")) * 197
 dev = "cuda"
 x768 = torch.randn(M, 768, device=dev).bfloat16()
 x3072 = torch.randn(M, 3072, device=dev).bfloat16()
@@ -20,7 +20,7 @@ a = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
 g = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
 da = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
 dw = torch.zeros(3072, 768, device=dev)
-for _ in range(3):
+for _ in range(2):
     ops.gemm(x768, w_qkv, qkv, bias=bias[2304])
     ops.gemm(x768, w_o, o32, epilogue=ops.EPI_RESIDUAL, bias=bias[768], aux=res)
     ops.gemm(x768, w_1, a, C2=g, epilogue=ops.EPI_GELU, bias=bias[3072])

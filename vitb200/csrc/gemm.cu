@@ -415,10 +415,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float gl[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if constexpr (EPI == VB_EPI_GELU) gl[j] = gelu_erf(v[j]);
+                        if constexpr (EPI == VB_EPI_GELU) {   // C2 = gelu(x); C = gelu'(x) (what the backward epilogue multiplies by)
+                            float cdf, e;
+                            phi_parts(v[j], cdf, e);
+                            gl[j] = v[j] * cdf;
+                            v[j] = fmaf(v[j] * 0.39894228040143268f, e, cdf);
+                        }
                         if constexpr (EPI == VB_EPI_RESIDUAL) v[j] += x[j];
                         if constexpr (EPI == VB_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
-                        if constexpr (EPI == VB_EPI_DGELU) v[j] *= dgelu_erf(x[j]);
+                        if constexpr (EPI == VB_EPI_DGELU) v[j] *= x[j];   // AUX = gelu'(pre-activation), saved by the forward epilogue
                         if constexpr (EPI == VB_EPI_DRELU) v[j] = x[j] > 0.f ? v[j] : 0.f;
                     }
                     // ---- registers -> swizzled staging buffer (or straight to global on the bring-up path) ----
