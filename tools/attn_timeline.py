@@ -1,0 +1,32 @@
+"""In-kernel cycle stamps of the tcgen05 attention backward (CTA 0): where does an item's time go?"""
+import os, sys
+os.environ["VITB200_ATTN_TC_BWD"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vitb200 import ops, _lib
+B, H, S = 64, 12, 197
+D = H * 64
+M = B * S
+torch.manual_seed(0)
+qkv = torch.randn(M, 3 * D, device="cuda").bfloat16()
+o = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+lse = torch.empty(B, H, S, device="cuda")
+do = torch.randn(M, D, device="cuda").bfloat16()
+dqkv = torch.empty_like(qkv)
+delta = torch.empty(B, H, S, device="cuda")
+q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+ops.attention_fwd(q, k, v, o, lse, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
+dbg = torch.zeros(64 * 16, device="cuda", dtype=torch.int64)
+lib = _lib.load()
+for rep in range(2):
+    dbg.zero_()
+    lib.vb_debug_set_attn_timeline(dbg.data_ptr())
+    ops.attention_bwd(q, k, v, o, lse, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], delta, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
+    torch.cuda.synchronize()
+lib.vb_debug_set_attn_timeline(None)
+t = dbg.view(64, 16).cpu()
+t0 = t[0, 0].item()
+print("item: mma[tile_free->scores issued | ->p_full seen | ->out issued]  ew[s_full seen | elementwise done | o_full seen | readout done]  (cycles from start)")
+for i in range(12):
+    r = [(x.item() - t0) for x in t[i, :8]]
+    print(f"{i:2d}: mma {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | ew {r[4]:7d} {r[5]:7d} {r[6]:7d} {r[7]:7d}   item total {r[7]-r[0]:6d}  scoreMMA+wake {r[4]-r[1]:5d} elem {r[5]-r[4]:5d} p_full->mma {r[2]-r[5]:5d} outMMA+wake {r[6]-r[3]:5d} readout {r[7]-r[6]:5d}")
