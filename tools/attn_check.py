@@ -1,0 +1,45 @@
+"""Attention backward: tcgen05 five-product kernel vs the mma.sync kernel vs an fp32 PyTorch reference, several shapes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vitb200 import ops
+
+
+def run(B, H, S, mode):
+    os.environ["VITB200_ATTN_TC_BWD"] = mode
+    D = H * 64
+    M = B * S
+    g = torch.Generator(device="cuda").manual_seed(S * 131 + B)
+    qkv = (torch.randn(M, 3 * D, device="cuda", generator=g) * 1.5).bfloat16()
+    do = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    o = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, S, device="cuda")
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(B, H, S, device="cuda")
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    ops.attention_fwd(q, k, v, o, lse, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
+    ops.attention_bwd(q, k, v, o, lse, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], delta, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
+    torch.cuda.synchronize()
+    # fp32 reference
+    qf, kf, vf = [t.float().view(B, S, H, 64).transpose(1, 2).requires_grad_(True) for t in (q, k, v)]
+    of = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf)
+    of.backward(do.float().view(B, S, H, 64).transpose(1, 2))
+    ref = torch.cat([t.grad.transpose(1, 2).reshape(M, D) for t in (qf, kf, vf)], dim=1)
+    return dqkv.float(), ref
+
+
+ok = True
+for (B, H, S) in [(2, 3, 197), (3, 2, 198), (2, 4, 65), (1, 2, 128), (2, 2, 129), (1, 3, 208), (2, 1, 16), (1, 1, 192), (2, 2, 144), (37, 12, 197)]:
+    a, ref = run(B, H, S, "5")
+    b, _ = run(B, H, S, "0")
+    D = H * 64
+    errs = []
+    for i, name in enumerate("qkv"):
+        sl = slice(i * D, (i + 1) * D)
+        ea = ((a[:, sl] - ref[:, sl]).norm() / ref[:, sl].norm()).item()
+        eb = ((b[:, sl] - ref[:, sl]).norm() / ref[:, sl].norm()).item()
+        errs.append((name, ea, eb))
+    bad = any(not (ea < 2e-2) for _, ea, _ in errs)
+    ok &= not bad
+    print(f"B={B} H={H} S={S}: " + "  ".join(f"d{n}: tc5 {ea:.2e} mma {eb:.2e}" for n, ea, eb in errs) + ("  FAIL" if bad else ""))
+print("ALL OK" if ok else "FAILED")

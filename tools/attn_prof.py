@@ -1,9 +1,9 @@
-"""Small attention-only workload for ncu: B=64, H=12, S=197, forward + backward, 3 iterations."""
+"""Small attention-only workload for ncu: H=12, S=197, forward + backward, 3 iterations.  Usage: attn_prof.py [B]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vitb200 import ops
-B, H, S = 64, 12, 197
+B, H, S = (int(sys.argv[1]) if len(sys.argv) > 1 else 64), 12, 197
 D = H * 64
 M = B * S
 torch.manual_seed(0)

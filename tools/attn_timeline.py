@@ -4,7 +4,8 @@ os.environ["VITB200_ATTN_TC_BWD"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vitb200 import ops, _lib
-B, H, S = 64, 12, 197
+import sys
+B, H, S = (int(sys.argv[1]) if len(sys.argv) > 1 else 256), 12, 197
 D = H * 64
 M = B * S
 torch.manual_seed(0)
@@ -27,6 +28,8 @@ lib.vb_debug_set_attn_timeline(None)
 t = dbg.view(64, 16).cpu()
 t0 = t[0, 0].item()
 print("item: mma[tile_free->scores issued | ->p_full seen | ->out issued]  ew[s_full seen | elementwise done | o_full seen | readout done]  (cycles from start)")
-for i in range(12):
+prev_end = 0
+for i in range(42):
     r = [(x.item() - t0) for x in t[i, :8]]
-    print(f"{i:2d}: mma {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | ew {r[4]:7d} {r[5]:7d} {r[6]:7d} {r[7]:7d}   item total {r[7]-r[0]:6d}  scoreMMA+wake {r[4]-r[1]:5d} elem {r[5]-r[4]:5d} p_full->mma {r[2]-r[5]:5d} outMMA+wake {r[6]-r[3]:5d} readout {r[7]-r[6]:5d}")
+    gap = r[0] - prev_end; prev_end = r[7]
+    print(f"{i:2d}: gap {gap:6d} mma {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | ew {r[4]:7d} {r[5]:7d} {r[6]:7d} {r[7]:7d}   item total {r[7]-r[0]:6d}  scoreMMA+wake {r[4]-r[1]:5d} elem {r[5]-r[4]:5d} p_full->mma {r[2]-r[5]:5d} outMMA+wake {r[6]-r[3]:5d} readout {r[7]-r[6]:5d}")

@@ -238,24 +238,45 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]; one warp per (token, head).
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d].  Eight lanes per (token, head): each loads 16 bytes of O and dO
+// (a warp covers 4 consecutive heads = 512 contiguous bytes per tensor), 3 shuffle steps; 4 units in flight per thread.
+// HBM-bound: 2 x 128 B read + 4 B written per (token, head).
 // ----------------------------------------------------------------------------------------------------------
-__global__ void attn_delta_kernel(const AttnParams p) {
-    const int lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256) attn_delta_kernel(const AttnParams p) {
     const long long total = (long long)p.B * p.S * p.H;
-    if (wid >= total) return;
-    const int h = wid % p.H;
-    const long long bs = wid / p.H;
-    const int s = bs % p.S;
-    const int b = bs / p.S;
-    const long long row = (long long)b * p.batch_stride + (long long)s * p.tok_stride;
-    const uint32_t ov = *reinterpret_cast<const uint32_t*>(p.o + row * p.ldo + h * HD + lane * 2);
-    const uint32_t dv = *reinterpret_cast<const uint32_t*>(p.dout + row * p.lddo + h * HD + lane * 2);
-    float acc = __uint_as_float(ov << 16) * __uint_as_float(dv << 16) + __uint_as_float(ov & 0xFFFF0000u) * __uint_as_float(dv & 0xFFFF0000u);
+    const int sub = threadIdx.x & 7;
+    const long long units_per_iter = (long long)gridDim.x * (blockDim.x >> 3);
+    long long u0 = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    for (; u0 < total; u0 += 4 * units_per_iter) {
+        uint4 ov[4], dv[4];
+        long long didx[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) p.delta[((long long)b * p.H + h) * p.S + s] = acc;
+        for (int i = 0; i < 4; ++i) {
+            const long long u = u0 + i * units_per_iter;
+            const bool ok = u < total;
+            const long long uu = ok ? u : 0;
+            const int h = (int)(uu % p.H);
+            const long long bs = uu / p.H;
+            const int s = (int)(bs % p.S);
+            const int b = (int)(bs / p.S);
+            const long long row = (long long)b * p.batch_stride + (long long)s * p.tok_stride;
+            ov[i] = __ldg(reinterpret_cast<const uint4*>(p.o + row * p.ldo + h * HD + sub * 8));
+            dv[i] = __ldg(reinterpret_cast<const uint4*>(p.dout + row * p.lddo + h * HD + sub * 8));
+            didx[i] = ok ? ((long long)b * p.H + h) * p.S + s : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t oo[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w}, dd[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                acc += __uint_as_float(oo[j] << 16) * __uint_as_float(dd[j] << 16) + __uint_as_float(oo[j] & 0xFFFF0000u) * __uint_as_float(dd[j] & 0xFFFF0000u);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (sub == 0 && didx[i] >= 0) p.delta[didx[i]] = acc;
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -823,8 +844,16 @@ static int launch_short_bwd(const AttnParams& p, cudaStream_t st) {
     return VB_OK;
 }
 
+// one thread block covers 32 (token, head) units per iteration, 4 iterations in flight
+static unsigned delta_grid(long long units) {
+    long long g = (units + 127) / 128;
+    const long long cap = (long long)num_sms() * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
 int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream);   // attention_tc.cu (tcgen05 path, S <= 256)
 int attention_bwd_tc(const VbAttnDesc* d, cudaStream_t stream);
+int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream);   // attention_bwd_tc.cu (five-product tcgen05 path, S <= 208)
 
 static int check_common(const VbAttnDesc* d) {
     VB_REQUIRE(d != nullptr, "attention: null descriptor");
@@ -890,15 +919,23 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     VB_REQUIRE(d->lddo % 8 == 0 && d->lddq % 8 == 0 && d->lddk % 8 == 0 && d->lddv % 8 == 0, "attention_bwd: row pitches must be multiples of 8");
     const AttnParams p = to_params(d);
     cudaStream_t st = as_stream(stream);
+    // S <= 208 without a key-padding mask (every ViT / DeiT config): five-product tcgen05 backward (attention_bwd_tc.cu).
+    // VITB200_ATTN_TC_BWD=0 selects the mma.sync kernels below, =3 the older seven-product tcgen05 kernel (attention_tc.cu).
     const char* tc_env = getenv("VITB200_ATTN_TC_BWD");
-    // The tcgen05 backward (attention_tc.cu) is numerically validated but, being latency-bound on its TMEM slot
-    // hand-offs, not yet faster than the mma.sync kernel below: opt-in with VITB200_ATTN_TC_BWD=1.
-    if (d->S <= 256 && d->tok_stride == 1 && tc_env && tc_env[0] == '1') {
+    const char tc_mode = tc_env ? tc_env[0] : '5';
+    if (d->S <= 256 && d->tok_stride == 1 && tc_mode != '0') {
         const long long nw = (long long)d->B * d->S * d->H;
-        attn_delta_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, st>>>(p);
-        VB_CUDA_CHECK(cudaGetLastError());
-        const int tc = attention_bwd_tc(d, st);
-        if (tc <= 0) return tc;
+        if (tc_mode == '3') {
+            attn_delta_kernel<<<delta_grid(nw), 256, 0, st>>>(p);
+            VB_CUDA_CHECK(cudaGetLastError());
+            const int tc = attention_bwd_tc(d, st);
+            if (tc <= 0) return tc;
+        } else if (d->S <= 208 && d->key_padding_mask == nullptr) {
+            attn_delta_kernel<<<delta_grid(nw), 256, 0, st>>>(p);
+            VB_CUDA_CHECK(cudaGetLastError());
+            const int tc = attention_bwd_tc5(d, st);
+            if (tc <= 0) return tc;
+        }
     }
     if (d->S <= 256) {
         const int n_mt = (d->S + 15) / 16;
@@ -915,7 +952,7 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
         configured = true;
     }
     const long long nwarps = (long long)d->B * d->S * d->H;
-    attn_delta_kernel<<<(unsigned)((nwarps + 7) / 8), 256, 0, st>>>(p);
+    attn_delta_kernel<<<delta_grid(nwarps), 256, 0, st>>>(p);
     VB_CUDA_CHECK(cudaGetLastError());
     dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
     attn_bwd_dkdv_kernel<<<grid, 128, smem, st>>>(p);

@@ -1,0 +1,500 @@
+// tcgen05 / TMEM attention backward for short sequences (S <= 208: every ViT / DeiT config), head_dim 64.
+//
+// Five matrix products per head, P computed once (rows = keys):
+//   per 128-key tile t:   S^T = K_t Q^T,  dP^T = V_t dO^T                  (SS MMAs, N = npad, fp32 in TMEM)
+//     element-wise        P^T = exp2(S^T c - lse[q]),  dS^T = P^T o (dP^T - delta[q])
+//                         P^T  -> packed bf16 written over the S^T columns (A operand of dV, read from TMEM)
+//                         dS^T -> bf16 [key][query] staging tile in shared memory (A operand of dK and dQ)
+//     dV_t  = P^T dO            (TS MMA)         dK_t = dS^T Q / 8   (SS MMA, staging read K-major)
+//     dQ   += dS K_t / 8        (SS MMA, the same staging tile read MN-major; accumulated over the key tiles)
+// One persistent CTA per SM walks (batch, head) pairs.  Q / dO (whole head) and K_t / V_t (per key tile) arrive by TMA in
+// two 2-stage rings, so the loads of the next tile / head overlap the math of the current one.
+//
+// TMEM map (512 columns): [0,208) S^T, the packed P^T of 16-query group g overwrites columns [16g, 16g+8); [208,416) dP^T ->
+// once the queries < 128 are consumed the dead columns hold the dV [208,272) and dK [272,336) accumulators, and after the
+// whole element-wise pass the second-query-tile dQ accumulator [336,400); [448,512) is the dQ accumulator of query tile 0,
+// which persists across the key tiles.  The dQ contribution of key tile 0 to query tile 1 is carried in registers (the
+// TMEM budget is 32 columns short of keeping it resident).
+// The fourth 64-query staging block (queries 192..207) aliases the V_t buffer, which is dead once dP^T is complete.
+// Pipelining inside a tile: scores and the element-wise pass are split at query 128 (two commit / arrive points each),
+// so the second-stage products of the first part overlap the element-wise work on the second.  Accumulators are read out
+// into the dead K_t / V_t / Q buffers and leave by TMA store issued from a dedicated warp.
+//
+// Replaces the autograd of F.scaled_dot_product_attention reached from nn.MultiheadAttention (vanilla_vit.py:77,
+// torch/nn/functional.py:6676-6688).  delta = rowsum(dO o O) comes from attn_delta_kernel (attention.cu).
+#include <cuda.h>
+#include <cstdlib>
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+int make_tmap_3d(CUtensorMap* m, int dtype, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
+                 uint64_t batch_stride_elems, uint32_t box0, uint32_t box1);   // gemm.cu
+
+namespace bwd5 {
+
+constexpr int kEwWarps = 12;                           // element-wise / read-out warps (3 per TMEM lane quadrant)
+constexpr int kThreads = 128 + kEwWarps * 32;          // warps 0-3: TMA, MMA, TMEM alloc, stats
+constexpr uint32_t kMaxQ = 208;                        // padded queries / keys per head
+constexpr uint32_t kBlk = 128 * 128;                   // one 64-wide staging block / K_t / V_t tile: 128 rows x 128 B
+constexpr uint32_t kQBytes = kMaxQ * 128;              // Q or dO of one head
+constexpr uint32_t kStagingOff = 0;                    // 3 blocks (queries 0..191); block 3 aliases V_t
+constexpr uint32_t kQdoOff = 3 * kBlk;                 // 2 stages x {Q, dO}
+constexpr uint32_t kKvOff = kQdoOff + 4 * kQBytes;     // 2 stages x {K_t, V_t}
+constexpr uint32_t kStatsOff = kKvOff + 4 * kBlk;      // 2 stages x {-lse[208], delta[208]} fp32
+constexpr uint32_t kBarOff = kStatsOff + 2 * 2 * kMaxQ * 4;
+constexpr uint32_t kSmemBytes = kBarOff + 256 + 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+
+constexpr uint32_t kColST = 0, kColDPT = 208, kColDV = 208, kColDK = 272, kColDQ1 = 336, kColDQ0 = 448;
+
+struct Args {
+    long long* dbg;
+    int B, H, S, npad, nks, n_t, total_heads;
+    float scale, scale_log2;
+    const float* lse;
+    const float* delta;
+    long long batch_stride;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// Explicit shared-space accesses with 32-bit addresses (generic-pointer arithmetic costs 64-bit adds per access).  The
+// loads are volatile on purpose: they keep their program order relative to the (volatile) tcgen05.ld of the NEXT column
+// group, so the math that depends on them cannot be hoisted above that prefetch.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key)
+__device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_t (&dv)[16], uint32_t nls, uint32_t dls, float c,
+                                         uint32_t (&pp)[8], uint32_t (&pd)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 l4 = lds128(nls + 16 * i);
+        const float4 d4 = lds128(dls + 16 * i);
+        const float p0 = ex2f(fmaf(__uint_as_float(sv[4 * i + 0]), c, l4.x));
+        const float p1 = ex2f(fmaf(__uint_as_float(sv[4 * i + 1]), c, l4.y));
+        const float p2 = ex2f(fmaf(__uint_as_float(sv[4 * i + 2]), c, l4.z));
+        const float p3 = ex2f(fmaf(__uint_as_float(sv[4 * i + 3]), c, l4.w));
+        pp[2 * i] = pack2(p0, p1);
+        pp[2 * i + 1] = pack2(p2, p3);
+        pd[2 * i] = pack2(p0 * (__uint_as_float(dv[4 * i + 0]) - d4.x), p1 * (__uint_as_float(dv[4 * i + 1]) - d4.y));
+        pd[2 * i + 1] = pack2(p2 * (__uint_as_float(dv[4 * i + 2]) - d4.z), p3 * (__uint_as_float(dv[4 * i + 3]) - d4.w));
+    }
+}
+
+// NKS_T > 0: number of 16-query steps known at compile time (fully unrolled MMA issue); NKS_T == 0: generic.
+template <int NKS_T>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                    const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                    const __grid_constant__ CUtensorMap tmDV, const Args args) {
+#if defined(__CUDA_ARCH_FEAT_SM100_ALL)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* stats = reinterpret_cast<float*>(smem + kStatsOff);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+    uint64_t* qdo_full = bars;        // [2] count 2: TMA expect_tx + stats warp
+    uint64_t* qdo_empty = bars + 2;   // [2] store warp: the head's dQ tiles (parked in the Q / dO stage) have left
+    uint64_t* kv_full = bars + 4;     // [2]
+    uint64_t* kv_empty = bars + 6;    // [2] store warp: the tile's dV / dK tiles (parked in the K_t / V_t stage) have left
+    uint64_t* s_full = bars + 8;      // [2] scores of queries < 128 / >= 128 complete
+    uint64_t* p_full = bars + 10;     // [2] count kEwWarps: element-wise pass over queries < 128 / all queries done
+    uint64_t* o_full = bars + 12;
+    uint64_t* tile_free = bars + 13;  // count kEwWarps: accumulators read out, TMEM free for the next tile's scores
+    uint64_t* out_ready = bars + 14;  // count kEwWarps: output tiles staged in shared memory
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const uint32_t warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = args.S, n_t = args.n_t;
+    const int nks = NKS_T ? NKS_T : args.nks;
+    const int npad = nks * 16;
+    const int jA = nks < 8 ? nks : 8;          // 16-query groups of the first part (queries < 128)
+    const bool has_q1 = npad > 128;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+        tma_prefetch_desc(&tmDQ); tma_prefetch_desc(&tmDK); tma_prefetch_desc(&tmDV);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qdo_full[i], 2); mbar_init(&qdo_empty[i], 1);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], kEwWarps);
+        }
+        mbar_init(o_full, 1); mbar_init(tile_free, kEwWarps); mbar_init(out_ready, kEwWarps);
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) tmem_alloc<512>(tmem_ptr_smem);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {   // ---------------- TMA loader ----------------
+            int hc = 0, ic = 0;
+            for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
+                const int qs = hc & 1, b = head / args.H, h = head - b * args.H;
+                mbar_wait(&qdo_empty[qs], ((hc >> 1) & 1) ^ 1);
+                uint8_t* qb = smem + kQdoOff + qs * 2 * kQBytes;
+                mbar_arrive_expect_tx(&qdo_full[qs], 2 * npad * 128);
+                tma_load_3d(qb, &tmQ, &qdo_full[qs], h * 64, 0, b);
+                tma_load_3d(qb + kQBytes, &tmdO, &qdo_full[qs], h * 64, 0, b);
+                for (int t = 0; t < n_t; ++t, ++ic) {
+                    const int ks = ic & 1;
+                    mbar_wait(&kv_empty[ks], ((ic >> 1) & 1) ^ 1);
+                    uint8_t* kb = smem + kKvOff + ks * 2 * kBlk;
+                    mbar_arrive_expect_tx(&kv_full[ks], 2 * kBlk);
+                    tma_load_3d(kb, &tmK, &kv_full[ks], h * 64, t * 128, b);
+                    tma_load_3d(kb + kBlk, &tmV, &kv_full[ks], h * 64, t * 128, b);
+                }
+            }
+        }
+    } else if (warp_idx == 3) {
+        // ---------------- -lse / delta loader (whole warp) ----------------
+        int hc = 0;
+        for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
+            const int qs = hc & 1;
+            mbar_wait(&qdo_empty[qs], ((hc >> 1) & 1) ^ 1);
+            float* nl = stats + qs * 2 * kMaxQ;
+            float* dl = nl + kMaxQ;
+            const float* gl = args.lse + (long long)head * S;
+            const float* gd = args.delta + (long long)head * S;
+            // all loads first (independent, one round trip), then the shared-memory writes
+            float lv[7], dv[7];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                const int i = lane + 32 * r;
+                lv[r] = i < S ? -__ldg(gl + i) : -INFINITY;   // -inf => P = 0 for padded queries
+                dv[r] = i < S ? __ldg(gd + i) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                const int i = lane + 32 * r;
+                if (i < (int)kMaxQ) { nl[i] = lv[r]; dl[i] = dv[r]; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qdo_full[qs]);
+        }
+    } else if (warp_idx == 2) {
+        // ---------------- store warp: output tiles (shared memory) -> global by TMA, then recycle the buffers ----------------
+        int hc = 0, ic = 0;
+        for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
+            const int qs = hc & 1, b = head / args.H, h = head - b * args.H;
+            for (int t = 0; t < n_t; ++t, ++ic) {
+                const int ks = ic & 1;
+                mbar_wait(out_ready, ic & 1);
+                if (lane == 0) {
+                    uint8_t* kb = smem + kKvOff + ks * 2 * kBlk;
+                    tma_store_3d(&tmDV, kb, h * 64, t * 128, b);
+                    tma_store_3d(&tmDK, kb + kBlk, h * 64, t * 128, b);
+                    if (t == n_t - 1) {
+                        uint8_t* qb = smem + kQdoOff + qs * 2 * kQBytes;
+                        tma_store_3d(&tmDQ, qb, h * 64, 0, b);
+                        if (has_q1) tma_store_3d(&tmDQ, qb + kBlk, h * 64, 128, b);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                    mbar_arrive(&kv_empty[ks]);
+                    if (t == n_t - 1) mbar_arrive(&qdo_empty[qs]);
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    } else if (warp_idx == 1) {
+        // ---------------- MMA issuer: the whole warp walks the loops (uniform control flow, descriptors in uniform
+        // registers); one elected lane issues the tcgen05 instructions ----------------
+        const int nA = jA * 16, nB = npad - nA;
+        const uint32_t idesc_sA = umma_idesc_bf16(128, nA, 0, 0);
+        const uint32_t idesc_sB = umma_idesc_bf16(128, nB > 0 ? nB : 16, 0, 0);
+        constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, 0, 1);   // A K-major (or TMEM), B MN-major
+        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major
+        constexpr uint64_t kdesc = umma_smem_desc_base(0, 1024);        // K-major SW128
+        constexpr uint64_t mdesc = umma_smem_desc_base(kBlk, 1024);     // MN-major SW128, 64-wide atoms one block apart
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t stg = smem_u32(smem + kStagingOff);
+        int hc = 0, ic = 0;
+        for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
+            const int qs = hc & 1;
+            mbar_wait(&qdo_full[qs], (hc >> 1) & 1);
+            const uint32_t sQ = smem_u32(smem + kQdoOff + qs * 2 * kQBytes), sdO = sQ + kQBytes;
+            for (int t = 0; t < n_t; ++t, ++ic) {
+                const int ks = ic & 1;
+                const uint32_t sK = smem_u32(smem + kKvOff + ks * 2 * kBlk), sV = sK + kBlk;
+                mbar_wait(&kv_full[ks], (ic >> 1) & 1);
+                mbar_wait(tile_free, (ic & 1) ^ 1);
+                tcgen05_fence_after();
+                const bool dbg_on = args.dbg && blockIdx.x == 0 && ic < 64 && lane == 0;
+                if (dbg_on) args.dbg[ic * 16 + 0] = clock64();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tb + kColST, umma_smem_desc(kdesc, sK + k * 32), umma_smem_desc(kdesc, sQ + k * 32), idesc_sA, k > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tb + kColDPT, umma_smem_desc(kdesc, sV + k * 32), umma_smem_desc(kdesc, sdO + k * 32), idesc_sA, k > 0 ? 1u : 0u);
+                    umma_commit(&s_full[0]);
+                    if (nB > 0) {   // queries >= 128: rows 128.. of Q / dO, columns 128.. of the score regions
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss(tb + kColST + 128, umma_smem_desc(kdesc, sK + k * 32), umma_smem_desc(kdesc, sQ + kBlk + k * 32), idesc_sB, k > 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss(tb + kColDPT + 128, umma_smem_desc(kdesc, sV + k * 32), umma_smem_desc(kdesc, sdO + kBlk + k * 32), idesc_sB, k > 0 ? 1u : 0u);
+                        umma_commit(&s_full[1]);
+                    }
+                }
+                __syncwarp();
+                if (dbg_on) args.dbg[ic * 16 + 1] = clock64();
+                const uint64_t bd_do = umma_smem_desc(mdesc, sdO), bd_q = umma_smem_desc(mdesc, sQ), bd_k = umma_smem_desc(mdesc, sK);
+                const uint64_t ad_q0 = umma_smem_desc(mdesc, stg);
+                const uint64_t ad_q1 = umma_smem_desc(umma_smem_desc_base(sV - (stg + 2 * kBlk), 1024), stg + 2 * kBlk);
+                const uint64_t ad_k = umma_smem_desc(kdesc, stg), ad_kv = umma_smem_desc(kdesc, sV);
+                const int ksteps = (min(npad - t * 128, 128)) >> 4;
+                // ---- first part: queries < 128 ----
+                mbar_wait(&p_full[0], ic & 1);
+                tcgen05_fence_after();
+                if (dbg_on) args.dbg[ic * 16 + 2] = clock64();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)   // dV_t = P^T dO: A = packed P^T of group j at TMEM column 16 j
+                        if (j < jA) umma_bf16_ts(tb + kColDV, tb + kColST + 16 * j, bd_do + (uint64_t)(j * 128), idesc_kn, j > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)   // dK_t = dS^T Q: A = staging read K-major (64 queries per block)
+                        if (j < jA)
+                            umma_bf16_ss(tb + kColDK, ad_k + (uint64_t)((j >> 2) * (kBlk >> 4) + (j & 3) * 2), bd_q + (uint64_t)(j * 128), idesc_kn, j > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)   // dQ(0..127) += dS K_t: A = staging blocks 0,1 read MN-major, B = K_t MN-major
+                        if (j < ksteps)
+                            umma_bf16_ss(tb + kColDQ0, ad_q0 + (uint64_t)(j * 128), bd_k + (uint64_t)(j * 128), idesc_mn, (t > 0 || j > 0) ? 1u : 0u);
+                }
+                __syncwarp();
+                // ---- second part: queries >= 128 ----
+                mbar_wait(&p_full[1], ic & 1);
+                tcgen05_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 8; j < (NKS_T ? NKS_T : 13); ++j)
+                        if (NKS_T || j < nks) umma_bf16_ts(tb + kColDV, tb + kColST + 16 * j, bd_do + (uint64_t)(j * 128), idesc_kn, 1u);
+#pragma unroll
+                    for (int j = 8; j < (NKS_T ? NKS_T : 13); ++j)   // block 3 of the staging (queries 192..) is the V_t buffer
+                        if (NKS_T || j < nks)
+                            umma_bf16_ss(tb + kColDK, (j < 12 ? ad_k + (uint64_t)((j >> 2) * (kBlk >> 4) + (j & 3) * 2) : ad_kv), bd_q + (uint64_t)(j * 128),
+                                         idesc_kn, 1u);
+                    if (has_q1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)   // dQ(128..) = dS K_t: staging blocks 2,3
+                            if (j < ksteps)
+                                umma_bf16_ss(tb + kColDQ1, ad_q1 + (uint64_t)(j * 128), bd_k + (uint64_t)(j * 128), idesc_mn, j > 0 ? 1u : 0u);
+                    }
+                    umma_commit(o_full);
+                }
+                __syncwarp();
+                if (dbg_on) args.dbg[ic * 16 + 3] = clock64();
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ---------------- element-wise + read-out: 384 threads, three per tile row; 16-query group g belongs to part g % 3 ----------------
+        const uint32_t quad = warp_idx & 3, part = (warp_idx - 4) >> 2;
+        const uint32_t t_lane = tmem_base + ((quad * 32) << 16);
+        const int row_in_tile = quad * 32 + lane;
+        const float c = args.scale_log2;
+        const uint32_t swz = (uint32_t)(row_in_tile & 7);
+        const uint32_t stg_row = smem_u32(smem + kStagingOff) + row_in_tile * 128;
+        const uint32_t stats_u32 = smem_u32(stats);
+        float dq1c[32];   // dQ contribution of key tile 0 to query tile 1 (parts 1 and 2: columns 0..31 / 32..63)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dq1c[i] = 0.f;
+        int hc = 0, ic = 0;
+        for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
+            const int qs = hc & 1;
+            const uint32_t nls = stats_u32 + qs * 2 * kMaxQ * 4;
+            const uint32_t dls = nls + kMaxQ * 4;
+            const uint32_t q_row = smem_u32(smem + kQdoOff + qs * 2 * kQBytes) + row_in_tile * 128;   // dQ tiles park in the Q / dO stage
+            for (int t = 0; t < n_t; ++t, ++ic) {
+                const int ks = ic & 1;
+                const uint32_t kv_row = smem_u32(smem + kKvOff + ks * 2 * kBlk) + row_in_tile * 128;   // K_t row; V_t row = + kBlk
+                const bool dbg_on = args.dbg && blockIdx.x == 0 && ic < 64 && warp_idx == 4 && lane == 0;
+                mbar_wait(&s_full[0], ic & 1);
+                tcgen05_fence_after();
+                if (dbg_on) args.dbg[ic * 16 + 4] = clock64();
+                bool arrivedA = false;
+                auto arriveA = [&]() {
+                    tmem_st_wait();
+                    fence_proxy_async_smem();   // staging writes must be visible to the tensor core's (async proxy) reads
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[0]);
+                    arrivedA = true;
+                };
+                for (int g = part; g < nks; g += 3) {
+                    if (g >= 8 && !arrivedA) {
+                        arriveA();
+                        mbar_wait(&s_full[1], ic & 1);
+                        tcgen05_fence_after();
+                    } else if (g >= 8 && g < 11) {
+                        mbar_wait(&s_full[1], ic & 1);
+                        tcgen05_fence_after();
+                    }
+                    uint32_t sv[16], dv[16], pp[8], pd[8];
+                    tmem_ld_32x32b_x16(t_lane + kColST + g * 16, sv);
+                    tmem_ld_32x32b_x16(t_lane + kColDPT + g * 16, dv);
+                    tmem_ld_wait();
+                    ew_group(sv, dv, nls + g * 64, dls + g * 64, c, pp, pd);
+                    tmem_st_32x32b_x8(t_lane + kColST + g * 16, pp);
+                    const uint32_t dst = (g < 12) ? stg_row + (g >> 2) * kBlk : kv_row + kBlk;   // block 3 aliases V_t
+                    const uint32_t ch = (uint32_t)(g & 3) * 2;
+                    sts128(dst + ((ch ^ swz) << 4), pd[0], pd[1], pd[2], pd[3]);
+                    sts128(dst + (((ch + 1) ^ swz) << 4), pd[4], pd[5], pd[6], pd[7]);
+                }
+                if (!arrivedA) arriveA();
+                tmem_st_wait();
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (dbg_on) args.dbg[ic * 16 + 5] = clock64();
+                if (lane == 0) mbar_arrive(&p_full[1]);
+                // ---- read-out: accumulator slices -> bf16 tiles in the dead K_t / V_t (dV, dK) and Q / dO (dQ) buffers ----
+                mbar_wait(o_full, ic & 1);
+                tcgen05_fence_after();
+                if (dbg_on) args.dbg[ic * 16 + 6] = clock64();
+                const bool last = (t == n_t - 1);
+                auto stage32 = [&](const uint32_t (&r)[32], uint32_t row_addr, uint32_t hi, float mul) {
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        const uint32_t w0 = pack2(__uint_as_float(r[v4 * 8 + 0]) * mul, __uint_as_float(r[v4 * 8 + 1]) * mul);
+                        const uint32_t w1 = pack2(__uint_as_float(r[v4 * 8 + 2]) * mul, __uint_as_float(r[v4 * 8 + 3]) * mul);
+                        const uint32_t w2 = pack2(__uint_as_float(r[v4 * 8 + 4]) * mul, __uint_as_float(r[v4 * 8 + 5]) * mul);
+                        const uint32_t w3 = pack2(__uint_as_float(r[v4 * 8 + 6]) * mul, __uint_as_float(r[v4 * 8 + 7]) * mul);
+                        sts128(row_addr + (((hi * 4 + v4) ^ swz) << 4), w0, w1, w2, w3);
+                    }
+                };
+                // slices: part 0: dV lo, dK hi, [dQ0 lo]; part 1: dV hi, dQ1 lo, [dQ0 hi]; part 2: dK lo, dQ1 hi
+                {
+                    uint32_t r[32];
+                    const uint32_t col_a = part == 0 ? kColDV : (part == 1 ? kColDV + 32 : kColDK);
+                    tmem_ld_32x32b_x32(t_lane + col_a, r);
+                    tmem_ld_wait();
+                    stage32(r, part == 2 ? kv_row + kBlk : kv_row, part == 1 ? 1u : 0u, part == 2 ? args.scale : 1.0f);
+                }
+                if (part == 0) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_lane + kColDK + 32, r);
+                    tmem_ld_wait();
+                    stage32(r, kv_row + kBlk, 1u, args.scale);
+                } else if (has_q1) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_lane + kColDQ1 + (part - 1) * 32, r);
+                    tmem_ld_wait();
+                    if (last) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + dq1c[i]);
+                        stage32(r, q_row + kBlk, part - 1, args.scale);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) dq1c[i] = __uint_as_float(r[i]);
+                    }
+                }
+                if (last && part < 2) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_lane + kColDQ0 + part * 32, r);
+                    tmem_ld_wait();
+                    stage32(r, q_row, part, args.scale);
+                }
+                tcgen05_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(tile_free);   // TMEM is free: the next tile's score products may start
+                    mbar_arrive(out_ready);   // output tiles staged: the store warp takes over
+                }
+                if (dbg_on) args.dbg[ic * 16 + 7] = clock64();
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+#endif
+}
+
+static long long* g_dbg = nullptr;
+
+}  // namespace bwd5
+
+// Returns VB_OK if launched, 1 if this shape is not handled here.  `delta` must already hold rowsum(dO o O).
+int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
+    using namespace bwd5;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("VITB200_ATTN_TC_BWD");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!enabled || d->S > (int)kMaxQ || d->head_dim != 64 || d->tok_stride != 1 || d->key_padding_mask != nullptr) return 1;
+    const int S = d->S, npad = (S + 15) / 16 * 16;
+    Args a{};
+    a.B = d->B; a.H = d->H; a.S = S; a.npad = npad; a.nks = npad / 16;
+    a.n_t = (S + 127) / 128;
+    a.total_heads = d->B * d->H;
+    a.scale = 0.125f; a.scale_log2 = 0.125f * 1.4426950408889634f;
+    a.lse = d->lse; a.delta = d->delta;
+    a.batch_stride = d->batch_stride;
+    a.dbg = g_dbg;
+    CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
+    const uint64_t cols = (uint64_t)d->H * 64;
+    int rc;
+    if ((rc = make_tmap_3d(&tq, VB_BF16, d->q, cols, S, d->B, d->ldq, d->batch_stride * d->ldq, 64, npad))) return rc;
+    if ((rc = make_tmap_3d(&tk, VB_BF16, d->k, cols, S, d->B, d->ldk, d->batch_stride * d->ldk, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tv, VB_BF16, d->v, cols, S, d->B, d->ldv, d->batch_stride * d->ldv, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tdo, VB_BF16, d->dout, cols, S, d->B, d->lddo, d->batch_stride * d->lddo, 64, npad))) return rc;
+    // outputs: 128-row tiles, rows >= S are clipped by the TMA store
+    if ((rc = make_tmap_3d(&tdq, VB_BF16, d->dq, cols, S, d->B, d->lddq, d->batch_stride * d->lddq, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tdk, VB_BF16, d->dk, cols, S, d->B, d->lddk, d->batch_stride * d->lddk, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tdv, VB_BF16, d->dv, cols, S, d->B, d->lddv, d->batch_stride * d->lddv, 64, 128))) return rc;
+    int grid = num_sms();
+    if (grid > a.total_heads) grid = a.total_heads;
+    if (a.nks == 13) {
+        static bool configured = false;
+        if (!configured) {
+            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            configured = true;
+        }
+        attn_bwd_tc5_kernel<13><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            configured = true;
+        }
+        attn_bwd_tc5_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);
+    }
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+void attention_bwd_tc5_set_debug(long long* p) { bwd5::g_dbg = p; }
+
+}  // namespace vb

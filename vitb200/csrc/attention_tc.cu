@@ -567,12 +567,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // Returns VB_OK if launched, 1 if this shape is not handled here.  `delta` must already hold rowsum(dO o O).
 int attention_bwd_tc(const VbAttnDesc* d, cudaStream_t stream) {
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("VITB200_ATTN_TC_BWD");
-        enabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (!enabled || d->S > 208 || d->head_dim != 64 || d->tok_stride != 1) return 1;   // packed operands must end below TMEM column 192
+    if (d->S > 208 || d->head_dim != 64 || d->tok_stride != 1) return 1;   // packed operands must end below TMEM column 192
     const int S = d->S, npad = (S + 15) / 16 * 16, n_t = (S + 127) / 128;
     AttnBwdTcArgs a{};
     a.B = d->B; a.H = d->H; a.S = S; a.n_t = n_t; a.npad = npad; a.ng = npad / 16;
@@ -618,7 +613,9 @@ int attention_bwd_tc(const VbAttnDesc* d, cudaStream_t stream) {
 
 // Debug hook (not part of the documented ABI surface used by the engine): device buffer of >= 64*16 int64 that receives
 // cycle stamps from CTA 0 of the tcgen05 attention backward; pass NULL to disable.
+namespace vb { void attention_bwd_tc5_set_debug(long long* p); }
 extern "C" VB_API int vb_debug_set_attn_timeline(void* device_buffer) {
     vb::g_attn_dbg = reinterpret_cast<long long*>(device_buffer);
+    vb::attention_bwd_tc5_set_debug(reinterpret_cast<long long*>(device_buffer));
     return VB_OK;
 }
