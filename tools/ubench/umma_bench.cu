@@ -155,7 +155,12 @@ __global__ void __launch_bounds__(1024, 1) alu_kernel(int iters, long long* out,
                     __nv_bfloat162 v = __floats2bfloat162_rn(a[i], a[(i + 1) & 7]);
                     a[i] = __uint_as_float(*reinterpret_cast<uint32_t*>(&v));
                 } else if (MODE == 5) p[i] = mul2_(p[i], m2);
-                else a[i] = ex2_(fmaf(a[i], mf, cf)) * mf;
+                else if (MODE == 6) a[i] = ex2_(fmaf(a[i], mf, cf)) * mf;
+                else {   // 1 ex2 + 7 FMA-pipe ops per element (the attention-backward mix)
+                    float x = ex2_(fmaf(a[i], mf, cf));
+                    float y = fmaf(x, mf, cf); y = fmaf(y, mf, x); y = fmaf(y, cf, x); y = fmaf(y, mf, cf); y = fmaf(y, x, cf);
+                    a[i] = y * mf;
+                }
             }
         }
     }
@@ -200,10 +205,12 @@ void run_alu(const char* name, long long* out, float* sink) {
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
     long long* out; float* sink;
+    const bool alu_only = argc > 1;
     cudaMallocManaged(&out, 64 * sizeof(long long));
     cudaMalloc(&sink, 4096 * sizeof(float));
+    if (!alu_only) {
     run_mma<0, 256, 0, 0, 1>("SS N=256 K/K 1acc", out);
     run_mma<0, 208, 0, 0, 1>("SS N=208 K/K 1acc", out);
     run_mma<0, 128, 0, 0, 1>("SS N=128 K/K 1acc", out);
@@ -227,6 +234,7 @@ int main() {
     run_tmem<1>("2 ld x32 then wait", out, sink);
     run_tmem<2>("ld x16+wait", out, sink);
     run_tmem<3>("4 st x8 then wait", out, sink);
+    }
     run_alu<0>("ex2", out, sink);
     run_alu<1>("ffma", out, sink);
     run_alu<2>("fma.f32x2", out, sink);
@@ -234,6 +242,7 @@ int main() {
     run_alu<4>("cvt.bf16x2", out, sink);
     run_alu<5>("mul.f32x2", out, sink);
     run_alu<6>("ex2+ffma+fmul", out, sink);
+    run_alu<7>("ex2+7fma", out, sink);
     printf("done\n");
     return 0;
 }

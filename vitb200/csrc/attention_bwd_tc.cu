@@ -366,6 +366,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t ch = (uint32_t)(g & 3) * 2;
                     sts128(dst + ((ch ^ swz) << 4), pd[0], pd[1], pd[2], pd[3]);
                     sts128(dst + (((ch + 1) ^ swz) << 4), pd[4], pd[5], pd[6], pd[7]);
+                    if (dbg_on) args.dbg[ic * 16 + 8 + g / 3] = clock64();
                 }
                 if (!arrivedA) arriveA();
                 tmem_st_wait();

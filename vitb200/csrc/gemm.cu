@@ -102,6 +102,56 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot for two lanes of the epilogue math.  The
+// epilogue warps are issue-bound (8 warps feed a 256x256 tile every 6144 cycles at K = 768), not FMA-pipe-bound, so
+// halving the instruction count of the arithmetic is what moves the tensor pipe's duty cycle.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2_bcast(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+    f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// Two lanes of phi_parts(): gelu = x * Phi(x), dgelu = Phi(x) + x * pdf(x)   (same A&S 7.1.26 arithmetic as above)
+__device__ __forceinline__ void gelu_pair(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+    const f2 x = f2_pack(x0, x1);
+    const f2 ax = f2_pack(fabsf(x0), fabsf(x1));
+    float den0, den1;
+    f2_unpack(f2_fma(ax, f2_bcast(0.2316419f), f2_bcast(1.0f)), den0, den1);
+    const f2 t = f2_pack(fast_rcp(den0), fast_rcp(den1));
+    float a0, a1;
+    f2_unpack(f2_mul(f2_mul(x, f2_bcast(-0.72134752044448170f)), x), a0, a1);
+    const f2 e = f2_pack(fast_ex2(a0), fast_ex2(a1));   // exp(-x^2 / 2)
+    f2 poly = f2_fma(f2_bcast(0.5f * 1.061405429f), t, f2_bcast(0.5f * -1.453152027f));
+    poly = f2_fma(poly, t, f2_bcast(0.5f * 1.421413741f));
+    poly = f2_fma(poly, t, f2_bcast(0.5f * -0.284496736f));
+    poly = f2_fma(poly, t, f2_bcast(0.5f * 0.254829592f));
+    const f2 q = f2_mul(f2_mul(poly, t), e);             // 1 - Phi(|x|)
+    float h0, h1;
+    f2_unpack(f2_fma(q, f2_bcast(-1.0f), f2_bcast(0.5f)), h0, h1);   // 0.5 - q
+    h0 = __uint_as_float(__float_as_uint(h0) ^ (__float_as_uint(x0) & 0x80000000u));
+    h1 = __uint_as_float(__float_as_uint(h1) ^ (__float_as_uint(x1) & 0x80000000u));
+    const f2 cdf = f2_add(f2_pack(h0, h1), f2_bcast(0.5f));
+    f2_unpack(f2_mul(x, cdf), g0, g1);
+    f2_unpack(f2_fma(f2_mul(x, f2_bcast(0.39894228040143268f)), e, cdf), d0, d1);
+}
+
 struct UnitCoord {
     int m_blk, n_blk, batch, kb0, kb1;
 };
@@ -352,6 +402,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int g = 0; g < int(CPC / 32); ++g) {
                     const int colg = col0 + g * 32;
+                    // ---- bias (issued first: the global-load latency hides behind the TMEM load) ----
+                    float4 b4[8];
+                    const bool bias_vec = args.bias != nullptr && colg + 32 <= args.N;
+                    if (bias_vec) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(args.bias + colg) + j);
+                    }
                     // ---- accumulator -> registers (32 fp32 columns of this thread's row) ----
                     uint32_t acc[32];
                     tmem_ld_32x32b_x32(t_addr + ch * CPC + g * 32, acc);
@@ -365,19 +422,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                    // ---- bias ----
-                    if (args.bias != nullptr) {
-                        if (colg + 32 <= args.N) {
+                    if (bias_vec) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + colg + j));
-                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (colg + j < args.N) v[j] += __ldg(args.bias + colg + j);
+                        for (int j = 0; j < 8; ++j) {
+                            f2_unpack(f2_add(f2_pack(v[4 * j], v[4 * j + 1]), f2_pack(b4[j].x, b4[j].y)), v[4 * j], v[4 * j + 1]);
+                            f2_unpack(f2_add(f2_pack(v[4 * j + 2], v[4 * j + 3]), f2_pack(b4[j].z, b4[j].w)), v[4 * j + 2], v[4 * j + 3]);
                         }
+                    } else if (args.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (colg + j < args.N) v[j] += __ldg(args.bias + colg + j);
                     }
                     // ---- aux operand (same dtype / geometry as C) ----
                     float x[32];
@@ -411,20 +465,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             }
                         }
                     }
-                    // ---- fused math ----
+                    // ---- fused math (fp32x2-packed where the operation allows it) ----
                     float gl[32];
+                    if constexpr (EPI == VB_EPI_GELU) {   // C2 = gelu(x); C = gelu'(x) (what the backward epilogue multiplies by)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if constexpr (EPI == VB_EPI_GELU) {   // C2 = gelu(x); C = gelu'(x) (what the backward epilogue multiplies by)
-                            float cdf, e;
-                            phi_parts(v[j], cdf, e);
-                            gl[j] = v[j] * cdf;
-                            v[j] = fmaf(v[j] * 0.39894228040143268f, e, cdf);
+                        for (int j = 0; j < 32; j += 2) {
+                            float g0, g1, d0, d1;
+                            gelu_pair(v[j], v[j + 1], g0, g1, d0, d1);
+                            gl[j] = g0; gl[j + 1] = g1;
+                            v[j] = d0; v[j + 1] = d1;
                         }
-                        if constexpr (EPI == VB_EPI_RESIDUAL) v[j] += x[j];
-                        if constexpr (EPI == VB_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
-                        if constexpr (EPI == VB_EPI_DGELU) v[j] *= x[j];   // AUX = gelu'(pre-activation), saved by the forward epilogue
-                        if constexpr (EPI == VB_EPI_DRELU) v[j] = x[j] > 0.f ? v[j] : 0.f;
+                    } else if constexpr (EPI == VB_EPI_RESIDUAL) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) f2_unpack(f2_add(f2_pack(v[j], v[j + 1]), f2_pack(x[j], x[j + 1])), v[j], v[j + 1]);
+                    } else if constexpr (EPI == VB_EPI_DGELU) {   // AUX = gelu'(pre-activation), saved by the forward epilogue
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) f2_unpack(f2_mul(f2_pack(v[j], v[j + 1]), f2_pack(x[j], x[j + 1])), v[j], v[j + 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if constexpr (EPI == VB_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
+                            if constexpr (EPI == VB_EPI_DRELU) v[j] = x[j] > 0.f ? v[j] : 0.f;
+                        }
                     }
                     // ---- registers -> swizzled staging buffer (or straight to global on the bring-up path) ----
                     if (!args.direct) {

@@ -201,8 +201,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Remote arrive on a peer CTA's mbarrier.  Default semantics (no .release.cluster qualifier): an explicit cluster-scope
+// release compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrive (7 % of the GELU GEMM's stall samples); the
+// accumulator hand-off it signals is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, as in CUTLASS's
+// ClusterBarrier::arrive(cta_id).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on an mbarrier that may live in the peer CTA (shared::cluster address)
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
