@@ -851,8 +851,8 @@ static unsigned delta_grid(long long units) {
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream);   // attention_tc.cu (tcgen05 path, S <= 256)
-int attention_bwd_tc(const VbAttnDesc* d, cudaStream_t stream);
+int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream);   // attention_tc.cu (older tcgen05 path: S <= 256, key-padding masks)
+int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream);  // attention_fwd_tc.cu (S <= 208, no mask: three threads per row)
 int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream);   // attention_bwd_tc.cu (five-product tcgen05 path, S <= 208)
 
 static int check_common(const VbAttnDesc* d) {
@@ -890,7 +890,9 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (int rc = check_common(d)) return rc;
     const AttnParams p = to_params(d);
     if (d->S <= 256) {
-        const int tc = attention_fwd_tc(d, as_stream(stream));
+        int tc = attention_fwd_tc3(d, as_stream(stream));
+        if (tc <= 0) return tc;
+        tc = attention_fwd_tc(d, as_stream(stream));
         if (tc <= 0) return tc;   // launched (0) or failed with an error (< 0); 1 = shape not handled there
         const int n_mt = (d->S + 15) / 16;
         cudaStream_t st = as_stream(stream);
@@ -920,22 +922,13 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     const AttnParams p = to_params(d);
     cudaStream_t st = as_stream(stream);
     // S <= 208 without a key-padding mask (every ViT / DeiT config): five-product tcgen05 backward (attention_bwd_tc.cu).
-    // VITB200_ATTN_TC_BWD=0 selects the mma.sync kernels below, =3 the older seven-product tcgen05 kernel (attention_tc.cu).
+    // VITB200_ATTN_TC_BWD=0 selects the mma.sync kernels below (A/B comparisons).
     const char* tc_env = getenv("VITB200_ATTN_TC_BWD");
-    const char tc_mode = tc_env ? tc_env[0] : '5';
-    if (d->S <= 256 && d->tok_stride == 1 && tc_mode != '0') {
-        const long long nw = (long long)d->B * d->S * d->H;
-        if (tc_mode == '3') {
-            attn_delta_kernel<<<delta_grid(nw), 256, 0, st>>>(p);
-            VB_CUDA_CHECK(cudaGetLastError());
-            const int tc = attention_bwd_tc(d, st);
-            if (tc <= 0) return tc;
-        } else if (d->S <= 208 && d->key_padding_mask == nullptr) {
-            attn_delta_kernel<<<delta_grid(nw), 256, 0, st>>>(p);
-            VB_CUDA_CHECK(cudaGetLastError());
-            const int tc = attention_bwd_tc5(d, st);
-            if (tc <= 0) return tc;
-        }
+    if (d->S <= 208 && d->tok_stride == 1 && d->key_padding_mask == nullptr && !(tc_env && tc_env[0] == '0')) {
+        attn_delta_kernel<<<delta_grid((long long)d->B * d->S * d->H), 256, 0, st>>>(p);
+        VB_CUDA_CHECK(cudaGetLastError());
+        const int tc = attention_bwd_tc5(d, st);
+        if (tc <= 0) return tc;
     }
     if (d->S <= 256) {
         const int n_mt = (d->S + 15) / 16;

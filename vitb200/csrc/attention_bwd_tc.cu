@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
+#include "attn_tc_common.cuh"
 
 namespace vb {
 
@@ -58,29 +59,7 @@ struct Args {
     long long batch_stride;
 };
 
-__device__ __forceinline__ float ex2f(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-// Explicit shared-space accesses with 32-bit addresses (generic-pointer arithmetic costs 64-bit adds per access).  The
-// loads are volatile on purpose: they keep their program order relative to the (volatile) tcgen05.ld of the NEXT column
-// group, so the math that depends on them cannot be hoisted above that prefetch.
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
+using namespace atc;
 
 // 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key)
 __device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_t (&dv)[16], uint32_t nls, uint32_t dls, float c,

@@ -11,7 +11,7 @@ from ._lib import VbGemmDesc
 
 # kernels launched by libvitb200.so since import (bench.py reports the per-step delta as `gpu_launches`)
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 3,
+_KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 2,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
                      "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1}
 
