@@ -272,10 +272,10 @@ def main():
         gemm_flops = sum(f for _, _, f in rec)
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         # DRAM traffic per launch from the committed ncu --set full capture of the six representative ViT-B launches
-        # (profiles/r1_gemm_ncu.json; each shape occurs 12x per step, the wgrad shape stands for the 4 wgrad GEMMs per layer)
+        # (profiles/r1b_gemm_ncu.json; each shape occurs 12x per step, the wgrad shape stands for the 4 wgrad GEMMs per layer)
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_gemm_ncu.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r1b_gemm_ncu.json")) as fh:
                 prof = json.load(fh)
             traffic = sum(p["dram_bytes"] for p in prof) / len(prof)
         except Exception:
@@ -283,7 +283,7 @@ def main():
         roofline = {"bound": "tensor", "kernel": "vb::gemm_kernel (tcgen05, all launches of one step)", "achieved": achieved,
                     "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus, "traffic": traffic,
                     "traffic_note": "mean dram read+write bytes per launch over the 6 profiled ViT-B/16 GEMM shapes (ncu --set full, "
-                                    "profiles/r1_gemm_ncu_summary.txt); algorithmic bytes of the same launches are within 0.82-1.02x",
+                                    "profiles/r1b_gemm_ncu_summary.txt); algorithmic bytes of the same launches are within 0.83-1.01x",
                     "peak_kind": f"bf16_tflops_sustained ({src}); burst peak {peak}", "frac_of_burst": achieved / peak,
                     "launches_per_step": len(rec), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / K),
                     "algorithmic_gflop_per_launch_avg": gemm_flops / len(rec) / 1e9}
