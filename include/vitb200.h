@@ -129,6 +129,12 @@ typedef struct VbAttnDesc {
     float* delta;
     void* dq; void* dk; void* dv;
     int64_t lddq, lddk, lddv;
+    /* attention dropout (nn.MultiheadAttention(dropout=p), vanilla_vit.py:67): P is multiplied by keep / (1 - p) before P V;
+     * the mask is regenerated in backward from (*dropout_seed, dropout_stream, element).  p = 0 disables.  Only the tcgen05
+     * kernels (S <= 208, no key-padding mask) implement it; other shapes return VB_ERR_UNSUPPORTED when p > 0. */
+    float dropout_p;
+    uint32_t dropout_stream;
+    const uint32_t* dropout_seed; /* device pointer */
 } VbAttnDesc;
 VB_API int vb_attention_fwd(const VbAttnDesc* desc, void* stream);
 VB_API int vb_attention_bwd(const VbAttnDesc* desc, void* stream);
@@ -157,6 +163,21 @@ VB_API int vb_token_rows(float* x, const float* tok0, const float* tok1, const f
 VB_API int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, float* out_accum, void* stream);
 VB_API int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_patches_bf16, float* dpos, float* dtok0, float* dtok1,
                         float* dbias, int32_t B, int32_t S, int32_t D, int32_t n_prefix, void* stream);
+
+/* ---- Dropout ------------------------------------------------------------------------------
+ * Hidden-state dropout of the ViT encoder: nn.Dropout at vanilla_vit.py:38 (mlp.2), :42 (mlp.4), :68/:78
+ * (EncoderBlock.dropout) and :94/:104 (Encoder.dropout).  keep(i) = hash(*seed_dev, stream_id, i) >= p with i the
+ * row-major element index (row * cols + col); kept elements are scaled by 1 / (1 - p).  The same (seed, stream_id,
+ * rows x cols) regenerates the mask in backward.  The random stream differs from PyTorch's Philox stream (documented).
+ * vb_dropout_f32: dst = keep ? src / (1 - p) : 0  (+ aux), written as fp32 (dst_f32) and/or bf16 (dst_bf16); in place allowed.
+ * vb_dropout_bf16_pair: in place on x1 and (optional) x2 with one mask (GELU output and its saved derivative).
+ * vb_dropout_mask_u8: the keep mask itself (tests / oracle). */
+VB_API int vb_dropout_f32(const float* src, int64_t ldsrc, const float* aux, int64_t ldaux, float* dst_f32, int64_t lddst,
+                          void* dst_bf16, int64_t lddstb, int32_t rows, int32_t cols, float p, const uint32_t* seed_dev,
+                          uint32_t stream_id, void* stream);
+VB_API int vb_dropout_bf16_pair(void* x1, void* x2, int64_t ld, int32_t rows, int32_t cols, float p, const uint32_t* seed_dev,
+                                uint32_t stream_id, void* stream);
+VB_API int vb_dropout_mask_u8(uint8_t* out, int64_t n, float p, const uint32_t* seed_dev, uint32_t stream_id, void* stream);
 
 /* ---- Training-step tail -------------------------------------------------------------------
  * vb_cross_entropy: mean-reduction softmax cross-entropy (nn.CrossEntropyLoss at vanilla_vit.py:220,237) forward

@@ -24,11 +24,12 @@ import torch.nn.functional as F
 # ------------------------------------------------------------------------------------------------------------
 # ViT (models/image_classification/vanilla_vit.py)
 # ------------------------------------------------------------------------------------------------------------
-def mha_batch_first(x, in_w, in_b, out_w, out_b, num_heads):
-    """nn.MultiheadAttention(D, H, batch_first=True)(x, x, x, need_weights=False)  — vanilla_vit.py:67,77.
+def mha_batch_first(x, in_w, in_b, out_w, out_b, num_heads, attn_drop=None):
+    """nn.MultiheadAttention(D, H, dropout=p_attn, batch_first=True)(x, x, x, need_weights=False)  — vanilla_vit.py:67,77.
 
     Packed in-projection (torch/nn/functional.py:5835-5847), per-head softmax(QK^T/sqrt(hd))V via SDPA
-    (functional.py:6676-6682), out-projection (functional.py:6690).
+    (functional.py:6676-6682), out-projection (functional.py:6690).  ``attn_drop``: optional callable applied to the
+    [B,H,S,S] attention probabilities (dropout with an explicit mask; SDPA's dropout_p acts at the same place).
     """
     B, S, D = x.shape
     hd = D // num_heads
@@ -37,25 +38,46 @@ def mha_batch_first(x, in_w, in_b, out_w, out_b, num_heads):
     q = q.view(B, S, num_heads, hd).transpose(1, 2)
     k = k.view(B, S, num_heads, hd).transpose(1, 2)
     v = v.view(B, S, num_heads, hd).transpose(1, 2)
-    o = F.scaled_dot_product_attention(q, k, v)
+    if attn_drop is None:
+        o = F.scaled_dot_product_attention(q, k, v)
+    else:
+        o = attn_drop(torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)) @ v
     o = o.transpose(1, 2).reshape(B, S, D)
     return F.linear(o, out_w, out_b)
 
 
-def encoder_block(x, sd, prefix, num_heads, eps):
-    """EncoderBlock.forward — vanilla_vit.py:73-83 (pre-norm; dropout p=0)."""
+class ExplicitDropout:
+    """Dropout with caller-supplied keep masks (0/1 tensors): y = keep * x / (1 - p) — the arithmetic of nn.Dropout in train()
+    mode (vanilla_vit.py:38,42,68,94) with the random stream made an input, so that the GPU kernels' masks can be replayed.
+    ``masks[(layer, site)]``: site 0 = out-proj output, 1 = after GELU, 2 = MLP output, 3 = attention probabilities;
+    ``masks["embed"]`` = Encoder.dropout."""
+
+    def __init__(self, masks, p_hidden, p_attn):
+        self.masks, self.p_hidden, self.p_attn = masks, p_hidden, p_attn
+
+    def __call__(self, key, x):
+        p = self.p_attn if (isinstance(key, tuple) and key[1] == 3) else self.p_hidden
+        if p == 0 or key not in self.masks:
+            return x
+        return x * self.masks[key].reshape(x.shape).to(x.dtype) / (1.0 - p)
+
+
+def encoder_block(x, sd, prefix, num_heads, eps, drop=None, layer=0):
+    """EncoderBlock.forward — vanilla_vit.py:73-83 (pre-norm); ``drop``: None (p = 0) or an ExplicitDropout."""
+    dz = (lambda key, t: t) if drop is None else drop
     h = F.layer_norm(x, (x.shape[-1],), sd[prefix + "ln_1.weight"], sd[prefix + "ln_1.bias"], eps)
     a = mha_batch_first(h, sd[prefix + "self_attention.in_proj_weight"], sd[prefix + "self_attention.in_proj_bias"],
-                        sd[prefix + "self_attention.out_proj.weight"], sd[prefix + "self_attention.out_proj.bias"], num_heads)
-    x = a + x
+                        sd[prefix + "self_attention.out_proj.weight"], sd[prefix + "self_attention.out_proj.bias"], num_heads,
+                        attn_drop=None if (drop is None or drop.p_attn == 0) else (lambda P: drop((layer, 3), P)))
+    x = dz((layer, 0), a) + x                                                      # :78-79
     y = F.layer_norm(x, (x.shape[-1],), sd[prefix + "ln_2.weight"], sd[prefix + "ln_2.bias"], eps)
     y = F.linear(y, sd[prefix + "mlp.0.weight"], sd[prefix + "mlp.0.bias"])       # MLPBlock: vanilla_vit.py:33-34
-    y = F.gelu(y)                                                                  # nn.GELU() (erf): :50
+    y = dz((layer, 1), F.gelu(y))                                                  # nn.GELU() (erf) :50, mlp.2 dropout :38
     y = F.linear(y, sd[prefix + "mlp.3.weight"], sd[prefix + "mlp.3.bias"])       # :41
-    return x + y
+    return x + dz((layer, 2), y)                                                   # mlp.4 dropout :42, residual :83
 
 
-def vit_forward_features(sd, images, *, patch_size, num_layers, num_heads, eps=1e-6):
+def vit_forward_features(sd, images, *, patch_size, num_layers, num_heads, eps=1e-6, drop=None):
     """ViT.forward_features + Encoder.forward — vanilla_vit.py:186-207, :102-106."""
     n = images.shape[0]
     D = sd["class_token"].shape[-1]
@@ -63,8 +85,10 @@ def vit_forward_features(sd, images, *, patch_size, num_layers, num_heads, eps=1
     x = x.reshape(n, D, -1).permute(0, 2, 1)                                                   # :197-198
     x = torch.cat([sd["class_token"].expand(n, -1, -1), x], dim=1)                             # :202-203
     x = x + sd["encoder.pos_embedding"]                                                        # :104
+    if drop is not None:
+        x = drop("embed", x)                                                                   # Encoder.dropout :104
     for i in range(num_layers):
-        x = encoder_block(x, sd, f"encoder.layers.encoder_layer_{i}.", num_heads, eps)
+        x = encoder_block(x, sd, f"encoder.layers.encoder_layer_{i}.", num_heads, eps, drop=drop, layer=i)
     return F.layer_norm(x, (D,), sd["encoder.ln.weight"], sd["encoder.ln.bias"], eps)         # :106
 
 

@@ -5,7 +5,7 @@ missing or a call fails, a ``VbError`` is raised.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitb200.so")
@@ -42,6 +42,7 @@ class VbAttnDesc(Structure):
         ("delta", c_void_p),
         ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
         ("lddq", c_int64), ("lddk", c_int64), ("lddv", c_int64),
+        ("dropout_p", c_float), ("dropout_stream", c_uint32), ("dropout_seed", c_void_p),
     ]
 
 
@@ -72,6 +73,10 @@ SIGNATURES = {
                                  c_int32, c_void_p, c_int64, c_void_p]),
     "vb_add_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vb_add3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vb_dropout_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float,
+                               c_void_p, c_uint32, c_void_p]),
+    "vb_dropout_bf16_pair": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p, c_uint32, c_void_p]),
+    "vb_dropout_mask_u8": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_uint32, c_void_p]),
 }
 
 _lib = None

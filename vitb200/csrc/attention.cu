@@ -892,6 +892,7 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (d->S <= 256) {
         int tc = attention_fwd_tc3(d, as_stream(stream));
         if (tc <= 0) return tc;
+        if (d->dropout_p > 0.f) return fail(VB_ERR_UNSUPPORTED, "attention dropout needs the tcgen05 path (S <= 208, batch-first, no key-padding mask)");
         tc = attention_fwd_tc(d, as_stream(stream));
         if (tc <= 0) return tc;   // launched (0) or failed with an error (< 0); 1 = shape not handled there
         const int n_mt = (d->S + 15) / 16;
@@ -901,6 +902,7 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
         if (n_mt <= 14) return launch_short_fwd<7>(p, st);
         return launch_short_fwd<8>(p, st);
     }
+    if (d->dropout_p > 0.f) return fail(VB_ERR_UNSUPPORTED, "attention dropout needs the tcgen05 path (S <= 208, batch-first, no key-padding mask)");
     const int smem = 5 * TILE_BYTES;
     static bool configured = false;
     if (!configured) {
@@ -930,6 +932,7 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
         const int tc = attention_bwd_tc5(d, st);
         if (tc <= 0) return tc;
     }
+    if (d->dropout_p > 0.f) return fail(VB_ERR_UNSUPPORTED, "attention dropout needs the tcgen05 path (S <= 208, batch-first, no key-padding mask)");
     if (d->S <= 256) {
         const int n_mt = (d->S + 15) / 16;
         if (n_mt <= 6) return launch_short_bwd<3>(p, st);

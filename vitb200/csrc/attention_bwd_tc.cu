@@ -27,6 +27,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include "attn_tc_common.cuh"
+#include "dropout.cuh"
 
 namespace vb {
 
@@ -57,13 +58,20 @@ struct Args {
     const float* lse;
     const float* delta;
     long long batch_stride;
+    uint32_t drop_thresh, drop_stream;   // attention dropout (DROP instantiations)
+    float drop_inv_keep;
+    const uint32_t* drop_seed;
 };
 
 using namespace atc;
 
-// 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key)
+// 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key).
+// DROP (attention dropout): element (query q, key) of head-local index didx0 + j * S was kept iff its hash clears the threshold;
+// dV sees keep * P / (1 - p), and dP = keep * (dO V^T) / (1 - p) enters dS = P o (dP - delta) (delta = rowsum(dO o O) still holds).
+template <bool DROP>
 __device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_t (&dv)[16], uint32_t nls, uint32_t dls, float c,
-                                         uint32_t (&pp)[8], uint32_t (&pd)[8]) {
+                                         uint32_t (&pp)[8], uint32_t (&pd)[8], uint32_t dkey, uint32_t didx0, uint32_t S, uint32_t thresh,
+                                         float inv_keep) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float4 l4 = lds128(nls + 16 * i);
@@ -72,15 +80,27 @@ __device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_
         const float p1 = ex2f(fmaf(__uint_as_float(sv[4 * i + 1]), c, l4.y));
         const float p2 = ex2f(fmaf(__uint_as_float(sv[4 * i + 2]), c, l4.z));
         const float p3 = ex2f(fmaf(__uint_as_float(sv[4 * i + 3]), c, l4.w));
-        pp[2 * i] = pack2(p0, p1);
-        pp[2 * i + 1] = pack2(p2, p3);
-        pd[2 * i] = pack2(p0 * (__uint_as_float(dv[4 * i + 0]) - d4.x), p1 * (__uint_as_float(dv[4 * i + 1]) - d4.y));
-        pd[2 * i + 1] = pack2(p2 * (__uint_as_float(dv[4 * i + 2]) - d4.z), p3 * (__uint_as_float(dv[4 * i + 3]) - d4.w));
+        float g0 = __uint_as_float(dv[4 * i + 0]), g1 = __uint_as_float(dv[4 * i + 1]), g2 = __uint_as_float(dv[4 * i + 2]),
+              g3 = __uint_as_float(dv[4 * i + 3]);
+        if (DROP) {
+            const float k0 = dropout_keep(dkey, didx0 + (4 * i + 0) * S, thresh) ? inv_keep : 0.f;
+            const float k1 = dropout_keep(dkey, didx0 + (4 * i + 1) * S, thresh) ? inv_keep : 0.f;
+            const float k2 = dropout_keep(dkey, didx0 + (4 * i + 2) * S, thresh) ? inv_keep : 0.f;
+            const float k3 = dropout_keep(dkey, didx0 + (4 * i + 3) * S, thresh) ? inv_keep : 0.f;
+            pp[2 * i] = pack2(p0 * k0, p1 * k1);
+            pp[2 * i + 1] = pack2(p2 * k2, p3 * k3);
+            g0 *= k0; g1 *= k1; g2 *= k2; g3 *= k3;
+        } else {
+            pp[2 * i] = pack2(p0, p1);
+            pp[2 * i + 1] = pack2(p2, p3);
+        }
+        pd[2 * i] = pack2(p0 * (g0 - d4.x), p1 * (g1 - d4.y));
+        pd[2 * i + 1] = pack2(p2 * (g2 - d4.z), p3 * (g3 - d4.w));
     }
 }
 
 // NKS_T > 0: number of 16-query steps known at compile time (fully unrolled MMA issue); NKS_T == 0: generic.
-template <int NKS_T>
+template <int NKS_T, bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -301,6 +321,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t swz = (uint32_t)(row_in_tile & 7);
         const uint32_t stg_row = smem_u32(smem + kStagingOff) + row_in_tile * 128;
         const uint32_t stats_u32 = smem_u32(stats);
+        const uint32_t drop_key = DROP ? dropout_key(*args.drop_seed, args.drop_stream) : 0u;
         float dq1c[32];   // dQ contribution of key tile 0 to query tile 1 (parts 1 and 2: columns 0..31 / 32..63)
 #pragma unroll
         for (int i = 0; i < 32; ++i) dq1c[i] = 0.f;
@@ -313,6 +334,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int t = 0; t < n_t; ++t, ++ic) {
                 const int ks = ic & 1;
                 const uint32_t kv_row = smem_u32(smem + kKvOff + ks * 2 * kBlk) + row_in_tile * 128;   // K_t row; V_t row = + kBlk
+                const uint32_t drop_base = (uint32_t)head * (uint32_t)S * (uint32_t)S + (uint32_t)(t * 128 + row_in_tile);   // element (q, key) -> base + q * S
                 const bool dbg_on = args.dbg && blockIdx.x == 0 && ic < 64 && warp_idx == 4 && lane == 0;
                 mbar_wait(&s_full[0], ic & 1);
                 tcgen05_fence_after();
@@ -339,7 +361,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tmem_ld_32x32b_x16(t_lane + kColST + g * 16, sv);
                     tmem_ld_32x32b_x16(t_lane + kColDPT + g * 16, dv);
                     tmem_ld_wait();
-                    ew_group(sv, dv, nls + g * 64, dls + g * 64, c, pp, pd);
+                    ew_group<DROP>(sv, dv, nls + g * 64, dls + g * 64, c, pp, pd, drop_key, drop_base + (uint32_t)(g * 16) * (uint32_t)S, (uint32_t)S,
+                                   args.drop_thresh, args.drop_inv_keep);
                     tmem_st_32x32b_x8(t_lane + kColST + g * 16, pp);
                     const uint32_t dst = (g < 12) ? stg_row + (g >> 2) * kBlk : kv_row + kBlk;   // block 3 aliases V_t
                     const uint32_t ch = (uint32_t)(g & 3) * 2;
@@ -456,21 +479,30 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     if ((rc = make_tmap_3d(&tdv, VB_BF16, d->dv, cols, S, d->B, d->lddv, d->batch_stride * d->lddv, 64, 128))) return rc;
     int grid = num_sms();
     if (grid > a.total_heads) grid = a.total_heads;
-    if (a.nks == 13) {
-        static bool configured = false;
-        if (!configured) {
-            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            configured = true;
-        }
-        attn_bwd_tc5_kernel<13><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);
-    } else {
-        static bool configured = false;
-        if (!configured) {
-            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            configured = true;
-        }
-        attn_bwd_tc5_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);
+    const bool drop = d->dropout_p > 0.f;
+    if (drop) {
+        VB_REQUIRE(d->dropout_p < 1.f && d->dropout_seed != nullptr, "attention dropout: p must be < 1 and dropout_seed non-null");
+        VB_REQUIRE((long long)a.total_heads * S * S < (1ll << 32), "attention dropout: more than 2^32 score elements");
+        a.drop_thresh = dropout_threshold(d->dropout_p);
+        a.drop_inv_keep = 1.0f / (1.0f - d->dropout_p);
+        a.drop_seed = d->dropout_seed;
+        a.drop_stream = d->dropout_stream;
     }
+#define VB_BWD_LAUNCH(NKS, DR)                                                                                              \
+    do {                                                                                                                    \
+        static bool configured = false;                                                                                     \
+        if (!configured) {                                                                                                  \
+            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<NKS, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            configured = true;                                                                                              \
+        }                                                                                                                   \
+        attn_bwd_tc5_kernel<NKS, DR><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);            \
+    } while (0)
+    if (a.nks == 13) {
+        if (drop) VB_BWD_LAUNCH(13, true); else VB_BWD_LAUNCH(13, false);
+    } else {
+        if (drop) VB_BWD_LAUNCH(0, true); else VB_BWD_LAUNCH(0, false);
+    }
+#undef VB_BWD_LAUNCH
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

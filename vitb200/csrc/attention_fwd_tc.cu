@@ -17,6 +17,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include "attn_tc_common.cuh"
+#include "dropout.cuh"
 
 namespace vb {
 
@@ -45,9 +46,12 @@ struct Args {
     float scale_log2;
     float* lse;
     long long* dbg;   // optional in-kernel cycle stamps (tools/attn_timeline.py)
+    uint32_t drop_thresh, drop_stream;   // attention dropout (DROP instantiations): keep iff hash >= thresh, P *= 1 / (1 - p)
+    float drop_inv_keep;
+    const uint32_t* drop_seed;
 };
 
-template <int NKS_T>
+template <int NKS_T, bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Args args) {
@@ -179,9 +183,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t swz = (uint32_t)(row_in_tile & 7);
         const uint32_t xm_u32 = smem_u32(smem + kXmOff), xs_u32 = smem_u32(smem + kXsOff);
         const uint32_t out_row = smem_u32(smem + kOutOff) + row_in_tile * 128;
+        const uint32_t drop_key = DROP ? dropout_key(*args.drop_seed, args.drop_stream) : 0u;
         int j = 0;
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x) {
             for (int qt = 0; qt < n_qt; ++qt, ++j) {
+                const uint32_t drop_base = ((uint32_t)head * (uint32_t)S + (uint32_t)(qt * 128 + row_in_tile)) * (uint32_t)S;   // element (q, k) -> base + k
                 const uint32_t t_s = t_lane + (j & 1) * kMaxQ;
                 const uint32_t xoff = ((j & 3) * 3 * 128 + row_in_tile) * 4;
                 const bool dbg_on = args.dbg && blockIdx.x == 0 && j < 64 && warp_idx == 4 && lane == 0;
@@ -255,9 +261,13 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float p0 = ex2f(fmaf(__uint_as_float(r[2 * i]), c, nmg));
-                            const float p1 = ex2f(fmaf(__uint_as_float(r[2 * i + 1]), c, nmg));
+                            float p0 = ex2f(fmaf(__uint_as_float(r[2 * i]), c, nmg));
+                            float p1 = ex2f(fmaf(__uint_as_float(r[2 * i + 1]), c, nmg));
                             l0 += p0; l1 += p1;
+                            if (DROP) {   // the row sum keeps the un-dropped probabilities; P V sees keep * P / (1 - p)
+                                p0 = dropout_keep(drop_key, drop_base + g * 16 + 2 * i, args.drop_thresh) ? p0 * args.drop_inv_keep : 0.f;
+                                p1 = dropout_keep(drop_key, drop_base + g * 16 + 2 * i + 1, args.drop_thresh) ? p1 * args.drop_inv_keep : 0.f;
+                            }
                             pk[i] = pack2(p0, p1);
                         }
                         l += l0 + l1;
@@ -376,21 +386,30 @@ int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream) {
     if ((rc = make_tmap_3d(&to, VB_BF16, d->o, cols, S, d->B, d->ldo, d->batch_stride * d->ldo, 64, 128))) return rc;
     int grid = num_sms();
     if (grid > a.total_heads) grid = a.total_heads;
-    if (a.nks == 13) {
-        static bool configured = false;
-        if (!configured) {
-            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc3_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            configured = true;
-        }
-        attn_fwd_tc3_kernel<13><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, to, a);
-    } else {
-        static bool configured = false;
-        if (!configured) {
-            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            configured = true;
-        }
-        attn_fwd_tc3_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, to, a);
+    const bool drop = d->dropout_p > 0.f;
+    if (drop) {
+        VB_REQUIRE(d->dropout_p < 1.f && d->dropout_seed != nullptr, "attention dropout: p must be < 1 and dropout_seed non-null");
+        VB_REQUIRE((long long)a.total_heads * S * S < (1ll << 32), "attention dropout: more than 2^32 score elements");
+        a.drop_thresh = dropout_threshold(d->dropout_p);
+        a.drop_inv_keep = 1.0f / (1.0f - d->dropout_p);
+        a.drop_seed = d->dropout_seed;
+        a.drop_stream = d->dropout_stream;
     }
+#define VB_FWD_LAUNCH(NKS, DR)                                                                                              \
+    do {                                                                                                                    \
+        static bool configured = false;                                                                                     \
+        if (!configured) {                                                                                                  \
+            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc3_kernel<NKS, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            configured = true;                                                                                              \
+        }                                                                                                                   \
+        attn_fwd_tc3_kernel<NKS, DR><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, to, a);                            \
+    } while (0)
+    if (a.nks == 13) {
+        if (drop) VB_FWD_LAUNCH(13, true); else VB_FWD_LAUNCH(13, false);
+    } else {
+        if (drop) VB_FWD_LAUNCH(0, true); else VB_FWD_LAUNCH(0, false);
+    }
+#undef VB_FWD_LAUNCH
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

@@ -183,6 +183,9 @@ class VitEngine(FlatParams):
         self.g = globals_
         self.layers = layers
         self.two_heads = "headd_w" in globals_
+        # dropout: rates used by the next training forward; set by the owning module from its constructor arguments
+        self.p_drop, self.p_attn = 0.0, 0.0
+        self._drop_counter = None
         # gradient-production order: heads + final norm, blocks L-1..0, embedding
         seg0 = ["head_w", "head_b"] + (["headd_w", "headd_b"] if self.two_heads else []) + ["lnf_w", "lnf_b"]
         emb = ["pos", "cls"] + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
@@ -191,6 +194,24 @@ class VitEngine(FlatParams):
             self._order += [((li, r), layers[li][r]) for r in LAYER_ROLES]
         self._order += [(("g", r), globals_[r]) for r in emb]
         self._layout([len(seg0)] + [len(LAYER_ROLES)] * num_layers + [len(emb)])
+
+    # ------------------------------------------------------------------ dropout -----------------------------------
+    EMBED_SITE = 4000
+
+    @staticmethod
+    def drop_site(layer, site):
+        """stream id of a dropout site: site 0 = attention out-proj output (vanilla_vit.py:78), 1 = after GELU (mlp.2, :38),
+        2 = MLP output (mlp.4, :42), 3 = attention probabilities (nn.MultiheadAttention(dropout=), :67); EMBED_SITE = Encoder.dropout (:104)."""
+        return layer * 8 + site
+
+    def _begin_dropout(self, ws):
+        """New masks for this forward: bump the device-side counter and snapshot it into the workspace (graph-capturable)."""
+        if self._drop_counter is None or self._drop_counter.device != self.flat.device:
+            self._drop_counter = torch.zeros(1, device=self.flat.device, dtype=torch.int32)
+        self._drop_counter.add_(1)
+        if "drop_seed" not in ws:
+            ws["drop_seed"] = torch.zeros(1, device=self.flat.device, dtype=torch.int32)
+        ws["drop_seed"].copy_(self._drop_counter)
 
     # ------------------------------------------------------------------ workspaces --------------------------------
     def workspace(self, B, training):
@@ -249,6 +270,9 @@ class VitEngine(FlatParams):
                  c_row_offset=self.n_prefix, aux_broadcast=True)
         ops.token_rows(x0, self.f(("g", "cls")), self.f(("g", "dist")) if self.n_prefix == 2 else None, pos.view(self.S, self.D),
                        self.n_prefix)
+        if ws.get("p_drop", 0.0) > 0:
+            x02 = x0.view(ws["M"], self.D)
+            ops.dropout_f32(x02, ws["p_drop"], ws["drop_seed"], self.EMBED_SITE, dst=x02)
 
     def _block_fwd(self, li, x_in, x_out, buf, ws, training):
         B, S, D, H = ws["B"], self.S, self.D, self.H
@@ -258,14 +282,24 @@ class VitEngine(FlatParams):
                           mean=buf["mean1"] if training else None, rstd=buf["rstd1"] if training else None)
         ops.gemm(buf["h1"], self.w((li, "qkv_w")), buf["qkv"], bias=self.f((li, "qkv_b")))
         qkv = buf["qkv"]
+        pd, pa = ws.get("p_drop", 0.0), ws.get("p_attn", 0.0)
         ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"] if training else None, B=B, H=H, S=S,
-                          tok_stride=1, batch_stride=S)
-        ops.gemm(buf["o"], self.w((li, "proj_w")), x12, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "proj_b")), aux=xin2)
+                          tok_stride=1, batch_stride=S, dropout=(pa, ws["drop_seed"], self.drop_site(li, 3)) if pa > 0 else None)
+        if pd > 0:   # x1 = dropout(out_proj(o)) + x_in   (vanilla_vit.py:77-79)
+            ops.gemm(buf["o"], self.w((li, "proj_w")), ws["tmp32"], bias=self.f((li, "proj_b")))
+            ops.dropout_f32(ws["tmp32"], pd, ws["drop_seed"], self.drop_site(li, 0), aux=xin2, dst=x12)
+        else:
+            ops.gemm(buf["o"], self.w((li, "proj_w")), x12, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "proj_b")), aux=xin2)
         ops.layernorm_fwd(x12, self.f((li, "ln2_w")), self.f((li, "ln2_b")), self.eps, y_bf16=buf["h2"],
                           mean=buf["mean2"] if training else None, rstd=buf["rstd2"] if training else None)
         ops.gemm(buf["h2"], self.w((li, "fc1_w")), buf["a"] if training else None, C2=buf["g"], epilogue=ops.EPI_GELU,
                  bias=self.f((li, "fc1_b")))
-        ops.gemm(buf["g"], self.w((li, "fc2_w")), xout2, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "fc2_b")), aux=x12)
+        if pd > 0:   # mlp.2: the same mask scales gelu(x) and the saved gelu'(x), so the backward epilogue stays a single multiply
+            ops.dropout_bf16_pair(buf["g"], buf["a"], pd, ws["drop_seed"], self.drop_site(li, 1))
+            ops.gemm(buf["g"], self.w((li, "fc2_w")), ws["tmp32"], bias=self.f((li, "fc2_b")))
+            ops.dropout_f32(ws["tmp32"], pd, ws["drop_seed"], self.drop_site(li, 2), aux=x12, dst=xout2)   # mlp.4 + residual (:83)
+        else:
+            ops.gemm(buf["g"], self.w((li, "fc2_w")), xout2, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "fc2_b")), aux=x12)
 
     def forward(self, images, *, training, want):
         """want: 'logits' (head(s) on the prefix token rows) or 'features' ([B,S,D] fp32 after the final norm).
@@ -275,6 +309,14 @@ class VitEngine(FlatParams):
             images = images.contiguous().float()
         B = images.shape[0]
         ws = self.workspace(B, training)
+        ws["p_drop"] = float(self.p_drop) if training else 0.0
+        ws["p_attn"] = float(self.p_attn) if training else 0.0
+        if ws["p_drop"] > 0 or ws["p_attn"] > 0:
+            self._begin_dropout(ws)
+            if ws["p_drop"] > 0 and "tmp32" not in ws:
+                ws["tmp32"] = torch.empty(ws["M"], self.D, device=self.flat.device, dtype=torch.float32)
+        else:
+            ws.setdefault("drop_seed", None)
         self.refresh_bf16()
         self._embed(ws, images)
         xs = ws["x"]
@@ -315,12 +357,20 @@ class VitEngine(FlatParams):
         d2 = d.view(M, D)
         x_last = ws["x"][L]
         last_b2 = (L - 1, "fc2_b")
+        pd, pa, seed = ws.get("p_drop", 0.0), ws.get("p_attn", 0.0), ws.get("drop_seed")
+
+        def masked_operand(layer, site, bias_key):
+            # hidden dropout in backward: the bf16 GEMM operand of the dropped linear output is keep * d / (1 - p) (mask regenerated
+            # from the forward's seed); its column sum is that layer's bias gradient
+            ops.dropout_f32(d2, pd, seed, self.drop_site(layer, site), dst_bf16=d_bf)
+            ops.colsum_bf16(d_bf, self.gview(bias_key))
         if want == "features":
             gy = grads[0]
             if gy.dtype != torch.float32 or not gy.is_contiguous():
                 gy = gy.contiguous().float()
-            ops.layernorm_bwd(gy.view(M, D), x_last.view(M, D), ws["meanf"], ws["rstdf"], self.f(("g", "lnf_w")), dx=d2, dx_bf16=d_bf,
-                              dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")), dx_colsum=self.gview(last_b2))
+            ops.layernorm_bwd(gy.view(M, D), x_last.view(M, D), ws["meanf"], ws["rstdf"], self.f(("g", "lnf_w")), dx=d2,
+                              dx_bf16=d_bf if pd == 0 else None, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
+                              dx_colsum=self.gview(last_b2) if pd == 0 else None)
         else:
             d.zero_()
             d_bf.zero_()
@@ -344,13 +394,15 @@ class VitEngine(FlatParams):
                 d_rows = d[:, t, :]
                 db_rows = d_bf.view(B, S, D)[:, t, :]
                 ops.layernorm_bwd(ws["dy_tok"][sl], xr, ws["meanf"][sl], ws["rstdf"][sl], self.f(("g", "lnf_w")), dx=d_rows,
-                                  dx_bf16=db_rows, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
-                                  dx_colsum=self.gview(last_b2))
+                                  dx_bf16=db_rows if pd == 0 else None, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
+                                  dx_colsum=self.gview(last_b2) if pd == 0 else None)
+        if pd > 0:
+            masked_operand(L - 1, 2, last_b2)
         self._seg_done(0)
         for li in range(L - 1, -1, -1):
             buf = ws["layer"][li]
             x_in = ws["x"][li].view(M, D)
-            if li == L - 1 and want == "logits" and self.n_prefix == 1:
+            if li == L - 1 and want == "logits" and self.n_prefix == 1 and pd == 0:
                 # ViT.forward only consumes x[:, 0] (vanilla_vit.py:212): the gradient entering the last block is non-zero
                 # on the class-token rows only, so its MLP / out-proj backward runs on B rows instead of B*S.  The rows are
                 # addressed in place through strided views (row pitch S * width); nothing is gathered.
@@ -377,22 +429,31 @@ class VitEngine(FlatParams):
                 self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"))
                 ops.colsum_bf16(ws["da"], self.gview((li, "fc1_b")))
                 ops.gemm(ws["da"], self.w((li, "fc1_w")), dh, b_major=1)
-                ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d2, dx=d2, dx_bf16=d_bf,
-                                  dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")), dx_colsum=self.gview((li, "proj_b")))
+                ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d2, dx=d2,
+                                  dx_bf16=d_bf if pd == 0 else None, dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")),
+                                  dx_colsum=self.gview((li, "proj_b")) if pd == 0 else None)
+                if pd > 0:
+                    masked_operand(li, 0, (li, "proj_b"))
                 # ---- attention ----
                 self._wgrad(d_bf, buf["o"], (li, "proj_w"))
                 ops.gemm(d_bf, self.w((li, "proj_w")), dh, b_major=1)
             qkv, dqkv = buf["qkv"], ws["dqkv"]
             ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"], dh, dqkv[:, :D], dqkv[:, D:2 * D],
-                              dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S)
+                              dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S,
+                              dropout=(pa, seed, self.drop_site(li, 3)) if pa > 0 else None)
             self._wgrad(dqkv, buf["h1"], (li, "qkv_w"))
             ops.colsum_bf16(dqkv, self.gview((li, "qkv_b")))
             ops.gemm(dqkv, self.w((li, "qkv_w")), dh, b_major=1)
             prev_b2 = self.gview((li - 1, "fc2_b")) if li > 0 else None
-            ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "ln1_w")), dres=d2, dx=d2, dx_bf16=d_bf if li > 0 else None,
-                              dgamma=self.gview((li, "ln1_w")), dbeta=self.gview((li, "ln1_b")), dx_colsum=prev_b2)
+            ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "ln1_w")), dres=d2, dx=d2,
+                              dx_bf16=d_bf if (li > 0 and pd == 0) else None, dgamma=self.gview((li, "ln1_w")), dbeta=self.gview((li, "ln1_b")),
+                              dx_colsum=prev_b2 if pd == 0 else None)
+            if pd > 0 and li > 0:
+                masked_operand(li - 1, 2, (li - 1, "fc2_b"))
             self._seg_done(L - li)
         # ---- embedding ----
+        if pd > 0:   # Encoder.dropout (vanilla_vit.py:104): gradient of x + pos is keep * d / (1 - p)
+            ops.dropout_f32(d2, pd, seed, self.EMBED_SITE, dst=d2)
         ops.embed_bwd(d, ws["possum"], ws["dxp"], self.gview(("g", "pos")).view(-1), self.gview(("g", "cls")).view(-1),
                       self.gview(("g", "dist")).view(-1) if self.n_prefix == 2 else None, self.gview(("g", "conv_b")), self.n_prefix)
         pat = ws["patches"].view(B * self.P, self.Kp_ld)[:, :self.Kp]

@@ -13,7 +13,8 @@ from ._lib import VbGemmDesc
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 2,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
-                     "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1}
+                     "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1, "vb_dropout_f32": 1, "vb_dropout_bf16_pair": 1,
+                     "vb_dropout_mask_u8": 1}
 
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_ACCUM = range(7)
 BF16, F32 = 0, 1
@@ -123,21 +124,55 @@ def _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, kpm):
     return d
 
 
-def attention_fwd(q, k, v, o, lse, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None):
+def _attn_dropout(d, dropout):
+    """dropout: None or (p, seed_dev int32/uint32 tensor, stream_id)."""
+    if dropout is not None and dropout[0] > 0:
+        d.dropout_p, d.dropout_seed, d.dropout_stream = float(dropout[0]), dropout[1].data_ptr(), int(dropout[2])
+
+
+def attention_fwd(q, k, v, o, lse, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None, dropout=None):
     """q/k/v/o: bf16 2-D views [tokens, H*64] (any row pitch); lse: fp32 [B,H,S] or None."""
     lib = _lib.load()
     d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask)
+    _attn_dropout(d, dropout)
     _lib.check(lib.vb_attention_fwd(ctypes.byref(d), _stream()), "vb_attention_fwd")
 
 
-def attention_bwd(q, k, v, o, lse, dout, dq, dk, dv, delta, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None):
+def attention_bwd(q, k, v, o, lse, dout, dq, dk, dv, delta, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None, dropout=None):
     lib = _lib.load()
     d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask)
+    _attn_dropout(d, dropout)
     d.dout, d.lddo = dout.data_ptr(), dout.stride(0)
     d.delta = delta.data_ptr()
     d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     d.lddq, d.lddk, d.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
     _lib.check(lib.vb_attention_bwd(ctypes.byref(d), _stream()), "vb_attention_bwd")
+
+
+def dropout_f32(src, p, seed_dev, stream_id, *, aux=None, dst=None, dst_bf16=None):
+    """dst / dst_bf16 = keep ? src / (1 - p) : 0 (+ aux); src, aux, dst fp32 [rows, cols] views, dst_bf16 bf16."""
+    lib = _lib.load()
+    rows, cols = src.shape
+    assert src.dtype == torch.float32 and src.stride(1) == 1
+    _lib.check(lib.vb_dropout_f32(src.data_ptr(), src.stride(0), _p(aux), aux.stride(0) if aux is not None else 0, _p(dst),
+                                  dst.stride(0) if dst is not None else 0, _p(dst_bf16), dst_bf16.stride(0) if dst_bf16 is not None else 0,
+                                  rows, cols, float(p), seed_dev.data_ptr(), int(stream_id), _stream()), "vb_dropout_f32")
+
+
+def dropout_bf16_pair(x1, x2, p, seed_dev, stream_id):
+    lib = _lib.load()
+    rows, cols = x1.shape
+    assert x1.dtype == torch.bfloat16 and x1.stride(1) == 1 and (x2 is None or (x2.shape == x1.shape and x2.stride(0) == x1.stride(0)))
+    _lib.check(lib.vb_dropout_bf16_pair(x1.data_ptr(), _p(x2), x1.stride(0), rows, cols, float(p), seed_dev.data_ptr(), int(stream_id),
+                                        _stream()), "vb_dropout_bf16_pair")
+
+
+def dropout_mask(n, p, seed_dev, stream_id, device):
+    """The keep mask (uint8, n elements) of dropout site `stream_id` (lets tests replay the kernels' masks)."""
+    lib = _lib.load()
+    out = torch.empty(n, device=device, dtype=torch.uint8)
+    _lib.check(lib.vb_dropout_mask_u8(out.data_ptr(), n, float(p), seed_dev.data_ptr(), int(stream_id), _stream()), "vb_dropout_mask_u8")
+    return out
 
 
 def cast_bf16(src, dst):

@@ -81,6 +81,9 @@ class Trainer:
         self.opt.zero_grad()
         self._loss.zero_()
         self._correct.zero_()
+        m = self.model
+        rates = (getattr(m, "dropout", getattr(m, "drop_rate", 0.0)), getattr(m, "attention_dropout", getattr(m, "attn_drop_rate", 0.0)))
+        eng.p_drop, eng.p_attn = (float(rates[0]), float(rates[1])) if m.training else (0.0, 0.0)
         outs, ws = eng.forward(images, training=True, want="logits")
         B = images.shape[0]
         world = self.reducer.world_size if self.reducer is not None else 1

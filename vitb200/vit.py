@@ -113,13 +113,14 @@ class _EncoderFn(torch.autograd.Function):
 
 def run_engine(engine, images, want, params, module_training, dropout_ps):
     needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    if module_training and any(p > 0 for p in dropout_ps):
-        raise NotImplementedError(
-            "vitb200: dropout > 0 in train() mode is not implemented in the fused kernels yet (SURVEY.md §8 f1); "
-            "construct the model with dropout=0.0 and attention_dropout=0.0, or call .eval()")
+    # dropout is active in train() mode only, as in nn.Dropout / nn.MultiheadAttention (vanilla_vit.py:38,42,67-68,94)
+    engine.p_drop, engine.p_attn = (float(dropout_ps[0]), float(dropout_ps[1])) if module_training else (0.0, 0.0)
     if needs_grad:
         return _EncoderFn.apply(engine, want, images, *params)
-    outs, _ = engine.forward(images, training=False, want=want)
+    if engine.p_drop > 0 or engine.p_attn > 0:   # train() under no_grad: dropout still applies; use the training workspaces
+        outs, _ = engine.forward(images, training=True, want=want)
+    else:
+        outs, _ = engine.forward(images, training=False, want=want)
     res = tuple(o.clone() for o in outs)
     return res if len(res) > 1 else res[0]
 
