@@ -18,8 +18,12 @@ def run(B, H, S, mode):
     delta = torch.empty(B, H, S, device="cuda")
     q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
     ops.attention_fwd(q, k, v, o, lse, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
-    ops.attention_bwd(q, k, v, o, lse, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], delta, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
+    cs = torch.zeros(3 * D, device="cuda")
+    ops.attention_bwd(q, k, v, o, lse, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], delta, B=B, H=H, S=S, tok_stride=1, batch_stride=S,
+                      dqkv_colsum=cs)
     torch.cuda.synchronize()
+    cs_ref = dqkv.float().sum(0)
+    run.colsum_err = ((cs - cs_ref).norm() / cs_ref.norm()).item()
     # fp32 reference
     qf, kf, vf = [t.float().view(B, S, H, 64).transpose(1, 2).requires_grad_(True) for t in (q, k, v)]
     of = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf)
@@ -30,8 +34,8 @@ def run(B, H, S, mode):
 
 ok = True
 for (B, H, S) in [(2, 3, 197), (3, 2, 198), (2, 4, 65), (1, 2, 128), (2, 2, 129), (1, 3, 208), (2, 1, 16), (1, 1, 192), (2, 2, 144), (37, 12, 197)]:
-    a, ref = run(B, H, S, "5")
     b, _ = run(B, H, S, "0")
+    a, ref = run(B, H, S, "5")
     D = H * 64
     errs = []
     for i, name in enumerate("qkv"):
@@ -39,7 +43,8 @@ for (B, H, S) in [(2, 3, 197), (3, 2, 198), (2, 4, 65), (1, 2, 128), (2, 2, 129)
         ea = ((a[:, sl] - ref[:, sl]).norm() / ref[:, sl].norm()).item()
         eb = ((b[:, sl] - ref[:, sl]).norm() / ref[:, sl].norm()).item()
         errs.append((name, ea, eb))
-    bad = any(not (ea < 2e-2) for _, ea, _ in errs)
+    bad = any(not (ea < 2e-2) for _, ea, _ in errs) or not (run.colsum_err < 1e-4)
+    errs.append(("colsum", run.colsum_err, run.colsum_err))
     ok &= not bad
     print(f"B={B} H={H} S={S}: " + "  ".join(f"d{n}: tc5 {ea:.2e} mma {eb:.2e}" for n, ea, eb in errs) + ("  FAIL" if bad else ""))
 print("ALL OK" if ok else "FAILED")

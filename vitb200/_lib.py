@@ -43,6 +43,7 @@ class VbAttnDesc(Structure):
         ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
         ("lddq", c_int64), ("lddk", c_int64), ("lddv", c_int64),
         ("dropout_p", c_float), ("dropout_stream", c_uint32), ("dropout_seed", c_void_p),
+        ("dqkv_colsum", c_void_p),
     ]
 
 

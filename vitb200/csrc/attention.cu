@@ -915,6 +915,19 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     return VB_OK;
 }
 
+extern "C" int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, float* out_accum, void* stream);   // elementwise.cu
+
+// paths that do not sum their output tiles in-kernel: dqkv_colsum[which] += column sums of dq / dk / dv
+static int bwd_colsums(const VbAttnDesc* d, void* stream) {
+    if (d->dqkv_colsum == nullptr) return VB_OK;
+    const int cols = d->H * 64;
+    const long long rows = (long long)d->B * d->S;
+    // token rows are contiguous for both layouts the engine uses (batch-first: b*S + s; sequence-first: s*N + b)
+    if (int rc = vb_colsum_bf16(d->dq, d->lddq, (int)rows, cols, d->dqkv_colsum, stream)) return rc;
+    if (int rc = vb_colsum_bf16(d->dk, d->lddk, (int)rows, cols, d->dqkv_colsum + cols, stream)) return rc;
+    return vb_colsum_bf16(d->dv, d->lddv, (int)rows, cols, d->dqkv_colsum + 2 * cols, stream);
+}
+
 extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     using namespace vb;
     if (int rc = check_arch()) return rc;
@@ -935,10 +948,12 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     if (d->dropout_p > 0.f) return fail(VB_ERR_UNSUPPORTED, "attention dropout needs the tcgen05 path (S <= 208, batch-first, no key-padding mask)");
     if (d->S <= 256) {
         const int n_mt = (d->S + 15) / 16;
-        if (n_mt <= 6) return launch_short_bwd<3>(p, st);
-        if (n_mt <= 10) return launch_short_bwd<5>(p, st);
-        if (n_mt <= 14) return launch_short_bwd<7>(p, st);
-        return launch_short_bwd<8>(p, st);
+        int rc;
+        if (n_mt <= 6) rc = launch_short_bwd<3>(p, st);
+        else if (n_mt <= 10) rc = launch_short_bwd<5>(p, st);
+        else if (n_mt <= 14) rc = launch_short_bwd<7>(p, st);
+        else rc = launch_short_bwd<8>(p, st);
+        return rc ? rc : bwd_colsums(d, stream);
     }
     const int smem = 6 * TILE_BYTES + 4 * TILE * (int)sizeof(float);
     static bool configured = false;
@@ -955,5 +970,5 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     VB_CUDA_CHECK(cudaGetLastError());
     attn_bwd_dq_kernel<<<grid, 128, 6 * TILE_BYTES, st>>>(p);
     VB_CUDA_CHECK(cudaGetLastError());
-    return VB_OK;
+    return bwd_colsums(d, stream);
 }

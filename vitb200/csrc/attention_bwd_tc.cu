@@ -61,6 +61,7 @@ struct Args {
     uint32_t drop_thresh, drop_stream;   // attention dropout (DROP instantiations)
     float drop_inv_keep;
     const uint32_t* drop_seed;
+    float* colsum;   // optional fp32 [3][H*64]: += column sums of the dq | dk | dv tiles (bias gradient of the in-projection)
 };
 
 using namespace atc;
@@ -202,19 +203,51 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int t = 0; t < n_t; ++t, ++ic) {
                 const int ks = ic & 1;
                 mbar_wait(out_ready, ic & 1);
+                const bool last = (t == n_t - 1);
+                uint8_t* kb = smem + kKvOff + ks * 2 * kBlk;
+                uint8_t* qb = smem + kQdoOff + qs * 2 * kQBytes;
                 if (lane == 0) {
-                    uint8_t* kb = smem + kKvOff + ks * 2 * kBlk;
                     tma_store_3d(&tmDV, kb, h * 64, t * 128, b);
                     tma_store_3d(&tmDK, kb + kBlk, h * 64, t * 128, b);
-                    if (t == n_t - 1) {
-                        uint8_t* qb = smem + kQdoOff + qs * 2 * kQBytes;
+                    if (last) {
                         tma_store_3d(&tmDQ, qb, h * 64, 0, b);
                         if (has_q1) tma_store_3d(&tmDQ, qb + kBlk, h * 64, 128, b);
                     }
                     tma_store_commit();
+                }
+                if (args.colsum != nullptr) {
+                    // While the tiles sit in shared memory: lane w sums bf16 columns 2w, 2w+1 (one 32-bit word of the swizzled row)
+                    // over the tile's valid rows and adds them to the in-projection bias gradient.
+                    auto tile_colsum = [&](uint32_t tile, int rows, float* dst) {
+                        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                        int r = 0;
+                        for (; r + 1 < rows; r += 2) {
+                            const uint32_t w0 = lds_u32(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                            const uint32_t w1 = lds_u32(tile + (r + 1) * 128 + (((lane >> 2) ^ ((r + 1) & 7)) << 4) + (lane & 3) * 4);
+                            a0 += __uint_as_float(w0 << 16); a1 += __uint_as_float(w0 & 0xFFFF0000u);
+                            b0 += __uint_as_float(w1 << 16); b1 += __uint_as_float(w1 & 0xFFFF0000u);
+                        }
+                        if (r < rows) {
+                            const uint32_t w0 = lds_u32(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                            a0 += __uint_as_float(w0 << 16); a1 += __uint_as_float(w0 & 0xFFFF0000u);
+                        }
+                        atomicAdd(dst + 2 * lane, a0 + b0);
+                        atomicAdd(dst + 2 * lane + 1, a1 + b1);
+                    };
+                    const int hd = args.H * 64;
+                    const int krows = min(128, S - t * 128);
+                    tile_colsum(smem_u32(kb), krows, args.colsum + 2 * hd + h * 64);          // dV
+                    tile_colsum(smem_u32(kb + kBlk), krows, args.colsum + hd + h * 64);       // dK
+                    if (last) {
+                        tile_colsum(smem_u32(qb), min(128, S), args.colsum + h * 64);         // dQ rows 0..127
+                        if (has_q1) tile_colsum(smem_u32(qb + kBlk), S - 128, args.colsum + h * 64);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
                     tma_store_wait_read<0>();
                     mbar_arrive(&kv_empty[ks]);
-                    if (t == n_t - 1) mbar_arrive(&qdo_empty[qs]);
+                    if (last) mbar_arrive(&qdo_empty[qs]);
                 }
                 __syncwarp();
             }
@@ -465,6 +498,7 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     a.scale = 0.125f; a.scale_log2 = 0.125f * 1.4426950408889634f;
     a.lse = d->lse; a.delta = d->delta;
     a.batch_stride = d->batch_stride;
+    a.colsum = d->dqkv_colsum;
     a.dbg = g_dbg;
     CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
     const uint64_t cols = (uint64_t)d->H * 64;

@@ -440,9 +440,8 @@ class VitEngine(FlatParams):
             qkv, dqkv = buf["qkv"], ws["dqkv"]
             ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"], dh, dqkv[:, :D], dqkv[:, D:2 * D],
                               dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S,
-                              dropout=(pa, seed, self.drop_site(li, 3)) if pa > 0 else None)
+                              dropout=(pa, seed, self.drop_site(li, 3)) if pa > 0 else None, dqkv_colsum=self.gview((li, "qkv_b")))
             self._wgrad(dqkv, buf["h1"], (li, "qkv_w"))
-            ops.colsum_bf16(dqkv, self.gview((li, "qkv_b")))
             ops.gemm(dqkv, self.w((li, "qkv_w")), dh, b_major=1)
             prev_b2 = self.gview((li - 1, "fc2_b")) if li > 0 else None
             ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "ln1_w")), dres=d2, dx=d2,

@@ -138,10 +138,15 @@ def attention_fwd(q, k, v, o, lse, *, B, H, S, tok_stride, batch_stride, key_pad
     _lib.check(lib.vb_attention_fwd(ctypes.byref(d), _stream()), "vb_attention_fwd")
 
 
-def attention_bwd(q, k, v, o, lse, dout, dq, dk, dv, delta, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None, dropout=None):
+def attention_bwd(q, k, v, o, lse, dout, dq, dk, dv, delta, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None, dropout=None,
+                  dqkv_colsum=None):
+    """dqkv_colsum: optional fp32 [3*H*64] accumulator of the column sums of dq|dk|dv (bias gradient of the packed in-projection)."""
     lib = _lib.load()
     d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask)
     _attn_dropout(d, dropout)
+    if dqkv_colsum is not None:
+        assert dqkv_colsum.dtype == torch.float32 and dqkv_colsum.is_contiguous() and dqkv_colsum.numel() == 3 * H * 64
+        d.dqkv_colsum = dqkv_colsum.data_ptr()
     d.dout, d.lddo = dout.data_ptr(), dout.stride(0)
     d.delta = delta.data_ptr()
     d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
