@@ -136,8 +136,9 @@ typedef struct VbAttnDesc {
     uint32_t dropout_stream;
     const uint32_t* dropout_seed; /* device pointer */
     /* backward only, optional: fp32 [3][H*64]; the column sums of dq | dk | dv over all tokens are ACCUMULATED into it (the bias
-     * gradient of the packed in-projection, torch/nn/functional.py:5835-5847).  The tcgen05 backward sums its output tiles while
-     * they sit in shared memory (atomicAdd); the other paths run the column-sum kernel after the attention kernels. */
+     * gradient of the packed in-projection, torch/nn/functional.py:5835-5847).  The tcgen05 backward sums its accumulator slices
+     * in registers (warp butterfly + atomicAdd) and leaves the dk part untouched: sum_k dS[q,k] = 0 makes the key-bias gradient
+     * exactly zero (softmax ignores a constant key offset).  The other paths run the column-sum kernel on dq, dk, dv. */
     float* dqkv_colsum;
 } VbAttnDesc;
 VB_API int vb_attention_fwd(const VbAttnDesc* desc, void* stream);

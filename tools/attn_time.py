@@ -32,7 +32,9 @@ def timeit(f, n=10):
 
 
 fwd = lambda: ops.attention_fwd(q, k, v, o, lse, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
-bwd = lambda: ops.attention_bwd(q, k, v, o, lse, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], delta, B=B, H=H, S=S, tok_stride=1, batch_stride=S)
+cs = torch.zeros(3 * D, device="cuda") if os.environ.get("ATTN_TIME_COLSUM") else None
+bwd = lambda: ops.attention_bwd(q, k, v, o, lse, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], delta, B=B, H=H, S=S, tok_stride=1, batch_stride=S,
+                                dqkv_colsum=cs)
 tf, tb = timeit(fwd), timeit(bwd)
 fl = 4.0 * S * S * 64 * B * H
 print(f"B={B} H={H} S={S} TC_BWD={os.environ.get('VITB200_ATTN_TC_BWD','0')}: fwd {tf*1e3:.1f} us ({fl/tf/1e9:.0f} TF/s)  bwd {tb*1e3:.1f} us ({2.5*fl/tb/1e9:.0f} TF/s)")

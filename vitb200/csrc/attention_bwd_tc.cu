@@ -61,7 +61,7 @@ struct Args {
     uint32_t drop_thresh, drop_stream;   // attention dropout (DROP instantiations)
     float drop_inv_keep;
     const uint32_t* drop_seed;
-    float* colsum;   // optional fp32 [3][H*64]: += column sums of the dq | dk | dv tiles (bias gradient of the in-projection)
+    float* colsum;   // optional fp32 [3][H*64]: += column sums of dq and dv (in-projection bias gradient; the dk part is exactly 0)
 };
 
 using namespace atc;
@@ -214,34 +214,6 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         if (has_q1) tma_store_3d(&tmDQ, qb + kBlk, h * 64, 128, b);
                     }
                     tma_store_commit();
-                }
-                if (args.colsum != nullptr) {
-                    // While the tiles sit in shared memory: lane w sums bf16 columns 2w, 2w+1 (one 32-bit word of the swizzled row)
-                    // over the tile's valid rows and adds them to the in-projection bias gradient.
-                    auto tile_colsum = [&](uint32_t tile, int rows, float* dst) {
-                        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-                        int r = 0;
-                        for (; r + 1 < rows; r += 2) {
-                            const uint32_t w0 = lds_u32(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-                            const uint32_t w1 = lds_u32(tile + (r + 1) * 128 + (((lane >> 2) ^ ((r + 1) & 7)) << 4) + (lane & 3) * 4);
-                            a0 += __uint_as_float(w0 << 16); a1 += __uint_as_float(w0 & 0xFFFF0000u);
-                            b0 += __uint_as_float(w1 << 16); b1 += __uint_as_float(w1 & 0xFFFF0000u);
-                        }
-                        if (r < rows) {
-                            const uint32_t w0 = lds_u32(tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-                            a0 += __uint_as_float(w0 << 16); a1 += __uint_as_float(w0 & 0xFFFF0000u);
-                        }
-                        atomicAdd(dst + 2 * lane, a0 + b0);
-                        atomicAdd(dst + 2 * lane + 1, a1 + b1);
-                    };
-                    const int hd = args.H * 64;
-                    const int krows = min(128, S - t * 128);
-                    tile_colsum(smem_u32(kb), krows, args.colsum + 2 * hd + h * 64);          // dV
-                    tile_colsum(smem_u32(kb + kBlk), krows, args.colsum + hd + h * 64);       // dK
-                    if (last) {
-                        tile_colsum(smem_u32(qb), min(128, S), args.colsum + h * 64);         // dQ rows 0..127
-                        if (has_q1) tile_colsum(smem_u32(qb + kBlk), S - 128, args.colsum + h * 64);
-                    }
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -415,6 +387,27 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tcgen05_fence_after();
                 if (dbg_on) args.dbg[ic * 16 + 6] = clock64();
                 const bool last = (t == n_t - 1);
+                // In-projection bias gradient: column sums of this warp's 32 x 32 accumulator slice by a transposing butterfly (31
+                // shuffles: after the step with offset o a lane keeps the half of its columns whose bit o matches its lane bit), one
+                // atomicAdd per lane.  Rows beyond the sequence are excluded.
+                auto colsum32 = [&](const uint32_t (&r)[32], float mul, bool row_valid, float* dst) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = row_valid ? __uint_as_float(r[i]) * mul : 0.f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = up ? v[i] : v[i + off];
+                            const float keep = up ? v[i + off] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    atomicAdd(dst + lane, v[0]);
+                };
+                const bool do_cs = args.colsum != nullptr;
+                const int hd = args.H * 64, hcol = (head - (head / args.H) * args.H) * 64;
                 auto stage32 = [&](const uint32_t (&r)[32], uint32_t row_addr, uint32_t hi, float mul) {
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4) {
@@ -432,6 +425,9 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tmem_ld_32x32b_x32(t_lane + col_a, r);
                     tmem_ld_wait();
                     stage32(r, part == 2 ? kv_row + kBlk : kv_row, part == 1 ? 1u : 0u, part == 2 ? args.scale : 1.0f);
+                    // part 0: dV columns 0..31, part 1: dV 32..63.  dK is skipped: sum_k dS[q,k] = sum_k P (dP - delta) = 0 for every query, so
+                    // the column sum of dK = dS^T Q (the key-bias gradient) is exactly zero — softmax ignores a constant key offset.
+                    if (do_cs && part < 2) colsum32(r, 1.0f, t * 128 + row_in_tile < S, args.colsum + 2 * hd + hcol + part * 32);
                 }
                 if (part == 0) {
                     uint32_t r[32];
@@ -446,6 +442,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + dq1c[i]);
                         stage32(r, q_row + kBlk, part - 1, args.scale);
+                        if (do_cs) colsum32(r, args.scale, 128 + row_in_tile < S, args.colsum + hcol + (part - 1) * 32);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) dq1c[i] = __uint_as_float(r[i]);
@@ -456,6 +453,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tmem_ld_32x32b_x32(t_lane + kColDQ0 + part * 32, r);
                     tmem_ld_wait();
                     stage32(r, q_row, part, args.scale);
+                    if (do_cs) colsum32(r, args.scale, row_in_tile < S, args.colsum + hcol + part * 32);
                 }
                 tcgen05_fence_before();
                 fence_proxy_async_smem();

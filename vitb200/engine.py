@@ -13,6 +13,8 @@ import torch
 
 from . import ops
 
+import os
+_FUSED_QKV_COLSUM = os.environ.get("VITB200_FUSED_QKV_COLSUM", "1") != "0"   # A/B switch: in-kernel column sums of dq|dk|dv
 LAYER_ROLES = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
 _ALIGN = 64  # elements; keeps every parameter 256-byte (fp32) / 128-byte (bf16) aligned for TMA and float4 access
 
@@ -440,8 +442,11 @@ class VitEngine(FlatParams):
             qkv, dqkv = buf["qkv"], ws["dqkv"]
             ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"], dh, dqkv[:, :D], dqkv[:, D:2 * D],
                               dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S,
-                              dropout=(pa, seed, self.drop_site(li, 3)) if pa > 0 else None, dqkv_colsum=self.gview((li, "qkv_b")))
+                              dropout=(pa, seed, self.drop_site(li, 3)) if pa > 0 else None,
+                              dqkv_colsum=self.gview((li, "qkv_b")) if _FUSED_QKV_COLSUM else None)
             self._wgrad(dqkv, buf["h1"], (li, "qkv_w"))
+            if not _FUSED_QKV_COLSUM:
+                ops.colsum_bf16(dqkv, self.gview((li, "qkv_b")))
             ops.gemm(dqkv, self.w((li, "qkv_w")), dh, b_major=1)
             prev_b2 = self.gview((li - 1, "fc2_b")) if li > 0 else None
             ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "ln1_w")), dres=d2, dx=d2,
