@@ -153,7 +153,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=dev)
         from vitb200.dp import GradReducer
-        reducer = GradReducer()
+        reducer = GradReducer(bucket_bytes=int(os.environ.get("VITB200_DP_BUCKET_MB", "48")) << 20)
     W = max(3, args.warmup)
     K = args.steps
     B = args.batch
@@ -263,10 +263,11 @@ def main():
             return out
 
         ops.gemm = timed_gemm
+        was_graph = trainer.use_cuda_graph
         trainer.use_cuda_graph = False      # one eager step so that every GEMM launch can be bracketed by events
         trainer.step(images, labels)
         torch.cuda.synchronize()
-        trainer.use_cuda_graph = (not args.no_graph) and reducer is None
+        trainer.use_cuda_graph = was_graph
         ops.gemm = orig
         gemm_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
         gemm_flops = sum(f for _, _, f in rec)
@@ -313,7 +314,13 @@ def main():
         print(json.dumps(line), flush=True)
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
+        if os.environ.get("VITB200_BENCH_DEBUG"):
+            print(f"[rank {rank}] before destroy_process_group", file=sys.stderr, flush=True)
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        if os.environ.get("VITB200_BENCH_DEBUG"):
+            print(f"[rank {rank}] after destroy_process_group", file=sys.stderr, flush=True)
     return 0
 
 

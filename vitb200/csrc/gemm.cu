@@ -30,6 +30,7 @@ constexpr uint32_t kEpiWarps = 8;
 constexpr uint32_t kFirstEpiWarp = 4;
 constexpr uint32_t kThreads = (kFirstEpiWarp + kEpiWarps) * 32;  // 384
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSchedStages = 4;   // depth of the dynamic scheduler's unit ring
 
 struct GemmArgs {
     int M, N, K, batches;
@@ -37,6 +38,7 @@ struct GemmArgs {
     int split_k, kb_per_split, num_units;
     int c_row_offset, aux_bcast, b_batched;
     int direct;
+    int* sched_counter;   // non-null: dynamic tile scheduling (units beyond the first per cluster are handed out by atomicAdd)
     const float* bias;
     void* C;
     void* C2;
@@ -53,10 +55,10 @@ struct EpiTraits {
     static constexpr uint32_t kBStageBytes = B_STAGE_BYTES / CG;
     static constexpr uint32_t kStageBytes = A_STAGE_BYTES + kBStageBytes;
     static constexpr uint32_t kEpiBytes = kEpiWarps * kBufsPerWarp * EPI_BUF_BYTES;
-    static constexpr uint32_t kBudget = 232448 - 1024 /*align*/ - 256 /*barriers*/;
+    static constexpr uint32_t kBudget = 232448 - 1024 /*align*/ - 512 /*barriers + scheduler ring*/;
     static constexpr uint32_t kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
     static constexpr uint32_t kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 1024;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + 1024;
 };
 
 // Exact-erf GELU via the Abramowitz-Stegun 7.1.26 rational approximation of erf (|abs err| < 1.5e-7, far below
@@ -197,7 +199,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
     uint64_t* aux_bar = tmem_empty_bar + 2;         // [kEpiWarps]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+    uint64_t* sched_full = aux_bar + kEpiWarps;          // [kSchedStages] scheduler ring: entry written
+    uint64_t* sched_empty = sched_full + kSchedStages;   // [kSchedStages] (leader's copy) entry read by every consumer of the pair
+    int* sched_unit = reinterpret_cast<int*>(sched_empty + kSchedStages);   // [kSchedStages]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sched_unit + kSchedStages);
 
     const uint32_t warp_idx = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -219,6 +224,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_init(&tmem_empty_bar[i], kEpiWarps * CG);   // (leader's copy) every epilogue warp of the pair arrives
         }
         for (uint32_t i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+        for (uint32_t i = 0; i < kSchedStages; ++i) {
+            mbar_init(&sched_full[i], 1);
+            mbar_init(&sched_empty[i], (1 + kEpiWarps) * CG + 1);   // producer + epilogue warps of each CTA, MMA issuer of the leader
+        }
         fence_barrier_init();
     }
     if (warp_idx == 2) {
@@ -231,11 +240,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp_idx == 0) {
+    // ---- tile scheduling ----------------------------------------------------------------------------------------------
+    // Static: cluster c owns units c, c + #clusters, ...  Dynamic (args.sched_counter): the first unit is still the cluster index,
+    // later ones come from a global atomic counter fetched by the scheduler warp of the leader CTA and broadcast to every role of
+    // both CTAs through a small shared-memory ring — so a cluster that starts late (its SMs were held by a co-running kernel,
+    // e.g. the NCCL all-reduce of the previous gradient bucket) simply takes fewer units instead of finishing a wave late.
+    const bool dynamic = args.sched_counter != nullptr;
+    const uint32_t sched_empty_leader = (CG == 2) ? mapa_u32(smem_u32(&sched_empty[0]), 0) : smem_u32(&sched_empty[0]);
+    struct SchedReader {
+        uint32_t stage = 0, phase = 0;
+    };
+    // next unit for this role (-1 = none); called by one lane (producer, MMA) or by the whole warp (epilogue: lane 0 releases)
+    auto sched_next = [&](SchedReader& rd, int u, bool whole_warp) -> int {
+        if (!dynamic) {
+            const int n = u + unit_stride;
+            return n < args.num_units ? n : -1;
+        }
+        mbar_wait(&sched_full[rd.stage], rd.phase);
+        const int n = *reinterpret_cast<volatile int*>(&sched_unit[rd.stage]);
+        if (whole_warp) __syncwarp();
+        if (!whole_warp || lane == 0) {
+            if (CG == 2 && rank != 0) mbar_arrive_cluster(sched_empty_leader + rd.stage * 8);
+            else mbar_arrive(&sched_empty[rd.stage]);
+        }
+        if (++rd.stage == kSchedStages) { rd.stage = 0; rd.phase ^= 1; }
+        return n;
+    };
+
+    if (warp_idx == 3) {
+        // ===================================== dynamic tile scheduler (leader CTA) ==============
+        if (dynamic && lane == 0 && rank == 0) {
+            const int nclusters = unit_stride;
+            const int total_fetches = (args.num_units > nclusters ? args.num_units - nclusters : 0) + nclusters;
+            const uint32_t unit_peer = (CG == 2) ? mapa_u32(smem_u32(&sched_unit[0]), 1) : 0;
+            const uint32_t full_peer = (CG == 2) ? mapa_u32(smem_u32(&sched_full[0]), 1) : 0;
+            uint32_t stage = 0, phase = 0;
+            while (true) {
+                mbar_wait(&sched_empty[stage], phase ^ 1);
+                const int v = atomicAdd(args.sched_counter, 1);
+                if (v == total_fetches - 1) atomicExch(args.sched_counter, 0);   // the last fetch of the launch re-arms the counter
+                int u = v + nclusters;
+                if (u >= args.num_units) u = -1;
+                sched_unit[stage] = u;
+                if (CG == 2) {
+                    st_shared_cluster_u32(unit_peer + stage * 4, (uint32_t)u);
+                    mbar_arrive_cluster_release(full_peer + stage * 8);
+                }
+                mbar_arrive(&sched_full[stage]);
+                if (u < 0) break;
+                if (++stage == kSchedStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int u = unit0; u < args.num_units; u += unit_stride) {
+            SchedReader rd;
+            for (int u = unit0; u >= 0; u = sched_next(rd, u, false)) {
                 const UnitCoord c = decode_unit<CG>(args, u, rank);
                 const int bb = args.b_batched ? c.batch : 0;
                 const int n_row0 = c.n_blk * BN + rank * (BN / CG);   // this CTA's share of the B tile
@@ -293,7 +354,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             constexpr uint32_t a_kstep = (AMAJ == 0) ? UK * 2 : UK * 128;
             constexpr uint32_t b_kstep = (BMAJ == 0) ? UK * 2 : UK * 128;
             uint32_t stage = 0, phase = 0, it = 0;
-            for (int u = unit0; u < args.num_units; u += unit_stride, ++it) {
+            SchedReader rd;
+            for (int u = unit0; u >= 0; u = sched_next(rd, u, false), ++it) {
                 const UnitCoord c = decode_unit<CG>(args, u, 0);
                 const uint32_t as = it & 1, ap = (it >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[as], ap ^ 1);
@@ -336,18 +398,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t row_off = lane * 128;
         uint32_t aux_phase = 0;
 
-        // Finds the first valid (unit, chunk) at or after (u, ch) for this warp; returns false when done.
-        auto next_valid = [&](int& u, int& ch) -> bool {
-            while (u < args.num_units) {
-                if (ch < int(kChunks)) {
-                    const UnitCoord c = decode_unit<CG>(args, u, rank);
-                    const int col0 = c.n_blk * BN + half * 128 + ch * CPC;
-                    if (col0 < args.N) return true;
-                }
-                u += unit_stride;
-                ch = 0;
-            }
-            return false;
+        // number of this warp's column chunks of unit u that lie inside N (chunks are ordered by column)
+        auto valid_chunks = [&](int u) -> int {
+            const UnitCoord c = decode_unit<CG>(args, u, rank);
+            int n = 0;
+#pragma unroll
+            for (int ch = 0; ch < int(kChunks); ++ch)
+                if (c.n_blk * BN + half * 128 + ch * int(CPC) < args.N) n = ch + 1;
+            return n;
         };
         auto issue_aux = [&](int u, int ch) {
             const UnitCoord c = decode_unit<CG>(args, u, rank);
@@ -356,20 +414,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_arrive_expect_tx(&aux_bar[ew], EPI_BUF_BYTES);
             tma_load_3d(buf_aux, &tmAux, &aux_bar[ew], col0, row0, args.aux_bcast ? 0 : c.batch);
         };
-
-        if constexpr (T::kHasAux) {
-            if (!args.direct && lane == 0) {
-                int u = unit0, ch = 0;
-                if (next_valid(u, ch)) issue_aux(u, ch);
-            }
-        }
+        // The aux tile of the next chunk is prefetched one chunk ahead, across the unit boundary when the next unit is known
+        // (aux_issued is warp-uniform; lane 0 issues).
+        bool aux_issued = false;
+        SchedReader rd;
+        int cur = unit0;
+        int nxt = sched_next(rd, cur, true);
 
         uint32_t it = 0;
         auto release_tmem = [&](uint32_t as) {
             if (CG == 2 && rank != 0) mbar_arrive_cluster(tmem_empty_remote + as * 8);
             else mbar_arrive(&tmem_empty_bar[as]);
         };
-        for (int u = unit0; u < args.num_units; u += unit_stride, ++it) {
+        for (; cur >= 0; cur = nxt, nxt = (cur >= 0 ? sched_next(rd, cur, true) : -1), ++it) {
+            const int u = cur;
             const UnitCoord c = decode_unit<CG>(args, u, rank);
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             mbar_wait(&tmem_full_bar[as], ap);
@@ -378,10 +436,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int row_in_batch = c.m_blk * BM + quad * 32 + lane;  // GEMM row of this thread
             const int row0 = args.c_row_offset + c.m_blk * BM + quad * 32;
 
-            int n_valid_chunks = 0;
-#pragma unroll
-            for (int ch = 0; ch < int(kChunks); ++ch)
-                if (c.n_blk * BN + half * 128 + ch * int(CPC) < args.N) n_valid_chunks = ch + 1;
+            const int n_valid_chunks = valid_chunks(u);
             if (n_valid_chunks == 0) {
                 tcgen05_fence_before();
                 __syncwarp();
@@ -393,6 +448,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int col0 = c.n_blk * BN + half * 128 + ch * CPC;
                 if constexpr (T::kHasAux) {
                     if (!args.direct) {
+                        if (!aux_issued && lane == 0) issue_aux(u, ch);   // no look-ahead was possible (first chunk, ragged N)
                         mbar_wait(&aux_bar[ew], aux_phase);
                         aux_phase ^= 1;
                     }
@@ -548,13 +604,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (!args.direct) {
                     fence_proxy_async_smem();  // staging writes (and aux reads) ordered before the async proxy touches smem
                     __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (T::kHasAux) {
-                            // aux buffer consumed: prefetch the aux tile of the next chunk this warp will process
-                            int nu = u, nch = ch + 1;
-                            if (nch >= n_valid_chunks) { nu += unit_stride; nch = 0; }
-                            if (next_valid(nu, nch)) issue_aux(nu, nch);
+                    if constexpr (T::kHasAux) {
+                        // aux buffer consumed: prefetch the aux tile of the next chunk this warp will process
+                        if (ch + 1 < n_valid_chunks) {
+                            aux_issued = true;
+                            if (lane == 0) issue_aux(u, ch + 1);
+                        } else if (nxt >= 0 && valid_chunks(nxt) > 0) {
+                            aux_issued = true;
+                            if (lane == 0) issue_aux(nxt, 0);
+                        } else {
+                            aux_issued = false;
                         }
+                    }
+                    if (lane == 0) {
                         if constexpr (EPI == VB_EPI_ACCUM) {
                             tma_reduce_add_3d(&tmC, obuf, col0, row0, c.batch);
                         } else {
@@ -652,6 +714,33 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMa
     return VB_OK;
 }
 
+// Dynamic tile scheduling (see the kernel): VITB200_GEMM_DYNAMIC=0 selects the static round-robin schedule.
+static int dynamic_scheduling() {
+    static int dyn = -1;
+    if (dyn < 0) {
+        const char* e = getenv("VITB200_GEMM_DYNAMIC");
+        dyn = (e && e[0] == '0') ? 0 : 1;
+    }
+    return dyn;
+}
+// Pool of self-re-arming unit counters (the last fetch of a launch resets its counter), handed out round-robin so that
+// launches that may overlap never share one.  Allocated on first use (before any CUDA-graph capture: the first step is eager).
+static int* next_sched_counter() {
+    constexpr int kPool = 256;
+    static int* pool[16] = {};
+    static unsigned next[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (pool[dev] == nullptr) {
+        int* p = nullptr;
+        if (cudaMalloc(&p, kPool * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, kPool * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaDeviceSynchronize();
+        pool[dev] = p;
+    }
+    return pool[dev] + (next[dev]++ % kPool);
+}
+
 static int default_cta_group() {
     static int cg = 0;
     if (cg == 0) {
@@ -695,6 +784,7 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     a.aux_bcast = d->aux_batch_broadcast;
     a.b_batched = d->batch_stride_b != 0;
     a.direct = d->debug_direct_store;
+    a.sched_counter = nullptr;
     a.bias = d->bias;
     a.C = d->C; a.C2 = d->C2; a.AUX = d->AUX;
     a.ldc = d->ldc; a.ldc2 = d->ldc2; a.ldaux = d->ldaux;
@@ -737,6 +827,7 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     if (grid > a.num_units * cg) grid = a.num_units * cg;
     grid -= grid % cg;
     if (grid < cg) grid = cg;
+    if (dynamic_scheduling() && a.num_units > grid / cg) a.sched_counter = next_sched_counter();   // more units than clusters
 
 #define VB_LAUNCH(AM, BMJ, EP, CD)                                                              \
     do {                                                                                        \
