@@ -7,6 +7,11 @@
 // 67-68,94 — same Bernoulli(1-p) keep / scale-by-1/(1-p) semantics, different (documented) random stream.
 #pragma once
 #include <cstdint>
+#ifndef __CUDACC__   // host-only builds (tests/test_dropout_cpu.py compiles this header with g++)
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#endif
 
 namespace vb {
 
