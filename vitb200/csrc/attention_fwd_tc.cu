@@ -3,8 +3,10 @@
 // One persistent CTA per SM walks (batch, head) pairs; Q, K, V of a head arrive by TMA in a 2-stage ring.  Per 128-query tile:
 //   S = Q K^T        tcgen05.mma 128 x npad x 64 (SS) into one of two 208-column TMEM slots (tile j+1 is computed while the
 //                    softmax of tile j runs)
-//   softmax          384 threads, THREE PER QUERY ROW: 16-key group g belongs to column part g % 3.  Pass 1: partial row
-//                    maxima, exchanged through shared memory between the three warps of a TMEM lane quadrant (named barrier).
+//   softmax          TWO WARP GROUPS of 256 threads ping-pong the tiles (group j & 1 owns tile j and TMEM slot j & 1), so the
+//                    exp pass of one tile (MUFU) overlaps the row-max pass and the hand-offs of the other.  Inside a group TWO
+//                    THREADS PER QUERY ROW: 16-key group g belongs to column part g % 2.  Pass 1: partial row maxima,
+//                    exchanged through shared memory between the two warps of a TMEM lane quadrant (named barrier).
 //                    Pass 2: P = exp2(s c - m c) packed to bf16 over the group's own fp32 columns [16g, 16g+8) (hazard-free
 //                    for any group-to-warp assignment), partial row sums.
 //   O = P V          tcgen05.mma 128 x 64 x npad with the A operand read from TMEM, V as an MN-major smem operand; issued in
@@ -27,16 +29,16 @@ int make_tmap_3d(CUtensorMap* m, int dtype, const void* ptr, uint64_t d0, uint64
 namespace fwd3 {
 using namespace atc;
 
-constexpr int kEwWarps = 12;
+constexpr int kEwWarps = 16;                     // two softmax groups x (4 lane quadrants x 2 column parts)
 constexpr int kRoWarps = 4;                      // read-out warps (one per TMEM lane quadrant): O / l -> bf16 tile, lse
 constexpr int kThreads = 128 + (kEwWarps + kRoWarps) * 32;   // warps 0-3: TMA loader, MMA issuer, TMEM alloc + store warp, idle
 constexpr uint32_t kMaxQ = 208;
 constexpr uint32_t kOpBytes = kMaxQ * 128;      // Q, K or V of one head
 constexpr uint32_t kStageBytes = 3 * kOpBytes;
 constexpr uint32_t kOutOff = 2 * kStageBytes;   // 2 output tiles of 128 rows x 128 B
-constexpr uint32_t kXmOff = kOutOff + 2 * 16384;   // partial maxima  [4 tile slots][3 parts][128 rows]
-constexpr uint32_t kXsOff = kXmOff + 4 * 3 * 128 * 4;
-constexpr uint32_t kBarOff = kXsOff + 4 * 3 * 128 * 4;
+constexpr uint32_t kXmOff = kOutOff + 2 * 16384;   // partial maxima  [4 tile slots][2 parts][128 rows]
+constexpr uint32_t kXsOff = kXmOff + 4 * 2 * 128 * 4;
+constexpr uint32_t kBarOff = kXsOff + 4 * 2 * 128 * 4;
 constexpr uint32_t kSmemBytes = kBarOff + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 constexpr uint32_t kColO = 416;
@@ -62,12 +64,12 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* kv_full = bars;          // [2]
     uint64_t* kv_empty = bars + 2;     // [2] tcgen05.commit after the head's last P V product
     uint64_t* s_full = bars + 4;       // [2] per TMEM slot
-    uint64_t* p_full = bars + 6;       // [2] count kEwWarps: keys < 128 packed / all keys packed
-    uint64_t* o_full = bars + 8;
-    uint64_t* o_free = bars + 9;       // count kRoWarps: the O accumulator has been read out
-    uint64_t* out_ready = bars + 10;   // [2] count kRoWarps: output tile staged
-    uint64_t* out_free = bars + 12;    // [2] count 1: the TMA store has finished reading the tile
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* p_full = bars + 6;       // [2 slots][2] count 8 (one softmax group): keys < 128 packed / all keys packed
+    uint64_t* o_full = bars + 10;
+    uint64_t* o_free = bars + 11;      // count kRoWarps: the O accumulator has been read out
+    uint64_t* out_ready = bars + 12;   // [2] count kRoWarps: output tile staged
+    uint64_t* out_free = bars + 14;    // [2] count 1: the TMA store has finished reading the tile
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
 
     const uint32_t warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = args.S, n_qt = args.n_qt;
@@ -80,7 +82,8 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     if (warp_idx == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], kEwWarps);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[2 * i], 8); mbar_init(&p_full[2 * i + 1], 8);
             mbar_init(&out_ready[i], kRoWarps); mbar_init(&out_free[i], 1);
         }
         mbar_init(o_full, 1); mbar_init(o_free, kRoWarps);
@@ -148,13 +151,15 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             __syncwarp();
         };
+        // Program order S(0) S(1) PV(0) S(2) PV(1) S(3) ...: S(j+2) re-uses the slot whose P was consumed by PV(j) (in-order tensor pipe),
+        // and it is what lets softmax group j & 1 start its next tile — so a group can never run a whole tile ahead of its slowest warp.
         if (total_tiles > 0) issue_s(0);
+        if (total_tiles > 1) issue_s(1);
         for (int j = 0; j < total_tiles; ++j) {
-            if (j + 1 < total_tiles) issue_s(j + 1);
-            const int hc = j / n_qt, qt = j - hc * n_qt, st = hc & 1;
+            const int hc = j / n_qt, qt = j - hc * n_qt, st = hc & 1, slot = j & 1, par = (j >> 1) & 1;
             const uint64_t bd = umma_smem_desc(vdesc, smem_u32(smem + st * kStageBytes + 2 * kOpBytes));
-            const uint32_t a0 = tb + (j & 1) * kMaxQ;
-            mbar_wait(&p_full[0], j & 1);
+            const uint32_t a0 = tb + slot * kMaxQ;
+            mbar_wait(&p_full[2 * slot], par);
             mbar_wait(o_free, (j & 1) ^ 1);
             tcgen05_fence_after();
             if (elect_one()) {
@@ -163,7 +168,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (k < jA) umma_bf16_ts(tb + kColO, a0 + 16 * k, bd + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : 0u);
             }
             __syncwarp();
-            mbar_wait(&p_full[1], j & 1);
+            mbar_wait(&p_full[2 * slot + 1], par);
             tcgen05_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -173,24 +178,24 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (qt == n_qt - 1) umma_commit(&kv_empty[st]);
             }
             __syncwarp();
+            if (j + 2 < total_tiles) issue_s(j + 2);
         }
     } else if (warp_idx >= 4 && warp_idx < 4 + kEwWarps) {
         // ---------------- softmax ----------------
-        const uint32_t quad = warp_idx & 3, part = (warp_idx - 4) >> 2;
+        const uint32_t quad = warp_idx & 3, grp = (warp_idx - 4) >> 3, part = ((warp_idx - 4) >> 2) & 1;
         const uint32_t t_lane = tmem_base + ((quad * 32) << 16);
         const int row_in_tile = quad * 32 + lane;
         const float c = args.scale_log2;
-        const uint32_t swz = (uint32_t)(row_in_tile & 7);
         const uint32_t xm_u32 = smem_u32(smem + kXmOff), xs_u32 = smem_u32(smem + kXsOff);
-        const uint32_t out_row = smem_u32(smem + kOutOff) + row_in_tile * 128;
         const uint32_t drop_key = DROP ? dropout_key(*args.drop_seed, args.drop_stream) : 0u;
         int j = 0;
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x) {
             for (int qt = 0; qt < n_qt; ++qt, ++j) {
+                if ((uint32_t)(j & 1) != grp) continue;   // tile j belongs to softmax group j & 1
                 const uint32_t drop_base = ((uint32_t)head * (uint32_t)S + (uint32_t)(qt * 128 + row_in_tile)) * (uint32_t)S;   // element (q, k) -> base + k
                 const uint32_t t_s = t_lane + (j & 1) * kMaxQ;
-                const uint32_t xoff = ((j & 3) * 3 * 128 + row_in_tile) * 4;
-                const bool dbg_on = args.dbg && blockIdx.x == 0 && j < 64 && warp_idx == 4 && lane == 0;
+                const uint32_t xoff = ((j & 3) * 2 * 128 + row_in_tile) * 4;
+                const bool dbg_on = args.dbg && blockIdx.x == 0 && j < 64 && (warp_idx == 4 || warp_idx == 12) && lane == 0;
                 if (dbg_on) args.dbg[j * 16 + 0] = clock64();
                 mbar_wait(&s_full[j & 1], (j >> 1) & 1);
                 tcgen05_fence_after();
@@ -216,34 +221,31 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     };
                     int g = part;
                     if (g < nks) tmem_ld_32x32b_x16(t_s + g * 16, ra);
-                    for (; g < nks; g += 6) {
+                    for (; g < nks; g += 4) {
                         tmem_ld_wait();
-                        if (g + 3 < nks) tmem_ld_32x32b_x16(t_s + (g + 3) * 16, rb);
+                        if (g + 2 < nks) tmem_ld_32x32b_x16(t_s + (g + 2) * 16, rb);
                         reduce(ra, g);
-                        if (g + 3 < nks) {
+                        if (g + 2 < nks) {
                             tmem_ld_wait();
-                            if (g + 6 < nks) tmem_ld_32x32b_x16(t_s + (g + 6) * 16, ra);
-                            reduce(rb, g + 3);
+                            if (g + 4 < nks) tmem_ld_32x32b_x16(t_s + (g + 4) * 16, ra);
+                            reduce(rb, g + 2);
                         }
                     }
                 }
                 if (dbg_on) args.dbg[j * 16 + 2] = clock64();
                 sts32(xm_u32 + xoff + part * 512, mx);
-                named_bar_sync(1 + quad, 96);
-                mx = fmaxf(fmaxf(lds32(xm_u32 + xoff), lds32(xm_u32 + xoff + 512)), lds32(xm_u32 + xoff + 1024));
+                named_bar_sync(1 + grp * 4 + quad, 64);
+                mx = fmaxf(lds32(xm_u32 + xoff), lds32(xm_u32 + xoff + 512));
                 const float nm = -mx * c;
                 if (dbg_on) args.dbg[j * 16 + 3] = clock64();
                 // ---- pass 2: P = exp2(s c - m c) packed over the group's own columns; partial row sum ----
                 float l = 0.f;
                 bool arrivedA = false;
-                // No softmax warp may arrive for tile j before every warp has arrived for tile j - 1 (the mbarrier phases would
-                // mix): o_full(j - 1) completes only after all of them did.
-                if (j > 0) mbar_wait(o_full, (j - 1) & 1);
                 auto arriveA = [&]() {
                     tmem_st_wait();
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&p_full[0]);
+                    if (lane == 0) mbar_arrive(&p_full[2 * grp]);
                     arrivedA = true;
                 };
                 {
@@ -275,16 +277,16 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     };
                     int g = part;
                     if (g < nks) tmem_ld_32x32b_x16(t_s + g * 16, ra);
-                    for (; g < nks; g += 6) {
+                    for (; g < nks; g += 4) {
                         if (g >= 8 && !arrivedA) arriveA();
                         tmem_ld_wait();
-                        if (g + 3 < nks) tmem_ld_32x32b_x16(t_s + (g + 3) * 16, rb);
+                        if (g + 2 < nks) tmem_ld_32x32b_x16(t_s + (g + 2) * 16, rb);
                         emit(ra, g);
-                        if (g + 3 < nks) {
-                            if (g + 3 >= 8 && !arrivedA) arriveA();
+                        if (g + 2 < nks) {
+                            if (g + 2 >= 8 && !arrivedA) arriveA();
                             tmem_ld_wait();
-                            if (g + 6 < nks) tmem_ld_32x32b_x16(t_s + (g + 6) * 16, ra);
-                            emit(rb, g + 3);
+                            if (g + 4 < nks) tmem_ld_32x32b_x16(t_s + (g + 4) * 16, ra);
+                            emit(rb, g + 2);
                         }
                     }
                 }
@@ -293,7 +295,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[1]);
+                if (lane == 0) mbar_arrive(&p_full[2 * grp + 1]);
                 if (dbg_on) args.dbg[j * 16 + 4] = clock64();
             }
         }
@@ -309,7 +311,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         int j = 0;
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x) {
             for (int qt = 0; qt < n_qt; ++qt, ++j) {
-                const uint32_t xoff = ((j & 3) * 3 * 128 + row_in_tile) * 4;
+                const uint32_t xoff = ((j & 3) * 2 * 128 + row_in_tile) * 4;
                 const int buf = j & 1;
                 mbar_wait(&out_free[buf], ((j >> 1) & 1) ^ 1);
                 mbar_wait(o_full, j & 1);
@@ -321,8 +323,8 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_free);
-                const float tot = lds32(xs_u32 + xoff) + lds32(xs_u32 + xoff + 512) + lds32(xs_u32 + xoff + 1024);
-                const float mx = fmaxf(fmaxf(lds32(xm_u32 + xoff), lds32(xm_u32 + xoff + 512)), lds32(xm_u32 + xoff + 1024));
+                const float tot = lds32(xs_u32 + xoff) + lds32(xs_u32 + xoff + 512);
+                const float mx = fmaxf(lds32(xm_u32 + xoff), lds32(xm_u32 + xoff + 512));
                 const float inv = tot > 0.f ? 1.f / tot : 0.f;
                 const uint32_t dst = out_row + buf * 16384;
 #pragma unroll
