@@ -61,6 +61,7 @@ struct Args {
     uint32_t drop_thresh, drop_stream;   // attention dropout (DROP instantiations)
     float drop_inv_keep;
     const uint32_t* drop_seed;
+    int late_release;   // A/B switch (VITB200_ATTN_BWD_LATE_RELEASE=1): hand TMEM back only after the whole read-out
     float* colsum;   // optional fp32 [3][H*64]: += column sums of dq and dv (in-projection bias gradient; the dk part is exactly 0)
 };
 
@@ -418,48 +419,52 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         sts128(row_addr + (((hi * 4 + v4) ^ swz) << 4), w0, w1, w2, w3);
                     }
                 };
-                // slices: part 0: dV lo, dK hi, [dQ0 lo]; part 1: dV hi, dQ1 lo, [dQ0 hi]; part 2: dK lo, dQ1 hi
-                {
-                    uint32_t r[32];
-                    const uint32_t col_a = part == 0 ? kColDV : (part == 1 ? kColDV + 32 : kColDK);
-                    tmem_ld_32x32b_x32(t_lane + col_a, r);
+                // slices: part 0: dV lo, dK hi, [dQ0 lo]; part 1: dV hi, dQ1 lo, [dQ0 hi]; part 2: dK lo, dQ1 hi.
+                // The TMEM loads come first and TMEM is handed back (tile_free) as soon as the last of them has landed, so the next tile's
+                // score products run while the packing, the shared-memory stores and the column-sum butterflies are still in progress.
+                auto release_tmem = [&]() {
+                    if (args.late_release) return;
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tile_free);
+                };
+                const bool third = last && part < 2;          // this warp also reads a slice of the dQ(0..127) accumulator
+                const bool second = part == 0 || has_q1;
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(t_lane + (part == 0 ? kColDV : (part == 1 ? kColDV + 32 : kColDK)), ra);
+                if (second) tmem_ld_32x32b_x32(t_lane + (part == 0 ? kColDK + 32 : kColDQ1 + (part - 1) * 32), rb);
+                tmem_ld_wait();
+                if (!third) release_tmem();
+                stage32(ra, part == 2 ? kv_row + kBlk : kv_row, part == 1 ? 1u : 0u, part == 2 ? args.scale : 1.0f);
+                // part 0: dV columns 0..31, part 1: dV 32..63.  dK is skipped: sum_k dS[q,k] = sum_k P (dP - delta) = 0 for every query, so
+                // the column sum of dK = dS^T Q (the key-bias gradient) is exactly zero — softmax ignores a constant key offset.
+                if (do_cs && part < 2) colsum32(ra, 1.0f, t * 128 + row_in_tile < S, args.colsum + 2 * hd + hcol + part * 32);
+                if (third) {   // re-use ra for the dQ(0..127) slice; TMEM is free once it has landed
+                    tmem_ld_32x32b_x32(t_lane + kColDQ0 + part * 32, ra);
                     tmem_ld_wait();
-                    stage32(r, part == 2 ? kv_row + kBlk : kv_row, part == 1 ? 1u : 0u, part == 2 ? args.scale : 1.0f);
-                    // part 0: dV columns 0..31, part 1: dV 32..63.  dK is skipped: sum_k dS[q,k] = sum_k P (dP - delta) = 0 for every query, so
-                    // the column sum of dK = dS^T Q (the key-bias gradient) is exactly zero — softmax ignores a constant key offset.
-                    if (do_cs && part < 2) colsum32(r, 1.0f, t * 128 + row_in_tile < S, args.colsum + 2 * hd + hcol + part * 32);
+                    release_tmem();
                 }
                 if (part == 0) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_lane + kColDK + 32, r);
-                    tmem_ld_wait();
-                    stage32(r, kv_row + kBlk, 1u, args.scale);
+                    stage32(rb, kv_row + kBlk, 1u, args.scale);
                 } else if (has_q1) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_lane + kColDQ1 + (part - 1) * 32, r);
-                    tmem_ld_wait();
                     if (last) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + dq1c[i]);
-                        stage32(r, q_row + kBlk, part - 1, args.scale);
-                        if (do_cs) colsum32(r, args.scale, 128 + row_in_tile < S, args.colsum + hcol + (part - 1) * 32);
+                        for (int i = 0; i < 32; ++i) rb[i] = __float_as_uint(__uint_as_float(rb[i]) + dq1c[i]);
+                        stage32(rb, q_row + kBlk, part - 1, args.scale);
+                        if (do_cs) colsum32(rb, args.scale, 128 + row_in_tile < S, args.colsum + hcol + (part - 1) * 32);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) dq1c[i] = __uint_as_float(r[i]);
+                        for (int i = 0; i < 32; ++i) dq1c[i] = __uint_as_float(rb[i]);
                     }
                 }
-                if (last && part < 2) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_lane + kColDQ0 + part * 32, r);
-                    tmem_ld_wait();
-                    stage32(r, q_row, part, args.scale);
-                    if (do_cs) colsum32(r, args.scale, row_in_tile < S, args.colsum + hcol + part * 32);
+                if (third) {
+                    stage32(ra, q_row, part, args.scale);
+                    if (do_cs) colsum32(ra, args.scale, row_in_tile < S, args.colsum + hcol + part * 32);
                 }
-                tcgen05_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(tile_free);   // TMEM is free: the next tile's score products may start
+                    if (args.late_release) mbar_arrive(tile_free);
                     mbar_arrive(out_ready);   // output tiles staged: the store warp takes over
                 }
                 if (dbg_on) args.dbg[ic * 16 + 7] = clock64();
@@ -497,6 +502,7 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     a.lse = d->lse; a.delta = d->delta;
     a.batch_stride = d->batch_stride;
     a.colsum = d->dqkv_colsum;
+    { const char* e = getenv("VITB200_ATTN_BWD_LATE_RELEASE"); a.late_release = (e && e[0] == '1') ? 1 : 0; }
     a.dbg = g_dbg;
     CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
     const uint64_t cols = (uint64_t)d->H * 64;
