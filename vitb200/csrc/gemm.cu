@@ -16,6 +16,8 @@
 // Replaces the cuBLASLt calls behind nn.Linear / F.linear on the reference path
 // (vanilla_vit.py:33-42,77-79,212-213; torch/nn/functional.py:5835-5847,6690) and their autograd formulas.
 #include <cuda.h>
+#include <atomic>
+#include <mutex>
 #include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
@@ -728,9 +730,11 @@ static int dynamic_scheduling() {
 static int* next_sched_counter() {
     constexpr int kPool = 256;
     static int* pool[16] = {};
-    static unsigned next[16] = {};
+    static std::atomic<unsigned> next[16];   // forward and autograd threads may launch concurrently
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     if (pool[dev] == nullptr) {
         int* p = nullptr;
         if (cudaMalloc(&p, kPool * sizeof(int)) != cudaSuccess) return nullptr;
@@ -738,7 +742,7 @@ static int* next_sched_counter() {
         cudaDeviceSynchronize();
         pool[dev] = p;
     }
-    return pool[dev] + (next[dev]++ % kPool);
+    return pool[dev] + (next[dev].fetch_add(1, std::memory_order_relaxed) % kPool);
 }
 
 static int default_cta_group() {
