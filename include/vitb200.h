@@ -145,6 +145,9 @@ VB_API int vb_attention_fwd(const VbAttnDesc* desc, void* stream);
 VB_API int vb_attention_bwd(const VbAttnDesc* desc, void* stream);
 /* profiling aid: device buffer (>= 1024 int64) receiving in-kernel cycle stamps of the tcgen05 backward; NULL disables */
 VB_API int vb_debug_set_attn_timeline(void* device_buffer);
+/* same for the GEMM: >= 8 int64 of cluster 0's MMA issuer (total cycles, waiting for operand stages, for a free accumulator, for
+ * the tile scheduler, tiles issued); NULL disables */
+VB_API int vb_debug_set_gemm_timeline(void* device_buffer);
 
 /* ---- Helper kernels around the encoder (HBM-bound) -----------------------------------------------------------
  * vb_cast_f32_to_bf16: flat fp32 -> bf16 cast (master parameters -> tensor-core operands), n % 4 == 0.

@@ -64,6 +64,7 @@ SIGNATURES = {
                                  c_int64, c_float, c_void_p, c_void_p]),
     "vb_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                              c_float, c_int32, c_float, c_void_p, c_void_p]),
+    "vb_debug_set_gemm_timeline": (c_int, [c_void_p]),
     "vb_debug_set_attn_timeline": (c_int, [c_void_p]),
     "vb_attention_fwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),
     "vb_attention_bwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),

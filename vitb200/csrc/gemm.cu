@@ -40,6 +40,7 @@ struct GemmArgs {
     int split_k, kb_per_split, num_units;
     int c_row_offset, aux_bcast, b_batched;
     int direct;
+    long long* dbg;       // optional: cycle accounting of cluster 0's MMA issuer (vb_debug_set_gemm_timeline)
     int* sched_counter;   // non-null: dynamic tile scheduling (units beyond the first per cluster are handed out by atomicAdd)
     const float* bias;
     void* C;
@@ -52,14 +53,16 @@ template <int EPI, int CG>
 struct EpiTraits {
     static constexpr bool kHasAux = (EPI == VB_EPI_RESIDUAL || EPI == VB_EPI_DGELU || EPI == VB_EPI_DRELU);
     static constexpr bool kTwoOut = (EPI == VB_EPI_GELU);
-    // staging buffers per epilogue warp: [aux-in] + out0 + out1 (out1 = second output for GELU, else double buffer)
-    static constexpr uint32_t kBufsPerWarp = (kHasAux ? 1 : 0) + 2;
+    // staging buffers per epilogue warp: [aux-in] + out0 [+ out1 = second output of GELU].  Single-buffered on purpose: the MMA issuer
+    // waits for a free accumulator < 1 % of the time but for operand stages ~20-35 % (tools/gemm_timeline.py), so shared memory
+    // is worth more as one more pipeline stage than as a second store buffer.
+    static constexpr uint32_t kBufsPerWarp = (kHasAux ? 1 : 0) + (kTwoOut ? 2 : 1);
     static constexpr uint32_t kBStageBytes = B_STAGE_BYTES / CG;
     static constexpr uint32_t kStageBytes = A_STAGE_BYTES + kBStageBytes;
     static constexpr uint32_t kEpiBytes = kEpiWarps * kBufsPerWarp * EPI_BUF_BYTES;
     static constexpr uint32_t kBudget = 232448 - 1024 /*align*/ - 512 /*barriers + scheduler ring*/;
     static constexpr uint32_t kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
-    static constexpr uint32_t kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+    static constexpr uint32_t kStages = kStagesRaw > 7 ? 7 : kStagesRaw;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + 1024;
 };
 
@@ -357,14 +360,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             constexpr uint32_t b_kstep = (BMAJ == 0) ? UK * 2 : UK * 128;
             uint32_t stage = 0, phase = 0, it = 0;
             SchedReader rd;
-            for (int u = unit0; u >= 0; u = sched_next(rd, u, false), ++it) {
+            const bool dbg_on = args.dbg != nullptr && blockIdx.x == 0;
+            long long t_begin = 0, w_full = 0, w_tmem = 0, w_sched = 0, t0 = 0;
+            if (dbg_on) t_begin = clock64();
+            int u = unit0;
+            while (u >= 0) {
                 const UnitCoord c = decode_unit<CG>(args, u, 0);
                 const uint32_t as = it & 1, ap = (it >> 1) & 1;
+                if (dbg_on) t0 = clock64();
                 mbar_wait(&tmem_empty_bar[as], ap ^ 1);
+                if (dbg_on) w_tmem += clock64() - t0;
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int kb = c.kb0; kb < c.kb1; ++kb) {
+                    if (dbg_on) t0 = clock64();
                     mbar_wait(&full_bar[stage], phase);
+                    if (dbg_on) w_full += clock64() - t0;
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(smem_b + stage * kBStage);
@@ -383,6 +394,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 // accumulator complete -> epilogue warps of both CTAs
                 if (CG == 2) umma_commit_2sm(&tmem_full_bar[as], 0x3);
                 else umma_commit(&tmem_full_bar[as]);
+                if (dbg_on) t0 = clock64();
+                u = sched_next(rd, u, false);
+                if (dbg_on) w_sched += clock64() - t0;
+                ++it;
+            }
+            if (dbg_on) {
+                args.dbg[0] = clock64() - t_begin; args.dbg[1] = w_full; args.dbg[2] = w_tmem; args.dbg[3] = w_sched; args.dbg[4] = it;
             }
         }
     } else if (warp_idx >= kFirstEpiWarp) {
@@ -438,7 +456,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int row_in_batch = c.m_blk * BM + quad * 32 + lane;  // GEMM row of this thread
             const int row0 = args.c_row_offset + c.m_blk * BM + quad * 32;
 
-            const int n_valid_chunks = valid_chunks(u);
+            const int n_valid_chunks = (args.direct == 2) ? 0 : valid_chunks(u);   // direct == 2: profiling aid, epilogue skipped entirely
             if (n_valid_chunks == 0) {
                 tcgen05_fence_before();
                 __syncwarp();
@@ -456,7 +474,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 const bool write_c = (EPI != VB_EPI_GELU) || args.C != nullptr;
-                uint8_t* obuf = (T::kTwoOut || (chunk_count & 1) == 0) ? buf_o0 : buf_o1;
+                // (Tried and rejected: 16-byte global stores straight from registers instead of staging + TMA store — the LSU handles 32
+                // rows per instruction and becomes the bottleneck at K = 768: 10.4 k vs 7.5 k cycles per tile.)
+                uint8_t* obuf = buf_o0;
 #pragma unroll
                 for (int g = 0; g < int(CPC / 32); ++g) {
                     const int colg = col0 + g * 32;
@@ -476,6 +496,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) release_tmem(as);
+                    }
+                    if (args.direct == 3) {   // profiling aid: TMEM loads only (keeps the loaded values alive, writes nothing)
+                        uint32_t x_ = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x_ ^= acc[j];
+                        if (x_ == 0x12345678u && args.C2 != nullptr) reinterpret_cast<uint32_t*>(args.C2)[0] = x_;
+                        continue;
                     }
                     float v[32];
 #pragma unroll
@@ -549,11 +576,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     // ---- registers -> swizzled staging buffer (or straight to global on the bring-up path) ----
                     if (!args.direct) {
                         if (g == 0) {
-                            // GELU: both buffers belong to the previous chunk's store -> wait for all; otherwise the two
-                            // buffers alternate, so only the store issued two chunks ago has to have drained
+                            // the staging buffer is single: the previous chunk's TMA store must have finished reading it
                             if (lane == 0) {
-                                if (T::kTwoOut) tma_store_wait_read<0>();
-                                else tma_store_wait_read<1>();
+                                tma_store_wait_read<0>();
                             }
                             __syncwarp();
                         }
@@ -745,6 +770,8 @@ static int* next_sched_counter() {
     return pool[dev] + (next[dev].fetch_add(1, std::memory_order_relaxed) % kPool);
 }
 
+static long long* g_gemm_dbg = nullptr;
+
 static int default_cta_group() {
     static int cg = 0;
     if (cg == 0) {
@@ -789,6 +816,7 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     a.b_batched = d->batch_stride_b != 0;
     a.direct = d->debug_direct_store;
     a.sched_counter = nullptr;
+    a.dbg = g_gemm_dbg;
     a.bias = d->bias;
     a.C = d->C; a.C2 = d->C2; a.AUX = d->AUX;
     a.ldc = d->ldc; a.ldc2 = d->ldc2; a.ldaux = d->ldaux;
@@ -856,4 +884,11 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     }
 #undef VB_LAUNCH
     return fail(VB_ERR_UNSUPPORTED, "no GEMM instantiation for a_major=%d b_major=%d epilogue=%d c_dtype=%d", am, bm, ep, cd);
+}
+
+// Debug hook: device buffer of >= 8 int64 receiving the cycle accounting of cluster 0's MMA issuer (total, waiting for operand
+// stages, waiting for a free accumulator, waiting for the scheduler, tiles); NULL disables.  tools/gemm_timeline.py
+extern "C" VB_API int vb_debug_set_gemm_timeline(void* device_buffer) {
+    vb::g_gemm_dbg = reinterpret_cast<long long*>(device_buffer);
+    return VB_OK;
 }

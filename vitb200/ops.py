@@ -77,7 +77,7 @@ def gemm(A, B, C, *, a_major=0, b_major=0, epilogue=EPI_STORE, bias=None, aux=No
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
         d.bias = bias.data_ptr()
     d.max_ctas = max_ctas
-    d.debug_direct_store = 1 if direct else 0
+    d.debug_direct_store = int(direct)
     _lib.check(lib.vb_gemm_bf16(ctypes.byref(d), _stream()), "vb_gemm_bf16")
     return out
 
