@@ -40,10 +40,11 @@ def test_deit_distilled_training(distill):
     assert avg.shape == (B, 100) and rel_l2(avg, ref_avg) < LOGIT_TOL
 
 
-def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos):
+def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos, pre_norm=False):
     from vitb200.detr import TransformerEncoder, TransformerEncoderLayer
-    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, False), 31)
-    enc = TransformerEncoder(TransformerEncoderLayer(d_model, nhead, ffn, 0.0, "relu", False), layers)
+    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, pre_norm), 31)
+    enc = TransformerEncoder(TransformerEncoderLayer(d_model, nhead, ffn, 0.0, "relu", pre_norm), layers,
+                             torch.nn.LayerNorm(d_model) if pre_norm else None)   # transformer.py:32-33
     enc.load_state_dict(sd)
     enc = enc.cuda().train()
     g = torch.Generator().manual_seed(32)
@@ -57,7 +58,7 @@ def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos):
     ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     rsrc = src.clone().requires_grad_(True)
     rpos = pos.clone().requires_grad_(True) if with_pos else None
-    ref = O.detr_encoder_forward(ref_sd, rsrc, nhead=nhead, num_layers=layers, src_key_padding_mask=kpm, pos=rpos)
+    ref = O.detr_encoder_forward(ref_sd, rsrc, nhead=nhead, num_layers=layers, normalize_before=pre_norm, src_key_padding_mask=kpm, pos=rpos)
     ref.backward(gout)
     # Calibration (BASELINE.md §6 rule): the bf16 path must be no worse than max(1e-2, the reference's own
     # autocast-bf16 error against the same fp32 truth) -- measured here on the oracle, with 25 % head-room.
@@ -66,7 +67,7 @@ def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos):
     asrc = src.clone().requires_grad_(True)
     apos = pos.clone().requires_grad_(True) if with_pos else None
     with torch.autocast("cpu", dtype=torch.bfloat16):
-        ac = O.detr_encoder_forward(ac_sd, asrc, nhead=nhead, num_layers=layers, src_key_padding_mask=kpm, pos=apos)
+        ac = O.detr_encoder_forward(ac_sd, asrc, nhead=nhead, num_layers=layers, normalize_before=pre_norm, src_key_padding_mask=kpm, pos=apos)
     ac.float().backward(gout)
     floor_in = max(1e-2, rel_l2(asrc.grad, rsrc.grad))
     floor_w = max(1e-2, max(rel_l2(ac_sd[k].grad, ref_sd[k].grad) for k in sd))
@@ -90,3 +91,14 @@ def test_detr_encoder_masked_with_pos():
 @pytest.mark.gpu
 def test_detr_encoder_short_no_mask_no_pos():
     _detr_run(S=70, N=2, d_model=256, nhead=4, ffn=512, layers=3, masked=False, with_pos=False)
+
+
+@pytest.mark.gpu
+def test_detr_encoder_pre_norm_masked_with_pos():
+    """normalize_before=True: TransformerEncoderLayer.forward_pre + the final encoder LayerNorm (transformer.py:228-241, 32-33, 112-113)."""
+    _detr_run(S=300, N=3, d_model=512, nhead=8, ffn=2048, layers=2, masked=True, with_pos=True, pre_norm=True)
+
+
+@pytest.mark.gpu
+def test_detr_encoder_pre_norm_no_pos():
+    _detr_run(S=70, N=2, d_model=256, nhead=4, ffn=512, layers=3, masked=False, with_pos=False, pre_norm=True)

@@ -39,17 +39,19 @@ def test_oracle_vit_matches_reference_golden(name):
         assert rel_l2(sd[k].grad, g) < 1e-4, k
 
 
-def test_oracle_detr_matches_reference_golden():
-    gd = load("detr_enc_d256.pt")
+@pytest.mark.parametrize("name", ["detr_enc_d256.pt", "detr_enc_prenorm_d256.pt"])
+def test_oracle_detr_matches_reference_golden(name):
+    gd = load(name)
     d, h, ffn, L, S, N, seed = gd["d_model"], gd["nhead"], gd["ffn"], gd["layers"], gd["S"], gd["N"], gd["seed"]
-    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.detr_param_shapes(d, ffn, L, False), seed).items()}
+    pre = bool(gd.get("pre_norm", False))     # forward_pre + final encoder norm (transformer.py:228-241, 32-33) vs forward_post
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.detr_param_shapes(d, ffn, L, pre), seed).items()}
     g = torch.Generator().manual_seed(seed + 1)
     src = torch.randn(S, N, d, generator=g, requires_grad=True)
     pos = torch.randn(S, N, d, generator=g, requires_grad=True)
     valid = torch.randint(S // 2, S + 1, (N,), generator=g)
     kpm = torch.arange(S)[None, :] >= valid[:, None]
     gout = torch.randn(S, N, d, generator=g)
-    out = O.detr_encoder_forward(sd, src, nhead=h, num_layers=L, src_key_padding_mask=kpm, pos=pos)
+    out = O.detr_encoder_forward(sd, src, nhead=h, num_layers=L, normalize_before=pre, src_key_padding_mask=kpm, pos=pos)
     out.backward(gout)
     assert rel_l2(out, gd["out"]) < 1e-5
     assert abs(src.grad.norm().item() - gd["dsrc_norm"]) < 1e-4 * gd["dsrc_norm"]

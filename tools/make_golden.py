@@ -59,9 +59,10 @@ def vit_case(name, cfg, batch, seed):
     print(name, "loss", loss.item())
 
 
-def detr_case(name, d_model, nhead, ffn, layers, S, N, seed):
-    enc = RefEnc(RefLayer(d_model, nhead, ffn, 0.0, "relu", False), layers)
-    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, False), seed)
+def detr_case(name, d_model, nhead, ffn, layers, S, N, seed, pre_norm=False):
+    # transformer.py:32-33: the encoder gets a final LayerNorm iff normalize_before
+    enc = RefEnc(RefLayer(d_model, nhead, ffn, 0.0, "relu", pre_norm), layers, torch.nn.LayerNorm(d_model) if pre_norm else None)
+    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, pre_norm), seed)
     enc.load_state_dict(sd)
     enc.train()
     g = torch.Generator().manual_seed(seed + 1)
@@ -73,7 +74,8 @@ def detr_case(name, d_model, nhead, ffn, layers, S, N, seed):
     out = enc(src, src_key_padding_mask=kpm, pos=pos)
     out.backward(gout)
     norms, full = grads_summary(enc.named_parameters())
-    torch.save({"d_model": d_model, "nhead": nhead, "ffn": ffn, "layers": layers, "S": S, "N": N, "seed": seed, "out": out.detach(),
+    torch.save({"d_model": d_model, "nhead": nhead, "ffn": ffn, "layers": layers, "S": S, "N": N, "seed": seed, "pre_norm": pre_norm,
+                "out": out.detach(),
                 "dsrc_norm": src.grad.norm().item(), "dpos_norm": pos.grad.norm().item(), "dsrc_row0": src.grad[0].clone(),
                 "grad_norms": norms, "grads_small": full}, os.path.join(OUT, name))
     print(name, "out norm", out.norm().item())
@@ -120,5 +122,6 @@ if __name__ == "__main__":
     vit_case("vit_tiny_b4.pt", TINY, 4, 101)
     vit_case("vit_b16x2_b2.pt", B16_2L, 2, 111)
     detr_case("detr_enc_d256.pt", 256, 4, 512, 2, 70, 2, 121)
+    detr_case("detr_enc_prenorm_d256.pt", 256, 4, 512, 2, 70, 2, 131, pre_norm=True)
     distill_case("distill_loss.pt", 131)
     kat_case("kat.pt")

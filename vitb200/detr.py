@@ -3,7 +3,8 @@ TransformerEncoder :98-115) on the hand-written sm_100a kernels.
 
 Same constructors, ``forward(src, src_mask=None, src_key_padding_mask=None, pos=None)`` signature, sequence-first
 [S, N, C] tensors and state_dict keys (``layers.{i}.self_attn.in_proj_weight`` ...).  The post-norm path
-(``normalize_before=False``, the reference default: transformer.py:27-28) is implemented; ``q = k = src + pos``,
+(``normalize_before=False``, the reference default: transformer.py:27-28) and the pre-norm variant (``forward_pre``,
+transformer.py:228-241) are implemented; ``q = k = src + pos``,
 ``v = src`` (transformer.py:218-219), boolean key-padding mask, ReLU (or GELU) feed-forward, LayerNorm eps 1e-5.
 The layer objects are parameter containers: the stack is executed by the enclosing ``TransformerEncoder``.
 """
@@ -68,10 +69,11 @@ class TransformerEncoderLayer(nn.Module):
 
 
 class DetrEngine(FlatParams):
-    def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5):
+    def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5, pre_norm=False):
         assert d_model % 128 == 0 and d_model // nhead == 64, "vitb200 kernels need d_model % 128 == 0 and head_dim == 64"
         self.D, self.H, self.F, self.L, self.eps = d_model, nhead, dim_feedforward, len(layers), eps
         self.act = activation
+        self.pre_norm = bool(pre_norm)   # TransformerEncoderLayer.forward_pre (transformer.py:228-241) instead of forward_post (:213-226)
         self.has_norm = norm is not None
         self._order = []
         seg = []
@@ -122,7 +124,8 @@ class DetrEngine(FlatParams):
         pos2 = pos.contiguous().float().view(M, D) if pos is not None else None
         ws["pos"], ws["kpm"] = pos2, kpm
         x = src2
-        epi_act = ops.EPI_RELU if self.act == "relu" else ops.EPI_GELU
+        if self.pre_norm:
+            return self._forward_pre(ws, x, pos2, kpm, training, S, N)
         for li in range(self.L):
             buf = ws["layer"][li if training else 0]
             if li == 0:
@@ -166,8 +169,113 @@ class DetrEngine(FlatParams):
             return ws["y"].view(S, N, D), ws
         return x.view(S, N, D), ws
 
+    # ------------------------------------------------------------------------------------------------------------------
+    # Pre-norm layers (normalize_before=True): src2 = norm1(src); q = k = src2 + pos; src += attn(q, k, src2);
+    # src2 = norm2(src); src += linear2(act(linear1(src2)))   — transformer.py:228-241; final encoder norm :112-113.
+    # Same kernels as the post-norm path; the residual stream stays fp32 and is never normalised in place.
+    # ------------------------------------------------------------------------------------------------------------------
+    def _forward_pre(self, ws, x, pos2, kpm, training, S, N):
+        M, D, H = ws["M"], self.D, self.H
+        if "xin" not in ws:
+            ws["xin"] = [torch.empty(M, D, device=x.device, dtype=torch.float32) for _ in range(self.L + 1 if training else 2)]
+        xs = ws["xin"]
+        xs[0].copy_(x)
+        for li in range(self.L):
+            buf = ws["layer"][li if training else 0]
+            x_in = xs[li] if training else xs[li & 1]
+            x_out = xs[li + 1] if training else xs[(li + 1) & 1]
+            if pos2 is not None:   # bf16(norm1(x)) feeds v, bf16(norm1(x) + pos) feeds q = k
+                ops.layernorm_fwd(x_in, self.f((li, "norm1_w")), self.f((li, "norm1_b")), self.eps, y_bf16=buf["x_bf"],
+                                  mean=buf["mean1"], rstd=buf["rstd1"], add=pos2, y2_bf16=buf["qk_bf"])
+                qk_in = buf["qk_bf"]
+            else:
+                ops.layernorm_fwd(x_in, self.f((li, "norm1_w")), self.f((li, "norm1_b")), self.eps, y_bf16=buf["x_bf"],
+                                  mean=buf["mean1"], rstd=buf["rstd1"])
+                qk_in = buf["x_bf"]
+            in_w, in_b = self.w((li, "in_w")), self.f((li, "in_b"))
+            ops.gemm(qk_in, in_w[:2 * D], buf["qkb"], bias=in_b[:2 * D])
+            ops.gemm(buf["x_bf"], in_w[2 * D:], buf["vb"], bias=in_b[2 * D:])
+            ops.attention_fwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"] if training else None, B=N, H=H, S=S,
+                              tok_stride=N, batch_stride=1, key_padding_mask=kpm)
+            ops.gemm(buf["o"], self.w((li, "out_w")), buf["x1"], epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "out_b")), aux=x_in)
+            ops.layernorm_fwd(buf["x1"], self.f((li, "norm2_w")), self.f((li, "norm2_b")), self.eps, y_bf16=buf["x1_bf"],
+                              mean=buf["mean2"], rstd=buf["rstd2"])
+            if self.act == "relu":
+                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], epilogue=ops.EPI_RELU, bias=self.f((li, "lin1_b")))
+                act_out = buf["a"]
+            else:
+                if "g" not in buf:
+                    buf["g"] = torch.empty_like(buf["a"])
+                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], C2=buf["g"], epilogue=ops.EPI_GELU, bias=self.f((li, "lin1_b")))
+                act_out = buf["g"]
+            ops.gemm(act_out, self.w((li, "lin2_w")), x_out, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "lin2_b")), aux=buf["x1"])
+        x = xs[self.L] if training else xs[self.L & 1]
+        if self.has_norm:
+            ops.layernorm_fwd(x, self.f(("g", "norm_w")), self.f(("g", "norm_b")), self.eps, y_f32=ws["y"], mean=ws["meanf"], rstd=ws["rstdf"])
+            ws["x_last"] = x
+            return ws["y"].view(S, N, D), ws
+        return x.view(S, N, D), ws
+
+    def _backward_pre(self, ws, grad_out):
+        S, N, M, D, H, L = ws["S"], ws["N"], ws["M"], self.D, self.H, self.L
+        d, d_bf, dh, dh2 = ws["dA"], ws["dA_bf"], ws["dh"], ws["dh2"]   # d: fp32 gradient of the residual stream, updated in place
+        g = grad_out.contiguous().float().view(M, D)
+        pos2, kpm = ws["pos"], ws["kpm"]
+        dpos = None
+        if pos2 is not None:
+            dpos = ws["dpos"]
+            dpos.zero_()
+        seg = 0
+        last_b2 = self.gview((L - 1, "lin2_b"))
+        if self.has_norm:
+            ops.layernorm_bwd(g, ws["x_last"], ws["meanf"], ws["rstdf"], self.f(("g", "norm_w")), dx=d, dx_bf16=d_bf,
+                              dgamma=self.gview(("g", "norm_w")), dbeta=self.gview(("g", "norm_b")), dx_colsum=last_b2)
+            self._seg_done(seg)
+            seg += 1
+        else:
+            d.copy_(g)
+            ops.cast_bf16(d.view(-1), d_bf.view(-1))
+            ops.colsum_bf16(d_bf, last_b2)
+        for li in range(L - 1, -1, -1):
+            buf = ws["layer"][li]
+            x_in = ws["xin"][li]
+            # ---- FFN: x_out = x1 + linear2(act(linear1(norm2(x1)))) ----
+            act_out = buf["a"] if self.act == "relu" else buf["g"]
+            self._wgrad(d_bf, act_out, (li, "lin2_w"))
+            ops.gemm(d_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU if self.act == "relu" else ops.EPI_DGELU,
+                     aux=buf["a"])
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
+            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
+            ops.layernorm_bwd(dh, buf["x1"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dres=d, dx=d, dx_bf16=d_bf,
+                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")), dx_colsum=self.gview((li, "out_b")))
+            # ---- attention: x1 = x_in + out_proj(attn(q = k = norm1(x_in) + pos, v = norm1(x_in))) ----
+            self._wgrad(d_bf, buf["o"], (li, "out_w"))
+            ops.gemm(d_bf, self.w((li, "out_w")), dh, b_major=1)      # dO
+            dqk, dv = ws["dqk"], ws["dv"]
+            ops.attention_bwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"], dh, dqk[:, :D], dqk[:, D:], dv,
+                              ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm)
+            in_w = self.w((li, "in_w"))
+            self._wgrad(dqk, buf["qk_bf"] if pos2 is not None else buf["x_bf"], (li, "in_w"), rows=(0, 2 * D))
+            self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
+            gb = self.gview((li, "in_b"))
+            ops.colsum_bf16(dqk, gb[:2 * D])
+            ops.colsum_bf16(dv, gb[2 * D:])
+            ops.gemm(dqk, in_w[:2 * D], dh, b_major=1)                 # d(norm1(x) + pos) through q and k
+            ops.gemm(dv, in_w[2 * D:], dh2, b_major=1)                 # d norm1(x) through v
+            if dpos is not None:
+                ops.add3(dpos, dh, None, dpos, None)                   # d pos += dh
+            prev_b2 = self.gview((li - 1, "lin2_b")) if li > 0 else None
+            ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dres=d, dx=d, dx_bf16=d_bf if li > 0 else None,
+                              dgamma=self.gview((li, "norm1_w")), dbeta=self.gview((li, "norm1_b")), dx_colsum=prev_b2, dy_add=dh2)
+            self._seg_done(seg)
+            seg += 1
+        return d.view(S, N, D), (dpos.view(S, N, D) if dpos is not None else None)
+
     def backward(self, ws, grad_out):
         self.prepare_grads()
+        if self.pre_norm:
+            return self._backward_pre(ws, grad_out)
         S, N, M, D, H = ws["S"], ws["N"], ws["M"], self.D, self.H
         dA, dB, dA_bf, dB_bf, dh, dh2 = ws["dA"], ws["dB"], ws["dA_bf"], ws["dB_bf"], ws["dh"], ws["dh2"]
         g = grad_out.contiguous().float().view(M, D)
@@ -251,15 +359,12 @@ class TransformerEncoder(nn.Module):
         if eng is None:
             l0 = self.layers[0]
             eng = DetrEngine(list(self.layers), self.norm, l0.d_model, l0.nhead, l0.dim_feedforward, l0.activation_name,
-                             eps=float(l0.norm1.eps))
+                             eps=float(l0.norm1.eps), pre_norm=l0.normalize_before)
             self.__dict__["_engine"] = eng
         return eng
 
     def forward(self, src, mask=None, src_key_padding_mask=None, pos=None):
         l0 = self.layers[0]
-        if l0.normalize_before:
-            raise NotImplementedError("vitb200: the pre-norm DETR encoder path (normalize_before=True, transformer.py:228-241) is not "
-                                      "implemented yet; the reference default is post-norm")
         if mask is not None:
             raise NotImplementedError("vitb200: src_mask (attn_mask) is not supported; DETR passes None (transformer.py:59)")
         if self.training and l0.dropout_p > 0:
