@@ -89,3 +89,22 @@ def test_grad_accumulation_and_zero_grad():
     torch.nn.functional.cross_entropy(m(images), labels).backward()
     for n, p in m.named_parameters():
         assert rel_l2(p.grad, g1[n]) < 1e-3, n
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_delivers_every_batch_in_order():
+    """vitb200.data.DevicePrefetcher: double-buffered pinned staging must hand over exactly the loader's batches,
+    including a ragged last one, while the consumer keeps the previous batch busy on the compute stream."""
+    import torch
+    from vitb200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(8 if i < 6 else 3, 3, 32, 32, generator=g), torch.randint(0, 10, (8 if i < 6 else 3,), generator=g)) for i in range(7)]
+    seen = []
+    for img, lab in DevicePrefetcher(batches):
+        assert img.is_cuda and lab.is_cuda
+        busy = img.float() @ torch.randn(32, 32, device="cuda")   # keep the consumer stream busy with this batch
+        seen.append((img.clone(), lab.clone(), busy.sum()))
+    torch.cuda.synchronize()
+    assert len(seen) == len(batches)
+    for (img, lab, _), (himg, hlab) in zip(seen, batches):
+        assert torch.equal(img.cpu(), himg) and torch.equal(lab.cpu(), hlab)
