@@ -162,6 +162,9 @@ VB_API int vb_debug_set_gemm_timeline(void* device_buffer);
 VB_API int vb_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* out_bf16 = bf16(a + b), b may be NULL (DETR: bf16 operand copies of src and src + pos, transformer.py:218) */
 VB_API int vb_add_cast_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
+/* out[r,:] = x[r,:] + pos[r % period,:], fp32 contiguous [rows, D] (Encoder.forward on caller-supplied tokens: input + pos_embedding,
+ * vanilla_vit.py:104; period = sequence length) */
+VB_API int vb_add_rows_bcast(const float* x, const float* pos, float* out, int64_t rows, int32_t period, int32_t D, void* stream);
 /* out = a + b_bf16 (+ c_bf16); accum += b_bf16 if accum != NULL (DETR backward: d_src and d_pos assembly) */
 VB_API int vb_add3(const float* a, const void* b_bf16, const void* c_bf16, float* out, float* accum, int64_t n, void* stream);
 VB_API int vb_patchify(const float* images, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,

@@ -26,6 +26,8 @@ assert m.device in ("cuda", "cpu", "mps")
 assert TransformerEncoder is vitb200.detr.TransformerEncoder
 from models.image_classification import deit   # imports timm.models.deit.VisionTransformerDistilled through the shim
 assert deit.VisionTransformerDistilled.__module__ == "vitb200.deit"
+from models.image_classification import t2t_vit
+assert t2t_vit.Encoder is vitb200.vit.Encoder and t2t_vit.EncoderBlock is vitb200.vit.EncoderBlock
 print("DROPIN_OK", len(m.state_dict()))
 """
 

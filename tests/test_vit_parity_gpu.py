@@ -108,3 +108,44 @@ def test_device_prefetcher_delivers_every_batch_in_order():
     assert len(seen) == len(batches)
     for (img, lab, _), (himg, hlab) in zip(seen, batches):
         assert torch.equal(img.cpu(), himg) and torch.equal(lab.cpu(), hlab)
+
+
+@pytest.mark.gpu
+def test_standalone_encoder_matches_oracle():
+    """vitb200.vit.Encoder used on its own (vanilla_vit.py:88-106; T2T_ViT's identical copy t2t_vit.py:89-110): tokens in,
+    normalised tokens out, gradients for the tokens and every parameter."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import vit_oracle as O
+    from vitb200.vit import Encoder
+    B, S, D, H, Fd, L = 5, 65, 256, 4, 512, 3
+    enc = Encoder(S, L, H, D, Fd, 0.0, 0.0)
+    g = torch.Generator().manual_seed(41)
+    with torch.no_grad():
+        for p in enc.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.05 + (1.0 if p.dim() == 1 and "ln" in "" else 0.0))
+        for n, p in enc.named_parameters():
+            if n.endswith("ln_1.weight") or n.endswith("ln_2.weight") or n == "ln.weight":
+                p.add_(1.0)
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    enc = enc.cuda().train()
+    x = torch.randn(B, S, D, generator=g)
+    gout = torch.randn(B, S, D, generator=g)
+    xc = x.cuda().requires_grad_(True)
+    out = enc(xc)
+    out.backward(gout.cuda())
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    h = xr + ref_sd["pos_embedding"]
+    for i in range(L):
+        h = O.encoder_block(h, ref_sd, f"layers.encoder_layer_{i}.", H, 1e-6)
+    ref = F.layer_norm(h, (D,), ref_sd["ln.weight"], ref_sd["ln.bias"], 1e-6)
+    ref.backward(gout)
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(out, ref) < 1.5e-2
+    assert rel(xc.grad, xr.grad) < 3e-2
+    worst = max((rel(p.grad, ref_sd[n].grad), n) for n, p in enc.named_parameters())
+    assert worst[0] < 3e-2, worst
+    enc.eval()
+    with torch.no_grad():
+        assert rel(enc(x.cuda()), ref) < 1.5e-2

@@ -74,6 +74,7 @@ SIGNATURES = {
                                  c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32,
                                  c_int32, c_void_p, c_int64, c_void_p]),
     "vb_add_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "vb_add_rows_bcast": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "vb_add3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vb_dropout_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float,
                                c_void_p, c_uint32, c_void_p]),

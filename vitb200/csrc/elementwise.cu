@@ -124,6 +124,19 @@ __global__ void embed_bwd_finalize_kernel(const float* __restrict__ possum, floa
     if (dbias) dbias[c] += bsum;
 }
 
+// ---- out[r, :] = x[r, :] + pos[r % period, :]  (Encoder.forward on caller-supplied tokens: input + pos_embedding, vanilla_vit.py:104)
+__global__ void add_rows_bcast_kernel(const float4* __restrict__ x, const float4* __restrict__ pos, float4* __restrict__ out, long long rows,
+                                      int period, int d4) {
+    const long long total = rows * d4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / d4;
+        const int c = (int)(i - r * d4);
+        float4 v = __ldg(x + i);
+        const float4 w = __ldg(pos + (long long)(r % period) * d4 + c);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        out[i] = v;
+    }
+}
 // ---- out_bf16 = bf16(a + b) (b optional): DETR q = k = src + pos operand and the bf16 copy of src -------------
 __global__ void add_cast_kernel(const float4* __restrict__ a, const float4* __restrict__ b, uint2* __restrict__ out, long long n4) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -231,6 +244,17 @@ extern "C" int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_pat
                                                                 D, n_prefix, bpc);
     VB_CUDA_CHECK(cudaGetLastError());
     embed_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, st>>>(possum_scratch, dpos, dtok0, dtok1, dbias, S, D, n_prefix);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_add_rows_bcast(const float* x, const float* pos, float* out, int64_t rows, int32_t period, int32_t D, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(x && pos && out && rows >= 0 && period > 0 && D > 0 && D % 4 == 0, "add_rows_bcast: bad arguments");
+    if (rows == 0) return VB_OK;
+    add_rows_bcast_kernel<<<grid_for(rows * (D / 4), 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pos), reinterpret_cast<float4*>(out), rows, period, D / 4);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

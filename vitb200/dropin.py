@@ -65,6 +65,14 @@ def install(reference_root, stub_missing=True):
     ref_vit.MLP = our_vit.MLP
     ref_tr.TransformerEncoderLayer = our_detr.TransformerEncoderLayer
     ref_tr.TransformerEncoder = our_detr.TransformerEncoder
+    # T2T_ViT carries a verbatim copy of the encoder classes (t2t_vit.py:25-110) and calls self.encoder(x) on its own tokens
+    # (SURVEY.md §8 a13): the stand-alone Encoder.forward serves it.
+    try:
+        ref_t2t = importlib.import_module("models.image_classification.t2t_vit")
+        ref_t2t.Encoder, ref_t2t.EncoderBlock = our_vit.Encoder, our_vit.EncoderBlock
+        ref_t2t.MLPBlock, ref_t2t.MLP = our_vit.MLPBlock, our_vit.MLP
+    except Exception:   # optional: its other imports (token_performer, load_data) may be unavailable
+        pass
 
     # timm shim for models/image_classification/deit.py:4-5
     have_timm = True

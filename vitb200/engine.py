@@ -168,17 +168,24 @@ class VitEngine(FlatParams):
     """Sequences the kernels for `n_prefix` token rows (1 = cls, 2 = cls + dist) + patches through L pre-norm blocks."""
 
     def __init__(self, *, image_size, patch_size, hidden_dim, num_heads, mlp_dim, num_layers, num_classes, n_prefix, eps,
-                 globals_, layers):
+                 globals_, layers, seq_length=None):
         """globals_: role -> Parameter for cls, [dist], pos, conv_w, conv_b, lnf_w, lnf_b, head_w, head_b, [headd_w, headd_b];
         layers: list of dicts role -> Parameter (LAYER_ROLES)."""
         assert hidden_dim % 128 == 0 and hidden_dim // num_heads == 64, \
             "vitb200 kernels need hidden_dim % 128 == 0 and head_dim == 64 (true for every reference config)"
+        # tokens mode (seq_length given): the stack is fed [B, S, D] tokens instead of images — a stand-alone Encoder
+        # (vanilla_vit.py:88-106): input + pos_embedding, dropout, L blocks, final LayerNorm; no patch embedding, no heads.
+        self.tokens_mode = seq_length is not None
+        if self.tokens_mode:
+            image_size, patch_size = 4, 4
         assert patch_size % 4 == 0 and image_size % patch_size == 0
         self.image_size, self.p = image_size, patch_size
         self.D, self.H, self.F, self.L, self.C = hidden_dim, num_heads, mlp_dim, num_layers, num_classes
         self.n_prefix, self.eps = n_prefix, eps
         self.P = (image_size // patch_size) ** 2
         self.S = self.P + n_prefix
+        if self.tokens_mode:
+            self.S, self.P, self.n_prefix = int(seq_length), int(seq_length), 0
         self.Kp = 3 * patch_size * patch_size
         self.Kp_ld = _round_up(self.Kp, 8)
         self.C_ld = _round_up(num_classes, 8)
@@ -191,6 +198,8 @@ class VitEngine(FlatParams):
         # gradient-production order: heads + final norm, blocks L-1..0, embedding
         seg0 = ["head_w", "head_b"] + (["headd_w", "headd_b"] if self.two_heads else []) + ["lnf_w", "lnf_b"]
         emb = ["pos", "cls"] + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
+        if self.tokens_mode:
+            seg0, emb = ["lnf_w", "lnf_b"], ["pos"]
         self._order = [(("g", r), globals_[r]) for r in seg0]
         for li in range(num_layers - 1, -1, -1):
             self._order += [((li, r), layers[li][r]) for r in LAYER_ROLES]
@@ -227,7 +236,8 @@ class VitEngine(FlatParams):
         e = lambda *shape, dtype=bf: torch.empty(*shape, device=dev, dtype=dtype)
         n_sets = self.L if training else 1
         ws = {"B": B, "M": M}
-        ws["patches"] = torch.zeros(B, self.P, self.Kp_ld, device=dev, dtype=bf)
+        if not self.tokens_mode:
+            ws["patches"] = torch.zeros(B, self.P, self.Kp_ld, device=dev, dtype=bf)
         ws["x"] = [e(B, S, D, dtype=f32) for _ in range(self.L + 1 if training else 2)]
         ws["layer"] = []
         for _ in range(n_sets):
@@ -237,8 +247,8 @@ class VitEngine(FlatParams):
                 "mean1": e(M, dtype=f32), "rstd1": e(M, dtype=f32), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32),
             })
         ws["y_all"] = None  # allocated on demand (forward_features)
-        ws["y_tok_f32"] = e(B * self.n_prefix, D, dtype=f32)
-        ws["y_tok"] = e(B * self.n_prefix, D)
+        ws["y_tok_f32"] = e(B * max(self.n_prefix, 1), D, dtype=f32)
+        ws["y_tok"] = e(B * max(self.n_prefix, 1), D)
         ws["meanf"] = e(M, dtype=f32)
         ws["rstdf"] = e(M, dtype=f32)
         ws["logits"] = [torch.zeros(B, self.C_ld, device=dev, dtype=f32) for _ in range(2 if self.two_heads else 1)]
@@ -250,17 +260,23 @@ class VitEngine(FlatParams):
             ws["dqkv"] = e(M, 3 * D)
             ws["delta"] = e(B, H, S, dtype=f32)
             ws["dlogits"] = [torch.zeros(B, self.C_ld, device=dev, dtype=bf) for _ in range(2 if self.two_heads else 1)]
-            ws["dy_tok"] = e(B * self.n_prefix, D)
+            ws["dy_tok"] = e(B * max(self.n_prefix, 1), D)
             ws["dh_cls"] = e(B, D)
             ws["stat_cls"] = [e(B, dtype=f32), e(B, dtype=f32)]
             ws["possum"] = e(S, D, dtype=f32)
-            ws["dxp"] = e(B * self.P, D)
+            ws["dxp"] = e(B * self.P, D) if not self.tokens_mode else None
         self._ws[key] = ws
         return ws
 
     # ------------------------------------------------------------------ forward -----------------------------------
     def _embed(self, ws, images):
         B = ws["B"]
+        if self.tokens_mode:   # images = caller-supplied tokens [B, S, D]
+            x02 = ws["x"][0].view(ws["M"], self.D)
+            ops.add_rows_bcast(images.view(ws["M"], self.D), self.f(("g", "pos")).view(self.S, self.D), x02)
+            if ws.get("p_drop", 0.0) > 0:
+                ops.dropout_f32(x02, ws["p_drop"], ws["drop_seed"], self.EMBED_SITE, dst=x02)
+            return
         pat = ws["patches"]
         if self.Kp_ld == self.Kp:
             ops.patchify(images, pat, self.p)
@@ -458,6 +474,10 @@ class VitEngine(FlatParams):
         # ---- embedding ----
         if pd > 0:   # Encoder.dropout (vanilla_vit.py:104): gradient of x + pos is keep * d / (1 - p)
             ops.dropout_f32(d2, pd, seed, self.EMBED_SITE, dst=d2)
+        if self.tokens_mode:   # d pos = sum_b d; d is the gradient w.r.t. the caller's tokens
+            ops.embed_bwd(d, ws["possum"], None, self.gview(("g", "pos")).view(-1), None, None, None, 0)
+            self._seg_done(L + 1)
+            return d
         ops.embed_bwd(d, ws["possum"], ws["dxp"], self.gview(("g", "pos")).view(-1), self.gview(("g", "cls")).view(-1),
                       self.gview(("g", "dist")).view(-1) if self.n_prefix == 2 else None, self.gview(("g", "conv_b")), self.n_prefix)
         pat = ws["patches"].view(B * self.P, self.Kp_ld)[:, :self.Kp]

@@ -13,7 +13,7 @@ from ._lib import VbGemmDesc
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 2,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
-                     "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1, "vb_dropout_f32": 1, "vb_dropout_bf16_pair": 1,
+                     "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1, "vb_add_rows_bcast": 1, "vb_dropout_f32": 1, "vb_dropout_bf16_pair": 1,
                      "vb_dropout_mask_u8": 1}
 
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_ACCUM = range(7)
@@ -243,6 +243,14 @@ def add_cast_bf16(a, b, out):
     lib = _lib.load()
     assert a.is_contiguous() and out.is_contiguous() and (b is None or b.is_contiguous())
     _lib.check(lib.vb_add_cast_bf16(a.data_ptr(), _p(b), out.data_ptr(), a.numel(), _stream()), "vb_add_cast_bf16")
+
+
+def add_rows_bcast(x, pos, out):
+    """out[r] = x[r] + pos[r % period]; x/out fp32 contiguous [rows, D], pos fp32 contiguous [period, D]."""
+    lib = _lib.load()
+    rows, D = x.shape
+    assert x.is_contiguous() and pos.is_contiguous() and out.is_contiguous() and x.dtype == torch.float32
+    _lib.check(lib.vb_add_rows_bcast(x.data_ptr(), pos.data_ptr(), out.data_ptr(), rows, pos.shape[0], D, _stream()), "vb_add_rows_bcast")
 
 
 def add3(a, b_bf16, c_bf16, out, accum=None):

@@ -88,9 +88,49 @@ class Encoder(nn.Module):
             layers[f"encoder_layer_{i}"] = EncoderBlock(num_heads, hidden_dim, mlp_dim, dropout, attention_dropout, norm_layer)
         self.layers = nn.Sequential(layers)
         self.ln = norm_layer(hidden_dim)
+        self.__dict__["_engine"] = None
+
+    # Stand-alone use (the reference's Encoder is a public class: vanilla_vit.py:88-106; T2T_ViT carries an identical copy,
+    # t2t_vit.py:89-110): input [B, S, D] -> input + pos_embedding -> dropout -> L blocks -> final LayerNorm, on the same kernels
+    # through a tokens-mode engine over this module's own parameters.  Inside a ViT the parent's engine runs the stack instead.
+    def _get_engine(self):
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            blocks = list(self.layers)
+            b0 = blocks[0]
+            D = self.pos_embedding.shape[-1]
+            eng = VitEngine(image_size=4, patch_size=4, hidden_dim=D, num_heads=b0.num_heads, mlp_dim=b0.mlp[0].out_features,
+                            num_layers=len(blocks), num_classes=1, n_prefix=0, eps=_norm_eps(self.ln),
+                            globals_={"pos": self.pos_embedding, "lnf_w": self.ln.weight, "lnf_b": self.ln.bias},
+                            layers=[b.roles() for b in blocks], seq_length=self.pos_embedding.shape[1])
+            self.__dict__["_engine"] = eng
+        return eng
 
     def forward(self, input: torch.Tensor):
-        raise RuntimeError("vitb200.Encoder is executed by its parent ViT (fused path); it has no standalone forward")
+        torch._assert(input.dim() == 3, f"Expected (batch_size, seq_length, hidden_dim) got {input.shape}")
+        eng = self._get_engine()
+        torch._assert(input.shape[1] == eng.S and input.shape[2] == eng.D, f"Expected (batch_size, {eng.S}, {eng.D}) got {input.shape}")
+        b0 = self.layers[0]
+        eng.p_drop, eng.p_attn = (float(self.dropout.p), float(b0.self_attention.dropout)) if self.training else (0.0, 0.0)
+        params = [p for _, p in eng._order]
+        x = input.contiguous().float()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+            return _TokensFn.apply(eng, x, *params)
+        outs, _ = eng.forward(x, training=(eng.p_drop > 0 or eng.p_attn > 0), want="features")
+        return outs[0].clone()
+
+    def __deepcopy__(self, memo):
+        import copy
+        eng = self.__dict__.pop("_engine", None)
+        try:
+            new = self.__class__.__new__(self.__class__)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                new.__dict__[k] = copy.deepcopy(v, memo)
+            new.__dict__["_engine"] = None
+        finally:
+            self.__dict__["_engine"] = eng
+        return new
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -109,6 +149,21 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, *grads):
         ctx.engine.backward(ctx.ws, list(grads), want=ctx.want)
         return (None, None, None) + (None,) * ctx.n_params
+
+
+class _TokensFn(torch.autograd.Function):
+    """Stand-alone Encoder: like _EncoderFn, but the input tokens receive a gradient too."""
+
+    @staticmethod
+    def forward(ctx, engine, tokens, *params):
+        outs, ws = engine.forward(tokens, training=True, want="features")
+        ctx.engine, ctx.ws, ctx.n_params = engine, ws, len(params)
+        return outs[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        d = ctx.engine.backward(ctx.ws, [grad], want="features")
+        return (None, d.clone()) + (None,) * ctx.n_params
 
 
 def run_engine(engine, images, want, params, module_training, dropout_ps):
