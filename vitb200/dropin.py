@@ -65,14 +65,6 @@ def install(reference_root, stub_missing=True):
     ref_vit.MLP = our_vit.MLP
     ref_tr.TransformerEncoderLayer = our_detr.TransformerEncoderLayer
     ref_tr.TransformerEncoder = our_detr.TransformerEncoder
-    # T2T_ViT carries a verbatim copy of the encoder classes (t2t_vit.py:25-110) and calls self.encoder(x) on its own tokens
-    # (SURVEY.md §8 a13): the stand-alone Encoder.forward serves it.
-    try:
-        ref_t2t = importlib.import_module("models.image_classification.t2t_vit")
-        ref_t2t.Encoder, ref_t2t.EncoderBlock = our_vit.Encoder, our_vit.EncoderBlock
-        ref_t2t.MLPBlock, ref_t2t.MLP = our_vit.MLPBlock, our_vit.MLP
-    except Exception:   # optional: its other imports (token_performer, load_data) may be unavailable
-        pass
 
     # timm shim for models/image_classification/deit.py:4-5
     have_timm = True
@@ -86,10 +78,39 @@ def install(reference_root, stub_missing=True):
         def create_model(name, *a, **k):
             raise RuntimeError(f"timm is not installed: cannot create teacher model '{name}'; pass your own teacher nn.Module "
                                "to utils.distillation_loss.DistillationLoss")
+        import torch
+
+        class DropPath(torch.nn.Module):
+            """Stochastic depth per sample (timm.models.layers.DropPath semantics), needed by token_transformer.py:7."""
+
+            def __init__(self, drop_prob=0.0, scale_by_keep=True):
+                super().__init__()
+                self.drop_prob, self.scale_by_keep = drop_prob, scale_by_keep
+
+            def forward(self, x):
+                if self.drop_prob == 0.0 or not self.training:
+                    return x
+                keep = 1.0 - self.drop_prob
+                mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+                if keep > 0.0 and self.scale_by_keep:
+                    mask.div_(keep)
+                return x * mask
+
         _stub("timm")
         _stub("timm.models", create_model=create_model)
+        sys.modules["timm.models"].__path__ = []   # a package, so that `timm.models.layers` / `.deit` resolve through sys.modules
         _stub("timm.models.deit", VisionTransformerDistilled=our_deit.VisionTransformerDistilled)
+        _stub("timm.models.layers", DropPath=DropPath)
         sys.modules["timm"].models = sys.modules["timm.models"]
         sys.modules["timm.models"].deit = sys.modules["timm.models.deit"]
+        sys.modules["timm.models"].layers = sys.modules["timm.models.layers"]
+    # T2T_ViT carries a verbatim copy of the encoder classes (t2t_vit.py:25-110) and calls self.encoder(x) on its own tokens
+    # (SURVEY.md §8 a13): the stand-alone Encoder.forward serves it.
+    try:
+        ref_t2t = importlib.import_module("models.image_classification.t2t_vit")
+        ref_t2t.Encoder, ref_t2t.EncoderBlock = our_vit.Encoder, our_vit.EncoderBlock
+        ref_t2t.MLPBlock, ref_t2t.MLP = our_vit.MLPBlock, our_vit.MLP
+    except Exception:   # optional: its other imports (token_performer, load_data) may be unavailable
+        pass
     return {"ViT": ViT, "TransformerEncoder": our_detr.TransformerEncoder, "TransformerEncoderLayer": our_detr.TransformerEncoderLayer,
             "VisionTransformerDistilled": our_deit.VisionTransformerDistilled}
