@@ -202,6 +202,16 @@ VB_API int vb_dropout_mask_u8(uint8_t* out, int64_t n, float p, const uint32_t* 
 VB_API int vb_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t C, float* loss_accum,
                             float weight, void* dlogits_bf16, int64_t lddz, float* dlogits_f32, int64_t lddzf,
                             float grad_scale, int32_t* correct_accum, void* stream);
+/* vb_distill_loss: DistillationLoss.forward (utils/distillation_loss.py:30-75) on the two student logits and the teacher's logits,
+ *   forward + both gradients in one pass: *loss_accum += (1-alpha)*CE(z, y) + alpha*D with D = CE(z_kd, argmax teacher) for
+ *   kind = 2 ('hard', :70-71; first maximal index as torch.argmax) or D = tau^2/(B*C) * KL(softmax(teacher/tau) || softmax(z_kd/tau))
+ *   for kind = 1 ('soft', :55-65, the legacy numel() normalisation).  Gradients (times grad_scale) go to bf16 and/or fp32 buffers;
+ *   correct_accum counts argmax(z) == y (the accuracy deit.py:72-74 tracks).  'none' is vb_cross_entropy. */
+VB_API int vb_distill_loss(const float* logits, int64_t ld, const float* logits_kd, int64_t ldkd, const float* teacher_logits,
+                           int64_t ldt, const int64_t* labels, int32_t B, int32_t C, int32_t kind, float alpha, float tau,
+                           float* loss_accum, void* dlogits_bf16, int64_t lddz, void* dlogits_kd_bf16, int64_t lddzkd,
+                           float* dlogits_f32, int64_t lddzf, float* dlogits_kd_f32, int64_t lddzkdf, float grad_scale,
+                           int32_t* correct_accum, void* stream);
 VB_API int vb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                         int32_t* step_counter_dev, void* stream);

@@ -102,3 +102,72 @@ def test_detr_encoder_pre_norm_masked_with_pos():
 @pytest.mark.gpu
 def test_detr_encoder_pre_norm_no_pos():
     _detr_run(S=70, N=2, d_model=256, nhead=4, ffn=512, layers=3, masked=False, with_pos=False, pre_norm=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hard", "soft"])
+def test_fused_distillation_loss_kernel(kind):
+    """vb_distill_loss against the oracle's DistillationLoss on the inputs of the reference-generated golden fixture
+    (tests/golden/distill_loss.pt): loss to 1e-5 of the reference's own value, both logits gradients to 1e-4 (fp32 accumulations)."""
+    import os
+    from vitb200 import ops
+    gd = torch.load(os.path.join(os.path.dirname(__file__), "golden", "distill_loss.pt"))
+    g = torch.Generator().manual_seed(gd["seed"])
+    B, C = 16, 100
+    out, kd = torch.randn(B, C, generator=g), torch.randn(B, C, generator=g)
+    labels = torch.randint(0, C, (B,), generator=g)
+    W = torch.randn(3 * 8 * 8, C, generator=g) * 0.05
+    teacher = torch.randn(B, 3, 8, 8, generator=g).flatten(1) @ W
+    if kind == "hard":
+        teacher[3, 7] = teacher[3, 50] = teacher[3].max() + 1.0   # tie: torch.argmax takes the first maximal index
+    ro, rk = out.clone().requires_grad_(True), kd.clone().requires_grad_(True)
+    ref = O.distillation_loss(ro, rk, labels, teacher, kind, 0.5, 5.0)
+    ref.backward()
+    loss = torch.zeros(1, device="cuda")
+    correct = torch.zeros(1, device="cuda", dtype=torch.int32)
+    dz, dk = torch.empty(B, C, device="cuda"), torch.empty(B, C, device="cuda")
+    dzb, dkb = torch.empty(B, C, device="cuda", dtype=torch.bfloat16), torch.empty(B, C, device="cuda", dtype=torch.bfloat16)
+    ops.distill_loss(out.cuda(), kd.cuda(), teacher.cuda(), labels.cuda(), loss, kind=kind, alpha=0.5, tau=5.0, dlogits_f32=dz,
+                     dlogits_kd_f32=dk, dlogits_bf16=dzb, dlogits_kd_bf16=dkb, correct_accum=correct)
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    if kind == "soft":
+        assert abs(loss.item() - gd["soft"]) < 1e-5      # the unmodified reference's value on the same inputs
+    assert rel_l2(dz, ro.grad) < 1e-4 and rel_l2(dk, rk.grad) < 1e-4
+    assert rel_l2(dzb, ro.grad) < 1e-2 and rel_l2(dkb, rk.grad) < 1e-2
+    assert correct.item() == (out.argmax(1) == labels).sum().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hard", "soft"])
+def test_distillation_trainer_step(kind):
+    """Trainer(distillation=...) (deit.py:57-70's loop body: teacher under no_grad, DistillationLoss, backward, Adam) against the
+    oracle: loss, and the first Adam update's direction through the flat gradient buffer."""
+    from vitb200.deit import VisionTransformerDistilled
+    from vitb200.trainer import Trainer
+    cfg = dict(img_size=32, patch_size=16, depth=2, num_heads=6, embed_dim=384, mlp_ratio=4, num_classes=100)
+    sd = O.seeded_state_dict(O.deit_param_shapes(**cfg), 41)
+    m = VisionTransformerDistilled(drop_rate=0.0, attn_drop_rate=0.0, **cfg)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.set_distilled_training(True)
+    B = 8
+    images, labels = O.seeded_images(B, 32, 42), O.seeded_labels(B, 100, 43)
+    Wt = torch.randn(3 * 32 * 32, 100, generator=torch.Generator().manual_seed(44)) * 0.02
+    teacher = torch.nn.Linear(3 * 32 * 32, 100, bias=False)
+    teacher.weight.data.copy_(Wt.t())
+    teacher_mod = torch.nn.Sequential(torch.nn.Flatten(1), teacher).cuda()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ro, rd = O.deit_forward(ref_sd, images, patch_size=16, depth=2, num_heads=6, training=True, distilled_training=True)
+    ref_loss = O.distillation_loss(ro, rd, labels, images.flatten(1) @ Wt, kind, 0.5, 5.0)
+    ref_loss.backward()
+    tr = Trainer(m, lr=1e-4, distillation=dict(teacher=teacher_mod, type=kind, alpha=0.5, tau=5.0), use_cuda_graph=False)
+    loss = tr.step(images.cuda(), labels.cuda())
+    assert abs(loss.item() - ref_loss.item()) < 1e-2 * max(1.0, abs(ref_loss.item()))
+    eng = m._get_engine()
+    worst = max(((rel_l2(p.grad, ref_sd[n].grad), n) for n, p in m.named_parameters()))
+    assert worst[0] < GRAD_TOL, worst
+    # graph path: three more steps replay the captured step (teacher eager, ahead of the replay) and the loss goes down
+    tr2 = Trainer(m, lr=1e-3, distillation=dict(teacher=teacher_mod, type=kind, alpha=0.5, tau=5.0))
+    losses = [tr2.step(images.cuda(), labels.cuda()).item() for _ in range(6)]
+    assert losses[-1] < losses[0], losses
+    assert eng is m._get_engine()

@@ -62,6 +62,9 @@ SIGNATURES = {
                              c_int32, c_int32, c_void_p]),
     "vb_cross_entropy": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_float, c_void_p, c_int64, c_void_p,
                                  c_int64, c_float, c_void_p, c_void_p]),
+    "vb_distill_loss": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_float,
+                                c_float, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_float,
+                                c_void_p, c_void_p]),
     "vb_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                              c_float, c_int32, c_float, c_void_p, c_void_p]),
     "vb_debug_set_gemm_timeline": (c_int, [c_void_p]),

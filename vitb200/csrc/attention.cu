@@ -9,6 +9,7 @@
 // head-major copy is ever made; O is written token-major, ready to be the A operand of the out-proj GEMM.
 // Token row index = b * batch_stride + s * tok_stride (batch-first ViT: (S,1); sequence-first DETR: (1,N)).
 #include "common.h"
+#include "dropout.cuh"
 #include <cstdlib>
 #include <cuda_bf16.h>
 
@@ -32,6 +33,11 @@ struct AttnParams {
     float* delta;              // [B, H, S]
     __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv;
     long long lddq, lddk, lddv;
+    // attention dropout (DROP instantiations of the 64x64-tile kernels): element ((b*H + h)*S + q)*S + key — the indexing of the
+    // tcgen05 kernels — is kept iff its hash clears drop_thresh; kept probabilities are scaled by drop_inv_keep
+    uint32_t drop_thresh, drop_stream;
+    float drop_inv_keep;
+    const uint32_t* drop_seed;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -148,6 +154,7 @@ __device__ __forceinline__ void store_rows(uint8_t* stage, int row0, const float
 // ----------------------------------------------------------------------------------------------------------
 // Forward: grid (ceil(S/64), H, B), 128 threads; warp w owns query rows [q0 + 16w, q0 + 16w + 16).
 // ----------------------------------------------------------------------------------------------------------
+template <bool DROP>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
@@ -168,6 +175,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const uint32_t drop_key = DROP ? dropout_key(*p.drop_seed, p.drop_stream) : 0u;
+    const uint32_t drop_row0 = (((uint32_t)b * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.S + (uint32_t)(q0 + warp * 16 + (lane >> 2))) * (uint32_t)p.S;
+    const uint32_t drop_row1 = drop_row0 + 8u * (uint32_t)p.S;
 
     for (int j = 0; j < nkv; ++j) {
         const int buf = j & 1;
@@ -219,6 +229,17 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
             l0 += s[nt][0] + s[nt][1];
             l1 += s[nt][2] + s[nt][3];
             o[nt][0] *= a0; o[nt][1] *= a0; o[nt][2] *= a1; o[nt][3] *= a1;
+        }
+        if (DROP) {   // the row sum keeps the un-dropped P (softmax first, dropout on the probabilities: functional.py:6650-6652)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t key = (uint32_t)(kbase + nt * 8 + e);
+                    s[nt][e] = dropout_keep(drop_key, drop_row0 + key, p.drop_thresh) ? s[nt][e] * p.drop_inv_keep : 0.f;
+                    s[nt][e + 2] = dropout_keep(drop_key, drop_row1 + key, p.drop_thresh) ? s[nt][e + 2] * p.drop_inv_keep : 0.f;
+                }
+            }
         }
         mma_p_tile(o, s, smem_addr(sV + buf * TILE_BYTES));
         __syncthreads();  // everyone done with this K/V buffer before it is refilled
@@ -283,6 +304,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const AttnParams p) {
 // Backward dK, dV: grid (ceil(S/64), H, B); warp w owns keys [k0 + 16w, +16); loops over query blocks.
 //   S^T = K Q^T, P^T = exp2(S^T*c - lse[q]), dV += P^T dO, dP^T = V dO^T, dS^T = P^T o (dP^T - delta[q]), dK += dS^T Q
 // ----------------------------------------------------------------------------------------------------------
+template <bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sK = smem;
@@ -324,6 +346,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
         if (!dead1) dead1 = p.kpm[(long long)b * p.S + key1] != 0;
     }
 
+    const uint32_t drop_key = DROP ? dropout_key(*p.drop_seed, p.drop_stream) : 0u;
+    const uint32_t drop_head = ((uint32_t)b * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.S;
+
     for (int j = 0; j < nq; ++j) {
         const int buf = j & 1;
         if (j + 1 < nq) {
@@ -354,9 +379,15 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
                 const float l = sLse[buf * TILE + qi], dl = sDelta[buf * TILE + qi];
                 const float p0 = (qdead || dead0) ? 0.f : exp2f(st[nt][e] * p.scale_log2 - l);
                 const float p1 = (qdead || dead1) ? 0.f : exp2f(st[nt][e + 2] * p.scale_log2 - l);
-                st[nt][e] = p0; st[nt][e + 2] = p1;
-                dpt[nt][e] = p0 * (dpt[nt][e] - dl);
-                dpt[nt][e + 2] = p1 * (dpt[nt][e + 2] - dl);
+                float kp0 = 1.f, kp1 = 1.f;
+                if (DROP) {   // dV sees keep * P / (1 - p); dS = P o (keep * dP / (1 - p) - delta)
+                    const uint32_t qrow = (drop_head + (uint32_t)(j * TILE + qi)) * (uint32_t)p.S;
+                    kp0 = dropout_keep(drop_key, qrow + (uint32_t)key0, p.drop_thresh) ? p.drop_inv_keep : 0.f;
+                    kp1 = dropout_keep(drop_key, qrow + (uint32_t)key1, p.drop_thresh) ? p.drop_inv_keep : 0.f;
+                }
+                st[nt][e] = p0 * kp0; st[nt][e + 2] = p1 * kp1;
+                dpt[nt][e] = p0 * (dpt[nt][e] * kp0 - dl);
+                dpt[nt][e + 2] = p1 * (dpt[nt][e + 2] * kp1 - dl);
             }
         }
         mma_p_tile(dv, st, sdOb);   // dV += P^T dO
@@ -371,6 +402,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
 // Backward dQ: grid (ceil(S/64), H, B); warp w owns queries [q0 + 16w, +16); loops over key blocks.
 //   S = Q K^T, P = exp2(S*c - lse[row]), dP = dO V^T, dS = P o (dP - delta[row]), dQ += dS K
 // ----------------------------------------------------------------------------------------------------------
+template <bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
@@ -394,6 +426,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
     const float lse0 = r0 < p.S ? lse[r0] : 0.f, lse1 = r1 < p.S ? lse[r1] : 0.f;
     const float dl0 = r0 < p.S ? delta[r0] : 0.f, dl1 = r1 < p.S ? delta[r1] : 0.f;
 
+    const uint32_t drop_key = DROP ? dropout_key(*p.drop_seed, p.drop_stream) : 0u;
+    const uint32_t drop_row0 = (((uint32_t)b * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.S + (uint32_t)r0) * (uint32_t)p.S;
+    const uint32_t drop_row1 = drop_row0 + 8u * (uint32_t)p.S;
     uint32_t qf[4][4], dof[4][4];
     float dq[8][4];
 #pragma unroll
@@ -430,8 +465,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
                 if (!dead && p.kpm) dead = p.kpm[(long long)b * p.S + key] != 0;
                 const float p0 = dead ? 0.f : exp2f(s[nt][e] * p.scale_log2 - lse0);
                 const float p1 = dead ? 0.f : exp2f(s[nt][e + 2] * p.scale_log2 - lse1);
-                dp[nt][e] = p0 * (dp[nt][e] - dl0);
-                dp[nt][e + 2] = p1 * (dp[nt][e + 2] - dl1);
+                float kp0 = 1.f, kp1 = 1.f;
+                if (DROP) {
+                    kp0 = dropout_keep(drop_key, drop_row0 + (uint32_t)key, p.drop_thresh) ? p.drop_inv_keep : 0.f;
+                    kp1 = dropout_keep(drop_key, drop_row1 + (uint32_t)key, p.drop_thresh) ? p.drop_inv_keep : 0.f;
+                }
+                dp[nt][e] = p0 * (dp[nt][e] * kp0 - dl0);
+                dp[nt][e + 2] = p1 * (dp[nt][e + 2] * kp1 - dl1);
             }
         }
         mma_p_tile(dq, dp, sKb);     // dQ += dS K
@@ -879,10 +919,37 @@ static AttnParams to_params(const VbAttnDesc* d) {
     p.dout = (const __nv_bfloat16*)d->dout; p.lddo = d->lddo; p.delta = d->delta;
     p.dq = (__nv_bfloat16*)d->dq; p.dk = (__nv_bfloat16*)d->dk; p.dv = (__nv_bfloat16*)d->dv;
     p.lddq = d->lddq; p.lddk = d->lddk; p.lddv = d->lddv;
+    if (d->dropout_p > 0.f) {
+        p.drop_thresh = dropout_threshold(d->dropout_p);
+        p.drop_inv_keep = 1.0f / (1.0f - d->dropout_p);
+        p.drop_seed = d->dropout_seed;
+        p.drop_stream = d->dropout_stream;
+    }
     return p;
 }
 
 }  // namespace vb
+
+// 64x64-tile mma.sync kernels: any S, key-padding masks, both layouts, optional attention dropout
+static int launch_generic_fwd(const VbAttnDesc* d, const vb::AttnParams& p, cudaStream_t st) {
+    using namespace vb;
+    const int smem = 5 * TILE_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
+    if (d->dropout_p > 0.f) {
+        VB_REQUIRE(d->dropout_p < 1.f && d->dropout_seed, "attention: dropout needs 0 <= p < 1 and a device seed");
+        attn_fwd_kernel<true><<<grid, 128, smem, st>>>(p);
+    } else {
+        attn_fwd_kernel<false><<<grid, 128, smem, st>>>(p);
+    }
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
 
 extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     using namespace vb;
@@ -892,7 +959,7 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (d->S <= 256) {
         int tc = attention_fwd_tc3(d, as_stream(stream));
         if (tc <= 0) return tc;
-        if (d->dropout_p > 0.f) return fail(VB_ERR_UNSUPPORTED, "attention dropout needs the tcgen05 path (S <= 208, batch-first, no key-padding mask)");
+        if (d->dropout_p > 0.f) return launch_generic_fwd(d, p, as_stream(stream));   // masks / sequence-first layouts with dropout
         tc = attention_fwd_tc(d, as_stream(stream));
         if (tc <= 0) return tc;   // launched (0) or failed with an error (< 0); 1 = shape not handled there
         const int n_mt = (d->S + 15) / 16;
@@ -902,17 +969,7 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
         if (n_mt <= 14) return launch_short_fwd<7>(p, st);
         return launch_short_fwd<8>(p, st);
     }
-    if (d->dropout_p > 0.f) return fail(VB_ERR_UNSUPPORTED, "attention dropout needs the tcgen05 path (S <= 208, batch-first, no key-padding mask)");
-    const int smem = 5 * TILE_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
-    dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
-    attn_fwd_kernel<<<grid, 128, smem, as_stream(stream)>>>(p);
-    VB_CUDA_CHECK(cudaGetLastError());
-    return VB_OK;
+    return launch_generic_fwd(d, p, as_stream(stream));
 }
 
 extern "C" int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, float* out_accum, void* stream);   // elementwise.cu
@@ -945,8 +1002,9 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
         const int tc = attention_bwd_tc5(d, st);
         if (tc <= 0) return tc;
     }
-    if (d->dropout_p > 0.f) return fail(VB_ERR_UNSUPPORTED, "attention dropout needs the tcgen05 path (S <= 208, batch-first, no key-padding mask)");
-    if (d->S <= 256) {
+    const bool drop = d->dropout_p > 0.f;
+    if (drop) VB_REQUIRE(d->dropout_p < 1.f && d->dropout_seed, "attention_bwd: dropout needs 0 <= p < 1 and a device seed");
+    if (d->S <= 256 && !drop) {
         const int n_mt = (d->S + 15) / 16;
         int rc;
         if (n_mt <= 6) rc = launch_short_bwd<3>(p, st);
@@ -958,17 +1016,25 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     const int smem = 6 * TILE_BYTES + 4 * TILE * (int)sizeof(float);
     static bool configured = false;
     if (!configured) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_BYTES));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_BYTES));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_BYTES));
         configured = true;
     }
     const long long nwarps = (long long)d->B * d->S * d->H;
     attn_delta_kernel<<<delta_grid(nwarps), 256, 0, st>>>(p);
     VB_CUDA_CHECK(cudaGetLastError());
     dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
-    attn_bwd_dkdv_kernel<<<grid, 128, smem, st>>>(p);
-    VB_CUDA_CHECK(cudaGetLastError());
-    attn_bwd_dq_kernel<<<grid, 128, 6 * TILE_BYTES, st>>>(p);
+    if (drop) {
+        attn_bwd_dkdv_kernel<true><<<grid, 128, smem, st>>>(p);
+        VB_CUDA_CHECK(cudaGetLastError());
+        attn_bwd_dq_kernel<true><<<grid, 128, 6 * TILE_BYTES, st>>>(p);
+    } else {
+        attn_bwd_dkdv_kernel<false><<<grid, 128, smem, st>>>(p);
+        VB_CUDA_CHECK(cudaGetLastError());
+        attn_bwd_dq_kernel<false><<<grid, 128, 6 * TILE_BYTES, st>>>(p);
+    }
     VB_CUDA_CHECK(cudaGetLastError());
     return bwd_colsums(d, stream);
 }

@@ -44,6 +44,90 @@ __global__ void ce_kernel(const float* __restrict__ logits, long long ld, const 
     }
 }
 
+// Knowledge-distillation loss of utils/distillation_loss.py:30-75, forward + both logits gradients in one pass, one warp per sample:
+//   loss = (1-alpha) * CE(z, y) + alpha * D,   D = CE(z_kd, argmax teacher)                       (kind 2, 'hard', :70-71)
+//                                              D = T^2/(B*C) * sum q (log q - log p), p = softmax(z_kd/T), q = softmax(t/T)  (kind 1, 'soft', :55-65)
+// dz = (1-alpha)/B (softmax(z) - onehot(y));  dz_kd = alpha/B (softmax(z_kd) - onehot(argmax t))  or  alpha*T/(B*C) (p - q).
+struct WarpStat { float mx; int arg; float sum; };
+__device__ __forceinline__ WarpStat warp_softmax_stat(const float* __restrict__ z, int C, float inv_t, int lane) {
+    WarpStat r{-INFINITY, 0, 0.f};
+    for (int c = lane; c < C; c += 32) {
+        const float v = z[c] * inv_t;
+        if (v > r.mx) { r.mx = v; r.arg = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, r.mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, r.arg, o);
+        if (om > r.mx || (om == r.mx && oa < r.arg)) { r.mx = om; r.arg = oa; }
+    }
+    for (int c = lane; c < C; c += 32) r.sum += __expf(z[c] * inv_t - r.mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r.sum += __shfl_xor_sync(0xffffffffu, r.sum, o);
+    return r;
+}
+
+__global__ void distill_loss_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ logits_kd, long long ldkd,
+                                    const float* __restrict__ teacher, long long ldt, const long long* __restrict__ labels, int B, int C,
+                                    int kind, float alpha, float tau, float* __restrict__ loss_accum, __nv_bfloat16* __restrict__ dz,
+                                    long long lddz, __nv_bfloat16* __restrict__ dzkd, long long lddzkd, float* __restrict__ dz_f32,
+                                    long long lddzf, float* __restrict__ dzkd_f32, long long lddzkdf, float grad_scale,
+                                    int* __restrict__ correct_accum) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const float invB = 1.f / (float)B;
+    const float* z = logits + (long long)row * ld;
+    const int y = (int)labels[row];
+    // base criterion on the class-token logits
+    const WarpStat a = warp_softmax_stat(z, C, 1.f, lane);
+    float loss = (1.f - alpha) * invB * (a.mx + __logf(a.sum) - z[y]);
+    {
+        const float w = grad_scale * (1.f - alpha) * invB, inv = 1.f / a.sum;
+        for (int c = lane; c < C; c += 32) {
+            const float g = w * (__expf(z[c] - a.mx) * inv - (c == y ? 1.f : 0.f));
+            if (dz) dz[(long long)row * lddz + c] = __float2bfloat16_rn(g);
+            if (dz_f32) dz_f32[(long long)row * lddzf + c] = g;
+        }
+    }
+    const float* zk = logits_kd + (long long)row * ldkd;
+    const float* t = teacher + (long long)row * ldt;
+    if (kind == 2) {
+        const WarpStat ts = warp_softmax_stat(t, C, 1.f, lane);   // only the arg-max is used (first maximal index, as torch.argmax)
+        const WarpStat k = warp_softmax_stat(zk, C, 1.f, lane);
+        const int yt = ts.arg;
+        loss += alpha * invB * (k.mx + __logf(k.sum) - zk[yt]);
+        const float w = grad_scale * alpha * invB, inv = 1.f / k.sum;
+        for (int c = lane; c < C; c += 32) {
+            const float g = w * (__expf(zk[c] - k.mx) * inv - (c == yt ? 1.f : 0.f));
+            if (dzkd) dzkd[(long long)row * lddzkd + c] = __float2bfloat16_rn(g);
+            if (dzkd_f32) dzkd_f32[(long long)row * lddzkdf + c] = g;
+        }
+    } else {
+        const float inv_t = 1.f / tau;
+        const WarpStat ts = warp_softmax_stat(t, C, inv_t, lane);
+        const WarpStat k = warp_softmax_stat(zk, C, inv_t, lane);
+        const float lse_t = ts.mx + __logf(ts.sum), lse_k = k.mx + __logf(k.sum);
+        const float w = grad_scale * alpha * tau * invB / (float)C;
+        float kl = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float lq = t[c] * inv_t - lse_t, lp = zk[c] * inv_t - lse_k;
+            const float q = __expf(lq), p = __expf(lp);
+            kl += q * (lq - lp);
+            const float g = w * (p - q);
+            if (dzkd) dzkd[(long long)row * lddzkd + c] = __float2bfloat16_rn(g);
+            if (dzkd_f32) dzkd_f32[(long long)row * lddzkdf + c] = g;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+        loss += alpha * tau * tau * invB / (float)C * kl;
+    }
+    if (lane == 0) {
+        atomicAdd(loss_accum, loss);
+        if (correct_accum && a.arg == y) atomicAdd(correct_accum, 1);   // deit.py:72-74 counts the class-token head's arg-max
+    }
+}
+
 __global__ void step_inc_kernel(int* step) { *step += 1; }
 
 __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
@@ -90,6 +174,24 @@ extern "C" int vb_cross_entropy(const float* logits, int64_t ld, const int64_t* 
     ce_kernel<<<(B + 7) / 8, 256, 0, as_stream(stream)>>>(logits, ld, reinterpret_cast<const long long*>(labels), B, C, loss_accum, weight,
                                                           reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), lddz, dlogits_f32, lddzf,
                                                           grad_scale, correct_accum);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_distill_loss(const float* logits, int64_t ld, const float* logits_kd, int64_t ldkd, const float* teacher_logits,
+                               int64_t ldt, const int64_t* labels, int32_t B, int32_t C, int32_t kind, float alpha, float tau,
+                               float* loss_accum, void* dlogits_bf16, int64_t lddz, void* dlogits_kd_bf16, int64_t lddzkd,
+                               float* dlogits_f32, int64_t lddzf, float* dlogits_kd_f32, int64_t lddzkdf, float grad_scale,
+                               int32_t* correct_accum, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(logits && logits_kd && teacher_logits && labels && loss_accum && B > 0 && C > 0, "distill_loss: bad arguments");
+    VB_REQUIRE(kind == 1 || kind == 2, "distill_loss: kind must be 1 (soft) or 2 (hard)");
+    VB_REQUIRE(kind == 2 || tau > 0.f, "distill_loss: tau must be positive");
+    distill_loss_kernel<<<(B + 7) / 8, 256, 0, as_stream(stream)>>>(
+        logits, ld, logits_kd, ldkd, teacher_logits, ldt, reinterpret_cast<const long long*>(labels), B, C, kind, alpha, tau, loss_accum,
+        reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), lddz, reinterpret_cast<__nv_bfloat16*>(dlogits_kd_bf16), lddzkd, dlogits_f32, lddzf,
+        dlogits_kd_f32, lddzkdf, grad_scale, correct_accum);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

@@ -227,6 +227,23 @@ def cross_entropy(logits, labels, loss_accum, *, weight, dlogits_bf16=None, dlog
     _lib.check(rc, "vb_cross_entropy")
 
 
+def distill_loss(logits, logits_kd, teacher_logits, labels, loss_accum, *, kind, alpha, tau, dlogits_bf16=None, dlogits_kd_bf16=None,
+                 dlogits_f32=None, dlogits_kd_f32=None, grad_scale=1.0, correct_accum=None):
+    """DistillationLoss.forward (utils/distillation_loss.py:30-75) + both logits gradients; kind: 'soft' | 'hard'."""
+    lib = _lib.load()
+    B, C = logits.shape
+    for t in (logits, logits_kd, teacher_logits):
+        assert t.dtype == torch.float32 and t.stride(1) == 1 and t.shape == (B, C)
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    st = lambda t: t.stride(0) if t is not None else 0
+    rc = lib.vb_distill_loss(logits.data_ptr(), logits.stride(0), logits_kd.data_ptr(), logits_kd.stride(0), teacher_logits.data_ptr(),
+                             teacher_logits.stride(0), labels.data_ptr(), B, C, {"soft": 1, "hard": 2}[kind], float(alpha), float(tau),
+                             loss_accum.data_ptr(), _p(dlogits_bf16), st(dlogits_bf16), _p(dlogits_kd_bf16), st(dlogits_kd_bf16),
+                             _p(dlogits_f32), st(dlogits_f32), _p(dlogits_kd_f32), st(dlogits_kd_f32), float(grad_scale),
+                             _p(correct_accum), _stream())
+    _lib.check(rc, "vb_distill_loss")
+
+
 def adam_step(params, grads, exp_avg, exp_avg_sq, params_bf16, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
               step_counter=None):
     """step_counter: optional int32 device tensor holding the step number (incremented by the call; CUDA-graph friendly)."""

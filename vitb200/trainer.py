@@ -53,8 +53,17 @@ class Trainer:
     ``invalidate()`` after changing parameters from outside (load_state_dict, manual edits) so the bf16 shadow is
     refreshed."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, reducer=None, use_cuda_graph=True):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, reducer=None, use_cuda_graph=True,
+                 distillation=None):
+        """distillation: ``dict(teacher=module, type='hard'|'soft', alpha=..., tau=...)`` — the arguments of the reference's
+        ``DistillationLoss`` (utils/distillation_loss.py:21-28; deit.py:33-35) for a two-head (DeiT-style) model: the teacher runs
+        under ``no_grad`` on the same images ahead of the graph replay, the loss and both logits gradients come from one kernel."""
         self.model = model
+        self.distillation = distillation
+        if distillation is not None:
+            assert distillation["type"] in ("soft", "hard"), "distillation type 'none' is the plain cross-entropy trainer"
+            assert getattr(model._get_engine(), "two_heads", False), "distillation needs a model with a distillation head"
+        self._teacher_logits = None
         self.engine = model._get_engine()
         self.opt = FusedAdam(model, lr, betas, eps, weight_decay)
         self.reducer = reducer
@@ -90,8 +99,14 @@ class Trainer:
         outs, ws = eng.forward(images, training=True, want="logits")
         B = images.shape[0]
         world = self.reducer.world_size if self.reducer is not None else 1
-        ops.cross_entropy(outs[0], labels, self._loss, weight=1.0 / B, dlogits_bf16=ws["dlogits"][0][:, :eng.C],
-                          grad_scale=1.0 / world, correct_accum=self._correct)
+        if self.distillation is not None:
+            dl = self.distillation
+            ops.distill_loss(outs[0], outs[1], self._teacher_logits, labels, self._loss, kind=dl["type"], alpha=dl["alpha"],
+                             tau=dl.get("tau", 1.0), dlogits_bf16=ws["dlogits"][0][:, :eng.C], dlogits_kd_bf16=ws["dlogits"][1][:, :eng.C],
+                             grad_scale=1.0 / world, correct_accum=self._correct)
+        else:
+            ops.cross_entropy(outs[0], labels, self._loss, weight=1.0 / B, dlogits_bf16=ws["dlogits"][0][:, :eng.C],
+                              grad_scale=1.0 / world, correct_accum=self._correct)
         if self.reducer is not None:
             self.reducer.begin_step()
         eng.backward(ws, [None] * len(outs), want="logits", dlogits_ready=True)
@@ -109,6 +124,14 @@ class Trainer:
             self._loss = torch.zeros(1, device=dev, dtype=torch.float32)
             self._correct = torch.zeros(1, device=dev, dtype=torch.int32)
         key = (tuple(images.shape), str(images.dtype))
+        if self.distillation is not None:
+            # the teacher is a foreign nn.Module (deit.py:32: a CNN): it runs eagerly, outside the graph, into a static buffer
+            with torch.no_grad():
+                t = self.distillation["teacher"](images if images.is_cuda else images.to(dev, non_blocking=True)).float()
+            if self._teacher_logits is None or self._teacher_logits.shape != t.shape:
+                self._teacher_logits = torch.empty_like(t)
+                self._graphs.clear()
+            self._teacher_logits.copy_(t)
         if not self.use_cuda_graph:
             if not images.is_cuda:
                 images = images.to(dev, non_blocking=True)
