@@ -64,7 +64,7 @@ enum {
     VB_EPI_RESIDUAL = 2, /* C = acc + bias + AUX                                          */
     VB_EPI_RELU = 3,     /* C = max(acc + bias, 0)                                        */
     VB_EPI_DGELU = 4,    /* C = acc * AUX                   (AUX = gelu'(x) saved by VB_EPI_GELU) */
-    VB_EPI_DRELU = 5,    /* C = AUX > 0 ? acc : 0           (AUX = saved relu output)     */
+    VB_EPI_DRELU = 5,    /* C = AUX > 0 ? acc * drelu_scale : 0   (AUX = saved relu output) */
     VB_EPI_ACCUM = 6     /* C += acc  (fp32 C, TMA reduce-add; used by wgrad and split-K) */
 };
 enum { VB_BF16 = 0, VB_F32 = 1 };
@@ -87,6 +87,9 @@ typedef struct VbGemmDesc {
     const float* bias;        /* [N] fp32 or NULL */
     int32_t max_ctas;         /* 0 = one persistent CTA per SM */
     int32_t debug_direct_store; /* 1 = bypass the TMA-store epilogue (slow, for bring-up tests) */
+    float drelu_scale;        /* VB_EPI_DRELU only; 0 means 1.  1/(1-p) when AUX is the DROPPED relu output keep*relu(x)/(1-p)
+                               * (transformer.py:223: linear2(dropout(activation(linear1(src))))) */
+    int32_t reserved0;
 } VbGemmDesc;
 
 VB_API int vb_gemm_bf16(const VbGemmDesc* desc, void* stream);

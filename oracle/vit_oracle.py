@@ -199,7 +199,7 @@ def detr_param_shapes(d_model, dim_feedforward, num_layers, normalize_before):
     return shapes
 
 
-def _detr_self_attn(qk_in, v_in, sd, p, nhead, key_padding_mask):
+def _detr_self_attn(qk_in, v_in, sd, p, nhead, key_padding_mask, attn_drop=None):
     """self_attn(q, k, value=src, key_padding_mask=...)[0] with q = k = src + pos — transformer.py:218-219.
     q is k but k is not v => three separate projections (torch/nn/functional.py:5866-5873); explicit
     softmax(QK^T/sqrt(hd) + mask)V (functional.py:6630-6666); sequence-first tensors [S, N, C]."""
@@ -215,34 +215,42 @@ def _detr_self_attn(qk_in, v_in, sd, p, nhead, key_padding_mask):
     mask = None
     if key_padding_mask is not None:
         mask = torch.zeros(N, 1, 1, S, dtype=q.dtype, device=q.device).masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
-    o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+    if attn_drop is None:
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+    else:                                  # dropout on the [N,H,S,S] softmax weights (functional.py:6650-6652), explicit mask
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+        o = attn_drop(torch.softmax(sc if mask is None else sc + mask, dim=-1)) @ v
     o = o.permute(2, 0, 1, 3).reshape(S, N, D)
     return F.linear(o, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
 
 
 def detr_encoder_forward(sd, src, *, nhead, num_layers, normalize_before=False, activation="relu", src_key_padding_mask=None,
-                         pos=None, eps=1e-5):
-    """TransformerEncoder.forward over TransformerEncoderLayer.forward_post/pre — transformer.py:105-115, 213-241
-    (dropout p=0).  src, pos: [S, N, C]; src_key_padding_mask: [N, S] bool, True = padding."""
+                         pos=None, eps=1e-5, drop=None):
+    """TransformerEncoder.forward over TransformerEncoderLayer.forward_post/pre — transformer.py:105-115, 213-241.
+    src, pos: [S, N, C]; src_key_padding_mask: [N, S] bool, True = padding.  ``drop``: None (p = 0) or an ExplicitDropout whose
+    masks[(layer, site)] replay dropout1 (site 0, :220/:236), dropout (1, :223/:239), dropout2 (2, :224/:240) and the attention
+    dropout of nn.MultiheadAttention(dropout=p) (3, :195) — the reference uses ONE rate for all four."""
     act = F.relu if activation == "relu" else F.gelu
     D = src.shape[-1]
     x = src
+    dz = (lambda key, t: t) if drop is None else drop
     for i in range(num_layers):
         p = f"layers.{i}."
+        ad = None if (drop is None or drop.p_attn == 0) else (lambda P, i=i: drop((i, 3), P))
         if not normalize_before:                                                   # forward_post :213-226
             qk = x if pos is None else x + pos
-            x = x + _detr_self_attn(qk, x, sd, p, nhead, src_key_padding_mask)
+            x = x + dz((i, 0), _detr_self_attn(qk, x, sd, p, nhead, src_key_padding_mask, ad))
             x = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
-            y = F.linear(act(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])), sd[p + "linear2.weight"],
+            y = F.linear(dz((i, 1), act(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))), sd[p + "linear2.weight"],
                          sd[p + "linear2.bias"])
-            x = F.layer_norm(x + y, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+            x = F.layer_norm(x + dz((i, 2), y), (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
         else:                                                                      # forward_pre :228-241
             h = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
             qk = h if pos is None else h + pos
-            x = x + _detr_self_attn(qk, h, sd, p, nhead, src_key_padding_mask)
+            x = x + dz((i, 0), _detr_self_attn(qk, h, sd, p, nhead, src_key_padding_mask, ad))
             h = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
-            x = x + F.linear(act(F.linear(h, sd[p + "linear1.weight"], sd[p + "linear1.bias"])), sd[p + "linear2.weight"],
-                             sd[p + "linear2.bias"])
+            x = x + dz((i, 2), F.linear(dz((i, 1), act(F.linear(h, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))),
+                                        sd[p + "linear2.weight"], sd[p + "linear2.bias"]))
     if "norm.weight" in sd:                                                        # :112-113
         x = F.layer_norm(x, (D,), sd["norm.weight"], sd["norm.bias"], eps)
     return x

@@ -40,10 +40,24 @@ def test_deit_distilled_training(distill):
     assert avg.shape == (B, 100) and rel_l2(avg, ref_avg) < LOGIT_TOL
 
 
-def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos, pre_norm=False):
+def _detr_masks(eng, ws, S, N, p):
+    """The keep masks the kernels used in the last training forward (regenerated from the forward's seed), keyed like the oracle's
+    ExplicitDropout: (layer, site) with site 0 = dropout1, 1 = dropout, 2 = dropout2, 3 = attention weights."""
+    from vitb200 import ops
+    seed, dev, D, Fd, H = ws["drop_seed"], eng.flat.device, eng.D, eng.F, eng.H
+    masks = {}
+    for li in range(eng.L):
+        masks[(li, 0)] = ops.dropout_mask(S * N * D, p, seed, eng.drop_site(li, 0), dev).view(S, N, D).cpu().float()
+        masks[(li, 1)] = ops.dropout_mask(S * N * Fd, p, seed, eng.drop_site(li, 1), dev).view(S, N, Fd).cpu().float()
+        masks[(li, 2)] = ops.dropout_mask(S * N * D, p, seed, eng.drop_site(li, 2), dev).view(S, N, D).cpu().float()
+        masks[(li, 3)] = ops.dropout_mask(N * H * S * S, p, seed, eng.drop_site(li, 3), dev).view(N, H, S, S).cpu().float()
+    return masks
+
+
+def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos, pre_norm=False, p_drop=0.0, activation="relu"):
     from vitb200.detr import TransformerEncoder, TransformerEncoderLayer
     sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, pre_norm), 31)
-    enc = TransformerEncoder(TransformerEncoderLayer(d_model, nhead, ffn, 0.0, "relu", pre_norm), layers,
+    enc = TransformerEncoder(TransformerEncoderLayer(d_model, nhead, ffn, p_drop, activation, pre_norm), layers,
                              torch.nn.LayerNorm(d_model) if pre_norm else None)   # transformer.py:32-33
     enc.load_state_dict(sd)
     enc = enc.cuda().train()
@@ -55,10 +69,22 @@ def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos, pre_norm=Fals
         valid = torch.randint(S // 2, S + 1, (N,), generator=g)
         kpm = torch.arange(S)[None, :] >= valid[:, None]
     gout = torch.randn(S, N, d_model, generator=g)
+    csrc = src.cuda().requires_grad_(True)
+    cpos = pos.cuda().requires_grad_(True) if with_pos else None
+    out = enc(csrc, src_key_padding_mask=kpm.cuda() if masked else None, pos=cpos)
+    out.backward(gout.cuda())
+    drop = None
+    if p_drop > 0:   # replay the kernels' own masks in the oracle (the random stream differs from PyTorch's Philox by design)
+        eng = enc._get_engine()
+        masks = _detr_masks(eng, eng.workspace(S, N, True), S, N, p_drop)
+        for k, v in masks.items():
+            assert abs(v.mean().item() - (1 - p_drop)) < 0.02, (k, v.mean().item())
+        drop = O.ExplicitDropout(masks, p_drop, p_drop)
+    okw = dict(nhead=nhead, num_layers=layers, normalize_before=pre_norm, activation=activation, src_key_padding_mask=kpm, drop=drop)
     ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     rsrc = src.clone().requires_grad_(True)
     rpos = pos.clone().requires_grad_(True) if with_pos else None
-    ref = O.detr_encoder_forward(ref_sd, rsrc, nhead=nhead, num_layers=layers, normalize_before=pre_norm, src_key_padding_mask=kpm, pos=rpos)
+    ref = O.detr_encoder_forward(ref_sd, rsrc, pos=rpos, **okw)
     ref.backward(gout)
     # Calibration (BASELINE.md §6 rule): the bf16 path must be no worse than max(1e-2, the reference's own
     # autocast-bf16 error against the same fp32 truth) -- measured here on the oracle, with 25 % head-room.
@@ -67,14 +93,10 @@ def _detr_run(S, N, d_model, nhead, ffn, layers, masked, with_pos, pre_norm=Fals
     asrc = src.clone().requires_grad_(True)
     apos = pos.clone().requires_grad_(True) if with_pos else None
     with torch.autocast("cpu", dtype=torch.bfloat16):
-        ac = O.detr_encoder_forward(ac_sd, asrc, nhead=nhead, num_layers=layers, normalize_before=pre_norm, src_key_padding_mask=kpm, pos=apos)
+        ac = O.detr_encoder_forward(ac_sd, asrc, pos=apos, **okw)
     ac.float().backward(gout)
     floor_in = max(1e-2, rel_l2(asrc.grad, rsrc.grad))
     floor_w = max(1e-2, max(rel_l2(ac_sd[k].grad, ref_sd[k].grad) for k in sd))
-    csrc = src.cuda().requires_grad_(True)
-    cpos = pos.cuda().requires_grad_(True) if with_pos else None
-    out = enc(csrc, src_key_padding_mask=kpm.cuda() if masked else None, pos=cpos)
-    out.backward(gout.cuda())
     assert rel_l2(out, ref) < LOGIT_TOL, rel_l2(out, ref)
     assert rel_l2(csrc.grad, rsrc.grad) < 1.25 * floor_in, (rel_l2(csrc.grad, rsrc.grad), floor_in)
     if with_pos:
@@ -102,6 +124,34 @@ def test_detr_encoder_pre_norm_masked_with_pos():
 @pytest.mark.gpu
 def test_detr_encoder_pre_norm_no_pos():
     _detr_run(S=70, N=2, d_model=256, nhead=4, ffn=512, layers=3, masked=False, with_pos=False, pre_norm=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,N,d_model,nhead,ffn,masked,with_pos,pre_norm,p,act", [
+    (300, 3, 512, 8, 2048, True, True, False, 0.1, "relu"),    # the reference's default rate and layer type (transformer.py:27-28)
+    (70, 2, 256, 4, 512, False, False, False, 0.1, "relu"),    # short, un-masked: dropout routes it to the 64x64-tile kernels
+    (300, 2, 512, 8, 2048, True, True, True, 0.2, "relu"),     # pre-norm
+    (130, 2, 256, 4, 512, True, True, False, 0.1, "gelu"),
+])
+def test_detr_encoder_dropout_replayed_masks(S, N, d_model, nhead, ffn, masked, with_pos, pre_norm, p, act):
+    """dropout > 0 in train() mode (SURVEY.md §8 f1 for the DETR layer): attention-weight dropout inside the mma.sync attention kernels
+    (any S, key-padding masks, sequence-first), dropout1 / dropout / dropout2 as in transformer.py:220-224, 236-240."""
+    _detr_run(S=S, N=N, d_model=d_model, nhead=nhead, ffn=ffn, layers=2, masked=masked, with_pos=with_pos, pre_norm=pre_norm, p_drop=p,
+              activation=act)
+
+
+@pytest.mark.gpu
+def test_detr_encoder_dropout_eval_and_new_masks():
+    from vitb200.detr import TransformerEncoder, TransformerEncoderLayer
+    torch.manual_seed(0)
+    enc = TransformerEncoder(TransformerEncoderLayer(256, 4, 512, 0.1, "relu", False), 2).cuda().train()
+    src = torch.randn(90, 2, 256, device="cuda")
+    a, b = enc(src), enc(src)
+    assert (a - b).abs().max().item() > 1e-3          # new masks every forward
+    enc.eval()
+    with torch.no_grad():
+        c, d = enc(src), enc(src)
+    assert torch.equal(c, d)                           # eval(): dropout is the identity
 
 
 @pytest.mark.gpu

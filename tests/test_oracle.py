@@ -77,6 +77,66 @@ def test_oracle_distillation_loss_matches_reference_golden():
         assert abs(v - gd[kind]) < 1e-5, (kind, v, gd[kind])
 
 
+def _replayed_masks(seed, shapes, p):
+    """The masks tools/make_golden.py::ReplayedDropout drew inside the live reference, regenerated in the same call order."""
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.rand(sh, generator=g) >= p).float() for sh in shapes]
+
+
+@pytest.mark.parametrize("name", ["detr_enc_dropout_d256.pt", "detr_enc_prenorm_dropout_d256.pt"])
+def test_oracle_detr_dropout_sites_match_reference_golden(name):
+    """dropout > 0 in train(): the reference's four dropout sites per layer (transformer.py:195,220,223,224 / :236,239,240) with the
+    masks made an input.  Call order inside a reference layer: attention weights (site 3), dropout1 (0), dropout (1), dropout2 (2)."""
+    gd = load(name)
+    d, h, ffn, L, S, N, seed, p, pre = gd["d_model"], gd["nhead"], gd["ffn"], gd["layers"], gd["S"], gd["N"], gd["seed"], gd["p"], gd["pre_norm"]
+    drawn = _replayed_masks(seed + 2, gd["mask_shapes"], p)
+    assert len(drawn) == 4 * L and gd["mask_shapes"][0] == (N * h, S, S)
+    masks = {}
+    for i in range(L):
+        for j, site in enumerate((3, 0, 1, 2)):
+            masks[(i, site)] = drawn[4 * i + j]
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.detr_param_shapes(d, ffn, L, pre), seed).items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    src = torch.randn(S, N, d, generator=g, requires_grad=True)
+    pos = torch.randn(S, N, d, generator=g, requires_grad=True)
+    valid = torch.randint(S // 2, S + 1, (N,), generator=g)
+    kpm = torch.arange(S)[None, :] >= valid[:, None]
+    gout = torch.randn(S, N, d, generator=g)
+    out = O.detr_encoder_forward(sd, src, nhead=h, num_layers=L, normalize_before=pre, src_key_padding_mask=kpm, pos=pos,
+                                 drop=O.ExplicitDropout(masks, p, p))
+    out.backward(gout)
+    assert rel_l2(out, gd["out"]) < 1e-5
+    assert abs(src.grad.norm().item() - gd["dsrc_norm"]) < 1e-4 * gd["dsrc_norm"]
+    assert abs(pos.grad.norm().item() - gd["dpos_norm"]) < 1e-4 * gd["dpos_norm"]
+    for k, n in gd["grad_norms"].items():
+        assert abs(sd[k].grad.norm().item() - n) <= 1e-4 * max(n, 1e-6), k
+    for k, gr in gd["grads_small"].items():
+        assert rel_l2(sd[k].grad, gr) < 1e-4, k
+
+
+def test_oracle_vit_hidden_dropout_sites_match_reference_golden():
+    """ViT hidden dropout (vanilla_vit.py:104 Encoder.dropout, :78 after attention, :38 mlp.2, :42 mlp.4) with replayed masks; the
+    attention dropout of this path sits inside SDPA and cannot be replayed from outside (attention_dropout = 0 in the fixture)."""
+    gd = load("vit_tiny_hidden_dropout_b4.pt")
+    cfg, batch, seed, p = gd["cfg"], gd["batch"], gd["seed"], gd["p"]
+    drawn = _replayed_masks(seed + 3, gd["mask_shapes"], p)
+    L = cfg["num_layers"]
+    assert len(drawn) == 1 + 3 * L
+    masks = {"embed": drawn[0]}
+    for i in range(L):
+        for j, site in enumerate((0, 1, 2)):
+            masks[(i, site)] = drawn[1 + 3 * i + j]
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.vit_param_shapes(**cfg), seed).items()}
+    images, labels = O.seeded_images(batch, cfg["image_size"], seed + 1), O.seeded_labels(batch, cfg["num_classes"], seed + 2)
+    logits = O.vit_forward(sd, images, patch_size=cfg["patch_size"], num_layers=L, num_heads=cfg["num_heads"],
+                           drop=O.ExplicitDropout(masks, p, 0.0))
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    assert rel_l2(logits, gd["logits"]) < 1e-5 and abs(loss.item() - gd["loss"]) < 1e-5
+    for k, n in gd["grad_norms"].items():
+        assert abs(sd[k].grad.norm().item() - n) <= 1e-4 * max(n, 1e-6), k
+
+
 def test_known_answers_from_reference_init():
     """KAT-1/3/4: zero head => logits 0 and loss ln(C); key sets and parameter counts."""
     gd = load("kat.pt")

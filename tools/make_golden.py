@@ -97,6 +97,72 @@ def distill_case(name, seed):
     print(name, res)
 
 
+class ReplayedDropout:
+    """Context manager: torch.nn.functional.dropout (what nn.Dropout.forward and nn.MultiheadAttention's explicit-softmax path call)
+    draws its keep masks, in call order, from a seeded generator: keep = rand(x.shape) >= p, y = keep * x / (1 - p).  The oracle test
+    regenerates the same masks in the same order, which pins the SITES of the oracle's ExplicitDropout against the live reference."""
+
+    def __init__(self, seed):
+        self.g = torch.Generator().manual_seed(seed)
+        self.shapes = []
+
+    def __enter__(self):
+        import torch.nn.functional as Fn
+        self._orig = Fn.dropout
+
+        def fake(x, p=0.5, training=True, inplace=False):
+            if not training or p == 0:
+                return x
+            keep = (torch.rand(x.shape, generator=self.g) >= p).to(x.dtype)
+            self.shapes.append(tuple(x.shape))
+            return x * keep / (1.0 - p)
+        Fn.dropout = fake
+        return self
+
+    def __exit__(self, *exc):
+        import torch.nn.functional as Fn
+        Fn.dropout = self._orig
+
+
+def detr_dropout_case(name, d_model, nhead, ffn, layers, S, N, seed, p, pre_norm=False):
+    enc = RefEnc(RefLayer(d_model, nhead, ffn, p, "relu", pre_norm), layers, torch.nn.LayerNorm(d_model) if pre_norm else None)
+    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, pre_norm), seed)
+    enc.load_state_dict(sd)
+    enc.train()
+    g = torch.Generator().manual_seed(seed + 1)
+    src = torch.randn(S, N, d_model, generator=g, requires_grad=True)
+    pos = torch.randn(S, N, d_model, generator=g, requires_grad=True)
+    valid = torch.randint(S // 2, S + 1, (N,), generator=g)
+    kpm = torch.arange(S)[None, :] >= valid[:, None]
+    gout = torch.randn(S, N, d_model, generator=g)
+    with ReplayedDropout(seed + 2) as rd:
+        out = enc(src, src_key_padding_mask=kpm, pos=pos)
+    out.backward(gout)
+    norms, full = grads_summary(enc.named_parameters())
+    torch.save({"d_model": d_model, "nhead": nhead, "ffn": ffn, "layers": layers, "S": S, "N": N, "seed": seed, "pre_norm": pre_norm,
+                "p": p, "mask_shapes": rd.shapes, "out": out.detach(), "dsrc_norm": src.grad.norm().item(),
+                "dpos_norm": pos.grad.norm().item(), "grad_norms": norms, "grads_small": full}, os.path.join(OUT, name))
+    print(name, "out norm", out.norm().item(), "dropout calls", len(rd.shapes))
+
+
+def vit_hidden_dropout_case(name, cfg, batch, seed, p):
+    """Hidden dropout only (attention_dropout = 0): the attention dropout of the ViT path lives inside SDPA and cannot be replayed."""
+    m = RefViT(cfg["image_size"], cfg["patch_size"], cfg["num_layers"], cfg["num_heads"], cfg["hidden_dim"], cfg["mlp_dim"], p, 0.0,
+               cfg["num_classes"])
+    sd = O.seeded_state_dict(O.vit_param_shapes(**cfg), seed)
+    m.load_state_dict(sd)
+    m.train()
+    images, labels = O.seeded_images(batch, cfg["image_size"], seed + 1), O.seeded_labels(batch, cfg["num_classes"], seed + 2)
+    with ReplayedDropout(seed + 3) as rd:
+        logits = m(images)
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    norms, full = grads_summary(m.named_parameters())
+    torch.save({"cfg": cfg, "batch": batch, "seed": seed, "p": p, "mask_shapes": rd.shapes, "logits": logits.detach(), "loss": loss.item(),
+                "grad_norms": norms, "grads_small": full}, os.path.join(OUT, name))
+    print(name, "loss", loss.item(), "dropout calls", len(rd.shapes))
+
+
 def kat_case(name):
     torch.manual_seed(123)
     args = dict(get_args("vit_tiny_cifar10"))
@@ -125,3 +191,6 @@ if __name__ == "__main__":
     detr_case("detr_enc_prenorm_d256.pt", 256, 4, 512, 2, 70, 2, 131, pre_norm=True)
     distill_case("distill_loss.pt", 131)
     kat_case("kat.pt")
+    detr_dropout_case("detr_enc_dropout_d256.pt", 256, 4, 512, 2, 70, 2, 141, 0.1)
+    detr_dropout_case("detr_enc_prenorm_dropout_d256.pt", 256, 4, 512, 2, 70, 2, 151, 0.2, pre_norm=True)
+    vit_hidden_dropout_case("vit_tiny_hidden_dropout_b4.pt", dict(TINY, num_layers=3), 4, 161, 0.1)

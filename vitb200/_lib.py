@@ -27,6 +27,7 @@ class VbGemmDesc(Structure):
         ("AUX", c_void_p), ("ldaux", c_int64), ("batch_stride_aux", c_int64),
         ("bias", c_void_p),
         ("max_ctas", c_int32), ("debug_direct_store", c_int32),
+        ("drelu_scale", c_float), ("reserved0", c_int32),
     ]
 
 

@@ -40,6 +40,7 @@ struct GemmArgs {
     int split_k, kb_per_split, num_units;
     int c_row_offset, aux_bcast, b_batched;
     int direct;
+    float drelu_scale;    // VB_EPI_DRELU: kept elements are multiplied by this (1/(1-p) of the dropout after the activation)
     long long* dbg;       // optional: cycle accounting of cluster 0's MMA issuer (vb_debug_set_gemm_timeline)
     int* sched_counter;   // non-null: dynamic tile scheduling (units beyond the first per cluster are handed out by atomicAdd)
     const float* bias;
@@ -570,7 +571,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if constexpr (EPI == VB_EPI_RELU) v[j] = fmaxf(v[j], 0.f);
-                            if constexpr (EPI == VB_EPI_DRELU) v[j] = x[j] > 0.f ? v[j] : 0.f;
+                            if constexpr (EPI == VB_EPI_DRELU) v[j] = x[j] > 0.f ? v[j] * args.drelu_scale : 0.f;
                         }
                     }
                     // ---- registers -> swizzled staging buffer (or straight to global on the bring-up path) ----
@@ -815,6 +816,7 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     a.aux_bcast = d->aux_batch_broadcast;
     a.b_batched = d->batch_stride_b != 0;
     a.direct = d->debug_direct_store;
+    a.drelu_scale = d->drelu_scale > 0.f ? d->drelu_scale : 1.0f;
     a.sched_counter = nullptr;
     a.dbg = g_gemm_dbg;
     a.bias = d->bias;

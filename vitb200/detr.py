@@ -75,6 +75,8 @@ class DetrEngine(FlatParams):
         self.act = activation
         self.pre_norm = bool(pre_norm)   # TransformerEncoderLayer.forward_pre (transformer.py:228-241) instead of forward_post (:213-226)
         self.has_norm = norm is not None
+        self.p_drop = 0.0            # the layer's single rate (transformer.py:195,198,204-205); set per call by TransformerEncoder.forward
+        self._drop_counter = None
         self._order = []
         seg = []
         if self.has_norm:
@@ -85,6 +87,52 @@ class DetrEngine(FlatParams):
             self._order += [((li, k), r[k]) for k in DETR_ROLES]
             seg.append(len(DETR_ROLES))
         self._layout(seg)
+
+    @staticmethod
+    def drop_site(layer, site):
+        """stream id of a dropout site: 0 = dropout1 (attention output, transformer.py:220/236), 1 = dropout (after the activation,
+        :223/239), 2 = dropout2 (FFN output, :224/240), 3 = attention weights (nn.MultiheadAttention(dropout=), :195)."""
+        return layer * 8 + site
+
+    def _begin_dropout(self, ws):
+        """New masks for this forward: bump the device-side counter and snapshot it into the workspace (graph-capturable)."""
+        dev = self.flat.device
+        if self._drop_counter is None or self._drop_counter.device != dev:
+            self._drop_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._drop_counter.add_(1)
+        if ws.get("drop_seed") is None:
+            ws["drop_seed"] = torch.zeros(1, device=dev, dtype=torch.int32)
+            ws["tmp32"] = torch.empty(ws["M"], self.D, device=dev, dtype=torch.float32)
+        ws["drop_seed"].copy_(self._drop_counter)
+
+    def _ffn_fwd(self, ws, buf, li, pd):
+        """act(linear1(x1_bf)) (+ dropout, transformer.py:223/239) -> the bf16 A operand of linear2."""
+        if self.act == "relu":
+            ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], epilogue=ops.EPI_RELU, bias=self.f((li, "lin1_b")))
+            if pd > 0:   # a = keep * relu(x) / (1 - p): its sign pattern is the backward mask (VB_EPI_DRELU with drelu_scale)
+                ops.dropout_bf16_pair(buf["a"], None, pd, ws["drop_seed"], self.drop_site(li, 1))
+            return buf["a"]
+        if "g" not in buf:
+            buf["g"] = torch.empty_like(buf["a"])
+        ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], C2=buf["g"], epilogue=ops.EPI_GELU, bias=self.f((li, "lin1_b")))
+        if pd > 0:       # the same mask scales gelu(x) and the saved gelu'(x)
+            ops.dropout_bf16_pair(buf["g"], buf["a"], pd, ws["drop_seed"], self.drop_site(li, 1))
+        return buf["g"]
+
+    def _linear_residual(self, ws, A, wkey, bkey, li, site, residual, out, pd):
+        """out = residual + dropout(A W^T + b): one GEMM with the residual epilogue for p = 0, else an fp32 GEMM output followed by the
+        fused keep * x / (1 - p) + residual kernel."""
+        if pd > 0:
+            ops.gemm(A, self.w((li, wkey)), ws["tmp32"], bias=self.f((li, bkey)))
+            ops.dropout_f32(ws["tmp32"], pd, ws["drop_seed"], self.drop_site(li, site), aux=residual, dst=out)
+        else:
+            ops.gemm(A, self.w((li, wkey)), out, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, bkey)), aux=residual)
+
+    def _masked_operand(self, ws, d32, d_bf, li, site, bias_key):
+        """backward of a dropped linear output: the bf16 GEMM operand is keep * d / (1 - p) (mask regenerated from the forward's seed) and
+        its column sum is that layer's bias gradient."""
+        ops.dropout_f32(d32, ws["p_drop"], ws["drop_seed"], self.drop_site(li, site), dst_bf16=d_bf)
+        ops.colsum_bf16(d_bf, self.gview(bias_key))
 
     def workspace(self, S, N, training):
         key = (S, N, training)
@@ -123,6 +171,9 @@ class DetrEngine(FlatParams):
         src2 = src.contiguous().float().view(M, D)
         pos2 = pos.contiguous().float().view(M, D) if pos is not None else None
         ws["pos"], ws["kpm"] = pos2, kpm
+        pd = ws["p_drop"] = float(self.p_drop)   # 0 unless the module is in train() mode
+        if pd > 0:
+            self._begin_dropout(ws)
         x = src2
         if self.pre_norm:
             return self._forward_pre(ws, x, pos2, kpm, training, S, N)
@@ -135,19 +186,13 @@ class DetrEngine(FlatParams):
             ops.gemm(buf["qk_bf"], in_w[:2 * D], buf["qkb"], bias=in_b[:2 * D])
             ops.gemm(buf["x_bf"], in_w[2 * D:], buf["vb"], bias=in_b[2 * D:])
             ops.attention_fwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"] if training else None, B=N, H=H, S=S,
-                              tok_stride=N, batch_stride=1, key_padding_mask=kpm)
-            ops.gemm(buf["o"], self.w((li, "out_w")), buf["x1pre"], epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "out_b")), aux=x)
+                              tok_stride=N, batch_stride=1, key_padding_mask=kpm,
+                              dropout=(pd, ws["drop_seed"], self.drop_site(li, 3)) if pd > 0 else None)
+            self._linear_residual(ws, buf["o"], "out_w", "out_b", li, 0, x, buf["x1pre"], pd)
             ops.layernorm_fwd(buf["x1pre"], self.f((li, "norm1_w")), self.f((li, "norm1_b")), self.eps, y_bf16=buf["x1_bf"], y_f32=buf["x1"],
                               mean=buf["mean1"], rstd=buf["rstd1"])
-            if self.act == "relu":
-                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], epilogue=ops.EPI_RELU, bias=self.f((li, "lin1_b")))
-                act_out = buf["a"]
-            else:
-                if "g" not in buf:
-                    buf["g"] = torch.empty_like(buf["a"])
-                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], C2=buf["g"], epilogue=ops.EPI_GELU, bias=self.f((li, "lin1_b")))
-                act_out = buf["g"]
-            ops.gemm(act_out, self.w((li, "lin2_w")), buf["x2pre"], epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "lin2_b")), aux=buf["x1"])
+            act_out = self._ffn_fwd(ws, buf, li, pd)
+            self._linear_residual(ws, act_out, "lin2_w", "lin2_b", li, 2, buf["x1"], buf["x2pre"], pd)
             x_next = ws["x"][li & 1]
             last = li == self.L - 1
             nbuf = None if last else ws["layer"][(li + 1) if training else 0]
@@ -176,6 +221,7 @@ class DetrEngine(FlatParams):
     # ------------------------------------------------------------------------------------------------------------------
     def _forward_pre(self, ws, x, pos2, kpm, training, S, N):
         M, D, H = ws["M"], self.D, self.H
+        pd = ws["p_drop"]
         if "xin" not in ws:
             ws["xin"] = [torch.empty(M, D, device=x.device, dtype=torch.float32) for _ in range(self.L + 1 if training else 2)]
         xs = ws["xin"]
@@ -196,19 +242,13 @@ class DetrEngine(FlatParams):
             ops.gemm(qk_in, in_w[:2 * D], buf["qkb"], bias=in_b[:2 * D])
             ops.gemm(buf["x_bf"], in_w[2 * D:], buf["vb"], bias=in_b[2 * D:])
             ops.attention_fwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"] if training else None, B=N, H=H, S=S,
-                              tok_stride=N, batch_stride=1, key_padding_mask=kpm)
-            ops.gemm(buf["o"], self.w((li, "out_w")), buf["x1"], epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "out_b")), aux=x_in)
+                              tok_stride=N, batch_stride=1, key_padding_mask=kpm,
+                              dropout=(pd, ws["drop_seed"], self.drop_site(li, 3)) if pd > 0 else None)
+            self._linear_residual(ws, buf["o"], "out_w", "out_b", li, 0, x_in, buf["x1"], pd)
             ops.layernorm_fwd(buf["x1"], self.f((li, "norm2_w")), self.f((li, "norm2_b")), self.eps, y_bf16=buf["x1_bf"],
                               mean=buf["mean2"], rstd=buf["rstd2"])
-            if self.act == "relu":
-                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], epilogue=ops.EPI_RELU, bias=self.f((li, "lin1_b")))
-                act_out = buf["a"]
-            else:
-                if "g" not in buf:
-                    buf["g"] = torch.empty_like(buf["a"])
-                ops.gemm(buf["x1_bf"], self.w((li, "lin1_w")), buf["a"], C2=buf["g"], epilogue=ops.EPI_GELU, bias=self.f((li, "lin1_b")))
-                act_out = buf["g"]
-            ops.gemm(act_out, self.w((li, "lin2_w")), x_out, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "lin2_b")), aux=buf["x1"])
+            act_out = self._ffn_fwd(ws, buf, li, pd)
+            self._linear_residual(ws, act_out, "lin2_w", "lin2_b", li, 2, buf["x1"], x_out, pd)
         x = xs[self.L] if training else xs[self.L & 1]
         if self.has_norm:
             ops.layernorm_fwd(x, self.f(("g", "norm_w")), self.f(("g", "norm_b")), self.eps, y_f32=ws["y"], mean=ws["meanf"], rstd=ws["rstdf"])
@@ -226,16 +266,22 @@ class DetrEngine(FlatParams):
             dpos = ws["dpos"]
             dpos.zero_()
         seg = 0
+        pd = ws["p_drop"]
+        drop3 = lambda li: (pd, ws["drop_seed"], self.drop_site(li, 3)) if pd > 0 else None
+        drelu = dict(drelu_scale=1.0 / (1.0 - pd)) if (pd > 0 and self.act == "relu") else {}
         last_b2 = self.gview((L - 1, "lin2_b"))
         if self.has_norm:
-            ops.layernorm_bwd(g, ws["x_last"], ws["meanf"], ws["rstdf"], self.f(("g", "norm_w")), dx=d, dx_bf16=d_bf,
-                              dgamma=self.gview(("g", "norm_w")), dbeta=self.gview(("g", "norm_b")), dx_colsum=last_b2)
+            ops.layernorm_bwd(g, ws["x_last"], ws["meanf"], ws["rstdf"], self.f(("g", "norm_w")), dx=d, dx_bf16=d_bf if pd == 0 else None,
+                              dgamma=self.gview(("g", "norm_w")), dbeta=self.gview(("g", "norm_b")), dx_colsum=last_b2 if pd == 0 else None)
             self._seg_done(seg)
             seg += 1
         else:
             d.copy_(g)
-            ops.cast_bf16(d.view(-1), d_bf.view(-1))
-            ops.colsum_bf16(d_bf, last_b2)
+            if pd == 0:
+                ops.cast_bf16(d.view(-1), d_bf.view(-1))
+                ops.colsum_bf16(d_bf, last_b2)
+        if pd > 0:
+            self._masked_operand(ws, d, d_bf, L - 1, 2, (L - 1, "lin2_b"))
         for li in range(L - 1, -1, -1):
             buf = ws["layer"][li]
             x_in = ws["xin"][li]
@@ -243,18 +289,21 @@ class DetrEngine(FlatParams):
             act_out = buf["a"] if self.act == "relu" else buf["g"]
             self._wgrad(d_bf, act_out, (li, "lin2_w"))
             ops.gemm(d_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU if self.act == "relu" else ops.EPI_DGELU,
-                     aux=buf["a"])
+                     aux=buf["a"], **drelu)
             self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
             ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
             ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
-            ops.layernorm_bwd(dh, buf["x1"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dres=d, dx=d, dx_bf16=d_bf,
-                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")), dx_colsum=self.gview((li, "out_b")))
+            ops.layernorm_bwd(dh, buf["x1"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dres=d, dx=d, dx_bf16=d_bf if pd == 0 else None,
+                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")),
+                              dx_colsum=self.gview((li, "out_b")) if pd == 0 else None)
+            if pd > 0:
+                self._masked_operand(ws, d, d_bf, li, 0, (li, "out_b"))
             # ---- attention: x1 = x_in + out_proj(attn(q = k = norm1(x_in) + pos, v = norm1(x_in))) ----
             self._wgrad(d_bf, buf["o"], (li, "out_w"))
             ops.gemm(d_bf, self.w((li, "out_w")), dh, b_major=1)      # dO
             dqk, dv = ws["dqk"], ws["dv"]
             ops.attention_bwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"], dh, dqk[:, :D], dqk[:, D:], dv,
-                              ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm)
+                              ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm, dropout=drop3(li))
             in_w = self.w((li, "in_w"))
             self._wgrad(dqk, buf["qk_bf"] if pos2 is not None else buf["x_bf"], (li, "in_w"), rows=(0, 2 * D))
             self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
@@ -266,8 +315,11 @@ class DetrEngine(FlatParams):
             if dpos is not None:
                 ops.add3(dpos, dh, None, dpos, None)                   # d pos += dh
             prev_b2 = self.gview((li - 1, "lin2_b")) if li > 0 else None
-            ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dres=d, dx=d, dx_bf16=d_bf if li > 0 else None,
-                              dgamma=self.gview((li, "norm1_w")), dbeta=self.gview((li, "norm1_b")), dx_colsum=prev_b2, dy_add=dh2)
+            ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dres=d, dx=d,
+                              dx_bf16=d_bf if (li > 0 and pd == 0) else None, dgamma=self.gview((li, "norm1_w")),
+                              dbeta=self.gview((li, "norm1_b")), dx_colsum=prev_b2 if pd == 0 else None, dy_add=dh2)
+            if pd > 0 and li > 0:
+                self._masked_operand(ws, d, d_bf, li - 1, 2, (li - 1, "lin2_b"))
             self._seg_done(seg)
             seg += 1
         return d.view(S, N, D), (dpos.view(S, N, D) if dpos is not None else None)
@@ -285,6 +337,9 @@ class DetrEngine(FlatParams):
             dpos = ws["dpos"]
             dpos.zero_()
         seg = 0
+        pd = ws["p_drop"]
+        drop3 = lambda li: (pd, ws["drop_seed"], self.drop_site(li, 3)) if pd > 0 else None
+        drelu = dict(drelu_scale=1.0 / (1.0 - pd)) if (pd > 0 and self.act == "relu") else {}
         if self.has_norm:
             ops.layernorm_bwd(g, ws["x_last"], ws["meanf"], ws["rstdf"], self.f(("g", "norm_w")), dx=dA, dgamma=self.gview(("g", "norm_w")),
                               dbeta=self.gview(("g", "norm_b")))
@@ -294,26 +349,31 @@ class DetrEngine(FlatParams):
         for li in range(self.L - 1, -1, -1):
             buf = ws["layer"][li]
             # norm2: gradient w.r.t. x2pre = x1 + linear2(act(linear1(x1)))
-            ops.layernorm_bwd(g, buf["x2pre"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dx=dB, dx_bf16=dB_bf,
-                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")), dx_colsum=self.gview((li, "lin2_b")))
+            ops.layernorm_bwd(g, buf["x2pre"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dx=dB, dx_bf16=dB_bf if pd == 0 else None,
+                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")),
+                              dx_colsum=self.gview((li, "lin2_b")) if pd == 0 else None)
+            if pd > 0:   # dB stays the un-masked gradient of x2pre (the residual branch); the linear2 branch sees keep * dB / (1 - p)
+                self._masked_operand(ws, dB, dB_bf, li, 2, (li, "lin2_b"))
             act_out = buf["a"] if self.act == "relu" else buf["g"]
             self._wgrad(dB_bf, act_out, (li, "lin2_w"))
             if self.act == "relu":
-                ops.gemm(dB_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU, aux=buf["a"])
+                ops.gemm(dB_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU, aux=buf["a"], **drelu)
             else:
                 ops.gemm(dB_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"])
             self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
             ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
             ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
             # norm1: its output x1 received dB (residual) + dh (through the FFN); input is x1pre = src + out_proj(attn)
-            ops.layernorm_bwd(dB, buf["x1pre"], buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dx=dA, dx_bf16=dA_bf,
-                              dgamma=self.gview((li, "norm1_w")), dbeta=self.gview((li, "norm1_b")), dx_colsum=self.gview((li, "out_b")),
-                              dy_add=dh)
+            ops.layernorm_bwd(dB, buf["x1pre"], buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dx=dA, dx_bf16=dA_bf if pd == 0 else None,
+                              dgamma=self.gview((li, "norm1_w")), dbeta=self.gview((li, "norm1_b")),
+                              dx_colsum=self.gview((li, "out_b")) if pd == 0 else None, dy_add=dh)
+            if pd > 0:
+                self._masked_operand(ws, dA, dA_bf, li, 0, (li, "out_b"))
             self._wgrad(dA_bf, buf["o"], (li, "out_w"))
             ops.gemm(dA_bf, self.w((li, "out_w")), dh, b_major=1)      # dO
             dqk, dv = ws["dqk"], ws["dv"]
             ops.attention_bwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"], dh, dqk[:, :D], dqk[:, D:], dv,
-                              ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm)
+                              ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm, dropout=drop3(li))
             in_w = self.w((li, "in_w"))
             self._wgrad(dqk, buf["qk_bf"], (li, "in_w"), rows=(0, 2 * D))
             self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
@@ -367,10 +427,8 @@ class TransformerEncoder(nn.Module):
         l0 = self.layers[0]
         if mask is not None:
             raise NotImplementedError("vitb200: src_mask (attn_mask) is not supported; DETR passes None (transformer.py:59)")
-        if self.training and l0.dropout_p > 0:
-            raise NotImplementedError("vitb200: dropout > 0 in train() mode is not implemented in the fused kernels yet; "
-                                      "construct the layer with dropout=0.0 or call .eval()")
         eng = self._get_engine()
+        eng.p_drop = float(l0.dropout_p) if self.training else 0.0   # one rate for the four sites of a layer (transformer.py:195-205)
         kpm = None
         if src_key_padding_mask is not None:
             kpm = src_key_padding_mask.to(device=src.device, dtype=torch.uint8).contiguous()

@@ -42,7 +42,7 @@ def _mat(t, name):
 
 
 def gemm(A, B, C, *, a_major=0, b_major=0, epilogue=EPI_STORE, bias=None, aux=None, C2=None, split_k=1,
-         c_row_offset=0, aux_broadcast=False, max_ctas=0, direct=False):
+         c_row_offset=0, aux_broadcast=False, max_ctas=0, direct=False, drelu_scale=1.0):
     """C = epilogue(A @ B^T). ``A`` is [M,K] (a_major 0) or stored [K,M] (a_major 1); ``B`` is [N,K] or stored [K,N].
 
     3-D tensors add a leading batch dimension (B may stay 2-D to be shared). ``C``/``C2``/``aux`` are [M(+off),N].
@@ -78,6 +78,7 @@ def gemm(A, B, C, *, a_major=0, b_major=0, epilogue=EPI_STORE, bias=None, aux=No
         d.bias = bias.data_ptr()
     d.max_ctas = max_ctas
     d.debug_direct_store = int(direct)
+    d.drelu_scale = float(drelu_scale)
     _lib.check(lib.vb_gemm_bf16(ctypes.byref(d), _stream()), "vb_gemm_bf16")
     return out
 
