@@ -149,3 +149,40 @@ def test_standalone_encoder_matches_oracle():
     enc.eval()
     with torch.no_grad():
         assert rel(enc(x.cuda()), ref) < 1.5e-2
+
+
+@pytest.mark.gpu
+def test_small_batch_inference_graph_replay_matches_eager(monkeypatch):
+    """Eval forwards at small batch are replayed from a CUDA graph (engine.forward_inference): bit-identical to the eager kernel
+    sequence for fresh inputs, and parameter edits between calls are seen (the bf16 cast is part of the graph)."""
+    from vitb200.vit import ViT
+    torch.manual_seed(3)
+    m = ViT(32, 4, 3, 4, 256, 512, 0.1, 0.1, 10)
+    with torch.no_grad():
+        m.heads.head.weight.normal_(std=0.05)
+    m = m.cuda().eval()
+    xs = [torch.randn(3, 3, 32, 32, device="cuda") for _ in range(5)]
+    with torch.no_grad():
+        got = [m(x) for x in xs]                     # eager, capture + replay, replay, ...
+        feats = [m.forward_features(x) for x in xs[:3]]
+    eng = m._get_engine()
+    assert any(isinstance(v, tuple) for v in eng._infer_graphs.values()), "no inference graph was captured"
+    monkeypatch.setenv("VITB200_INFER_GRAPH", "0")
+    with torch.no_grad():
+        want = [m(x) for x in xs]
+        want_f = [m.forward_features(x) for x in xs[:3]]
+    for a, b in zip(got + feats, want + want_f):
+        assert torch.equal(a, b)
+    monkeypatch.setenv("VITB200_INFER_GRAPH", "1")
+    with torch.no_grad():
+        m.heads.head.bias.add_(1.0)
+        shifted = m(xs[0])
+    assert torch.allclose(shifted, want[0] + 1.0, atol=1e-5)
+    # a training step in between (other workspaces, fused optimizer) does not disturb the captured graph
+    m.train()
+    loss = torch.nn.functional.cross_entropy(m(xs[1]), torch.randint(0, 10, (3,), device="cuda"))
+    loss.backward()
+    m.eval()
+    with torch.no_grad():
+        again = m(xs[0])
+    assert torch.equal(again, shifted)

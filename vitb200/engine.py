@@ -85,6 +85,7 @@ class FlatParams:
         for key, p in self._order:
             p.grad = None
         self._ws.clear()
+        self.__dict__.setdefault("_infer_graphs", {}).clear()   # captured inference graphs hold the old buffers' addresses
         self.bf16_fresh = False
         self._sms = torch.cuda.get_device_properties(device).multi_processor_count
 
@@ -113,6 +114,39 @@ class FlatParams:
         o = self.offsets[key]
         v = self.flat_grad[o:o + p.numel()]
         return v.view(p.shape[0], -1) if p.dim() >= 2 else v
+
+    # ------------------------------------------------------------------ small-batch inference ---------------------
+    # At batch 1-32 an eval forward is launch-bound (ViT-L/16: ~175 kernels, each behind a ctypes call that encodes TMA descriptors;
+    # 3.4 ms at batch 1 where the kernels need < 1 ms), so it is replayed from a CUDA graph: first call per shape eager (lazy allocations,
+    # cudaFuncSetAttribute), second call captured, later calls copy the batch into the static input and replay.  The fp32 -> bf16
+    # parameter cast stays inside the graph, so parameter edits between calls are always seen.  VITB200_INFER_GRAPH=0 disables it.
+    INFER_GRAPH_MAX_BATCH = int(os.environ.get("VITB200_INFER_GRAPH_MAX_BATCH", "32"))
+
+    def forward_inference(self, x, *, want):
+        """forward(x, training=False, want=want) for a no-grad caller; CUDA-graph replay for small batches."""
+        self.ensure_bound()
+        if os.environ.get("VITB200_INFER_GRAPH", "1") == "0" or x.shape[0] > self.INFER_GRAPH_MAX_BATCH or not x.is_cuda \
+                or torch.cuda.is_current_stream_capturing():
+            return self.forward(x, training=False, want=want)[0]
+        graphs = self.__dict__.setdefault("_infer_graphs", {})
+        key = (tuple(x.shape), want)
+        ent = graphs.get(key)
+        if ent is None:
+            graphs[key] = "warm"
+            return self.forward(x, training=False, want=want)[0]
+        if ent == "warm":
+            static_in = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+            static_in.copy_(x)
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            self.bf16_fresh = False      # the captured forward must contain the fp32 -> bf16 parameter cast
+            with torch.cuda.graph(graph):
+                outs, _ = self.forward(static_in, training=False, want=want)
+            ent = graphs[key] = (graph, static_in, outs)
+        graph, static_in, outs = ent
+        static_in.copy_(x)
+        graph.replay()
+        return outs
 
     def refresh_bf16(self):
         # a fused optimizer step (trainer.FusedAdam) leaves the shadow up to date and sets bf16_fresh

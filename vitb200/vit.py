@@ -175,7 +175,7 @@ def run_engine(engine, images, want, params, module_training, dropout_ps):
     if engine.p_drop > 0 or engine.p_attn > 0:   # train() under no_grad: dropout still applies; use the training workspaces
         outs, _ = engine.forward(images, training=True, want=want)
     else:
-        outs, _ = engine.forward(images, training=False, want=want)
+        outs = engine.forward_inference(images, want=want)
     res = tuple(o.clone() for o in outs)
     return res if len(res) > 1 else res[0]
 
