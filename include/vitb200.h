@@ -156,7 +156,7 @@ VB_API int vb_debug_set_gemm_timeline(void* device_buffer);
  * vb_cast_f32_to_bf16: flat fp32 -> bf16 cast (master parameters -> tensor-core operands), n % 4 == 0.
  * vb_patchify: images [B,C,H,W] fp32 -> [B, (H/p)(W/p), C*p*p] bf16 with k = c*p*p + i*p + j, the operand of
  *              conv_proj-as-GEMM (nn.Conv2d(k=s=p) + reshape/permute, vanilla_vit.py:129,196-198).
- * vb_token_rows: x[b,t,:] = token_t + pos[t] for the n_prefix (1 = cls, 2 = cls+dist) leading rows of the
+ * vb_token_rows: x[b,t,:] = token_t + pos[t] (pos may be NULL: CPVT / CPE-ViT add it later) for the n_prefix (1 = cls, 2 = cls+dist) leading rows of the
  *              fp32 stream [B,S,D] (torch.cat + pos add, vanilla_vit.py:202-203,104).
  * vb_colsum_bf16: out[c] += sum_r x[r,c] (bias gradients of nn.Linear, autograd of vanilla_vit.py:34,41).
  * vb_embed_bwd: from dx [B,S,D] fp32: dpos += sum_b dx[b]; dtok_t += sum_b dx[b,t]; dbias += sum_{b,s>=n_prefix} dx[b,s];
@@ -192,6 +192,20 @@ VB_API int vb_dropout_f32(const float* src, int64_t ldsrc, const float* aux, int
 VB_API int vb_dropout_bf16_pair(void* x1, void* x2, int64_t ld, int32_t rows, int32_t cols, float p, const uint32_t* seed_dev,
                                 uint32_t stream_id, void* stream);
 VB_API int vb_dropout_mask_u8(uint8_t* out, int64_t n, float p, const uint32_t* seed_dev, uint32_t stream_id, void* stream);
+
+/* ---- Conditional positional encoding / PEG: depthwise 3x3 convolution over the G x G patch-token grid of a
+ * token-major fp32 stream [B, S = n_prefix + G*G, D]; the prefix (class) rows pass through.  Replaces ConditionalPositionalEncoding
+ * (cpe_vit.py:16-30 == cpvt.py:16-30: nn.Conv2d(D, D, 3, padding=1, groups=D) between two layout transposes).  w is the conv weight
+ * [D, 1, 3, 3] as stored by nn.Conv2d, bias [D].
+ *   fwd:        out = [x | conv(x) + bias] (+ pos[s,:] broadcast over the batch, NULL to skip) (+ x - sub, NULL to skip)
+ *   bwd_data:   dx = [dy | conv^T(dy)] (optional); sum_f32 / sum_bf16 = dy + dx (optional; CPVT block tail, cpvt.py:93-96)
+ *   bwd_weight: dw += sum dy * shifted x, db += sum dy over the patch rows (fp32 accumulation into the gradient buffer) */
+VB_API int vb_dwconv3x3_fwd(const float* x, const float* w, const float* bias, const float* pos, const float* sub, float* out,
+                            int32_t B, int32_t S, int32_t D, int32_t n_prefix, int32_t G, void* stream);
+VB_API int vb_dwconv3x3_bwd_data(const float* dy, const float* w, float* dx, float* sum_f32, void* sum_bf16, int32_t B, int32_t S,
+                                 int32_t D, int32_t n_prefix, int32_t G, void* stream);
+VB_API int vb_dwconv3x3_bwd_weight(const float* dy, const float* x, float* dw_accum, float* db_accum, int32_t B, int32_t S, int32_t D,
+                                   int32_t n_prefix, int32_t G, void* stream);
 
 /* ---- Training-step tail -------------------------------------------------------------------
  * vb_cross_entropy: mean-reduction softmax cross-entropy (nn.CrossEntropyLoss at vanilla_vit.py:220,237) forward

@@ -118,6 +118,73 @@ def vit_param_shapes(image_size, patch_size, num_layers, num_heads, hidden_dim, 
 
 
 # ------------------------------------------------------------------------------------------------------------
+# CPE-ViT / CPVT (conditional positional encodings) — cpe_vit.py, cpvt.py, cpvt_gap.py
+# ------------------------------------------------------------------------------------------------------------
+def cond_pos_encoding(x, w, b):
+    """ConditionalPositionalEncoding.forward — cpe_vit.py:21-30 == cpvt.py:21-30: depthwise 3x3 conv over the patch-token grid,
+    class token re-attached."""
+    B, S, D = x.shape
+    cls, t = x[:, :1, :], x[:, 1:, :]
+    G = int(math.sqrt(S - 1))
+    assert G * G == S - 1
+    t = t.transpose(1, 2).reshape(B, D, G, G)
+    t = F.conv2d(t, w, b, padding=1, groups=D)
+    t = t.reshape(B, D, S - 1).transpose(1, 2)
+    return torch.cat((cls, t), dim=1)
+
+
+def cpe_forward_features(sd, images, *, patch_size, num_layers, num_heads, peg_blocks, eps=1e-6, drop=None):
+    """CPEViT.forward_features (cpe_vit.py:181-202; Encoder :110-115 adds the learned pos_embedding) when ``peg_blocks`` is False,
+    CPVT.forward_features (cpvt.py:183-204; Encoder :111-113 has none; EncoderBlock :82-97 ends with
+    ``x = x + y; x = peg(x); return x + y``) when True."""
+    n = images.shape[0]
+    D = sd["class_token"].shape[-1]
+    dz = (lambda key, t: t) if drop is None else drop
+    x = F.conv2d(images, sd["conv_proj.weight"], sd["conv_proj.bias"], stride=patch_size)
+    x = x.reshape(n, D, -1).permute(0, 2, 1)
+    x = torch.cat([sd["class_token"].expand(n, -1, -1), x], dim=1)
+    x = cond_pos_encoding(x, sd["pos_embedding.conv.weight"], sd["pos_embedding.conv.bias"])
+    if not peg_blocks:
+        x = x + sd["encoder.pos_embedding"]
+    x = dz("embed", x)
+    for i in range(num_layers):
+        p = f"encoder.layers.encoder_layer_{i}."
+        if not peg_blocks:
+            x = encoder_block(x, sd, p, num_heads, eps, drop=drop, layer=i)
+            continue
+        h = F.layer_norm(x, (D,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], eps)
+        a = mha_batch_first(h, sd[p + "self_attention.in_proj_weight"], sd[p + "self_attention.in_proj_bias"],
+                            sd[p + "self_attention.out_proj.weight"], sd[p + "self_attention.out_proj.bias"], num_heads,
+                            attn_drop=None if (drop is None or drop.p_attn == 0) else (lambda P, i=i: drop((i, 3), P)))
+        x = dz((i, 0), a) + x
+        y = F.layer_norm(x, (D,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], eps)
+        y = dz((i, 1), F.gelu(F.linear(y, sd[p + "mlp.0.weight"], sd[p + "mlp.0.bias"])))
+        y = dz((i, 2), F.linear(y, sd[p + "mlp.3.weight"], sd[p + "mlp.3.bias"]))
+        x = x + y                                                                   # cpvt.py:93
+        x = cond_pos_encoding(x, sd[p + "peg.conv.weight"], sd[p + "peg.conv.bias"])  # :94
+        x = x + y                                                                   # :96
+    return F.layer_norm(x, (D,), sd["encoder.ln.weight"], sd["encoder.ln.bias"], eps)
+
+
+def cpe_forward(sd, images, **cfg):
+    x = cpe_forward_features(sd, images, **cfg)
+    return F.linear(x[:, 0], sd["heads.head.weight"], sd["heads.head.bias"])
+
+
+def cpe_param_shapes(image_size, patch_size, num_layers, num_heads, hidden_dim, mlp_dim, num_classes, *, peg_blocks):
+    """state_dict keys/shapes of CPEViT (cpe_vit.py:117-166) or CPVT / CPVTGAP (cpvt.py:118-167)."""
+    sh = vit_param_shapes(image_size, patch_size, num_layers, num_heads, hidden_dim, mlp_dim, num_classes)
+    D = hidden_dim
+    sh["pos_embedding.conv.weight"], sh["pos_embedding.conv.bias"] = (D, 1, 3, 3), (D,)
+    if peg_blocks:
+        del sh["encoder.pos_embedding"]
+        for i in range(num_layers):
+            p = f"encoder.layers.encoder_layer_{i}.peg.conv."
+            sh[p + "weight"], sh[p + "bias"] = (D, 1, 3, 3), (D,)
+    return sh
+
+
+# ------------------------------------------------------------------------------------------------------------
 # DeiT-style distilled ViT (timm VisionTransformerDistilled as used at deit.py:39-45,65,95-96)
 # ------------------------------------------------------------------------------------------------------------
 def deit_param_shapes(img_size, patch_size, depth, num_heads, embed_dim, mlp_ratio, num_classes):
@@ -276,6 +343,9 @@ def seeded_state_dict(shapes, seed, std=0.02):
             t = t * (1.0 / std) * math.sqrt(1.0 / shp[-1]) if len(shp) == 2 else t
         if k.endswith("conv_proj.weight") or k.endswith("patch_embed.proj.weight"):
             t = t * (1.0 / std) * math.sqrt(1.0 / (shp[1] * shp[2] * shp[3]))
+        if k.endswith("conv.weight") and tuple(shp[1:]) == (1, 3, 3):   # CPE / PEG depthwise conv: identity-ish, so the stream survives it
+            t = t * (0.15 / std)
+            t[:, 0, 1, 1] += 1.0
         if k.endswith("head.weight") or k.endswith("head_dist.weight"):
             t = t * (1.0 / std) * math.sqrt(1.0 / shp[-1])
         sd[k] = t

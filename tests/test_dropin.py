@@ -28,6 +28,14 @@ from models.image_classification import deit   # imports timm.models.deit.Vision
 assert deit.VisionTransformerDistilled.__module__ == "vitb200.deit"
 from models.image_classification import t2t_vit
 assert t2t_vit.Encoder is vitb200.vit.Encoder and t2t_vit.EncoderBlock is vitb200.vit.EncoderBlock
+from models.image_classification import cpvt, cpe_vit, cpvt_gap
+import vitb200.cpvt
+for mod, name in ((cpe_vit, "CPEViT"), (cpvt, "CPVT"), (cpvt_gap, "CPVTGAP")):
+    cls = getattr(mod, name)
+    assert issubclass(cls, getattr(vitb200.cpvt, name)) and cls.__module__ == mod.__name__
+    assert cls.train_model.__module__ == mod.__name__          # the reference's own loop
+    c = cls(**args)
+    assert c.device == "cuda" and len(c.state_dict()) > 90
 print("DROPIN_OK", len(m.state_dict()))
 """
 

@@ -137,6 +137,60 @@ def test_oracle_vit_hidden_dropout_sites_match_reference_golden():
         assert abs(sd[k].grad.norm().item() - n) <= 1e-4 * max(n, 1e-6), k
 
 
+@pytest.mark.parametrize("name", ["cpe_vit_tiny_b4.pt", "cpvt_tiny_b4.pt", "cpvt_gap_tiny_b4.pt"])
+def test_oracle_cpe_models_match_reference_golden(name):
+    """CPEViT / CPVT / CPVTGAP (cpe_vit.py, cpvt.py, cpvt_gap.py): conditional positional encodings."""
+    gd = load(name)
+    cfg, batch, seed, peg = gd["cfg"], gd["batch"], gd["seed"], gd["which"] != "CPEViT"
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.cpe_param_shapes(**cfg, peg_blocks=peg), seed).items()}
+    images, labels = O.seeded_images(batch, cfg["image_size"], seed + 1), O.seeded_labels(batch, cfg["num_classes"], seed + 2)
+    kw = dict(patch_size=cfg["patch_size"], num_layers=cfg["num_layers"], num_heads=cfg["num_heads"], peg_blocks=peg)
+    logits = O.cpe_forward(sd, images, **kw)
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    assert rel_l2(logits, gd["logits"]) < 1e-5 and abs(loss.item() - gd["loss"]) < 1e-5
+    feats = O.cpe_forward_features(sd, images, **kw).detach()
+    assert rel_l2(feats[:, 0], gd["features_cls"]) < 1e-5
+    assert abs(feats.norm().item() - gd["features_norm"]) < 1e-3 * gd["features_norm"]
+    for k, n in gd["grad_norms"].items():
+        assert abs(sd[k].grad.norm().item() - n) <= 1e-4 * max(n, 1e-6), k
+    for k, g in gd["grads_small"].items():
+        assert rel_l2(sd[k].grad, g) < 1e-4, k
+
+
+def test_cpe_module_keys_and_seed_parity():
+    """The drop-in CPE modules have the reference's state_dict keys / shapes; with the reference tree present, the same seed gives a
+    bit-identical initial state_dict (sub-modules are constructed in the reference's order)."""
+    from vitb200 import cpvt as ours
+    cfg = dict(image_size=32, patch_size=4, num_layers=2, num_heads=4, hidden_dim=256, mlp_dim=512, num_classes=10)
+    for cls, peg in ((ours.CPEViT, False), (ours.CPVT, True), (ours.CPVTGAP, True)):
+        m = cls(32, 4, 2, 4, 256, 512, 0.1, 0.1, 10)
+        sh = O.cpe_param_shapes(**cfg, peg_blocks=peg)
+        assert set(sh) == set(m.state_dict().keys())
+        assert all(tuple(m.state_dict()[k].shape) == tuple(v) for k, v in sh.items())
+        with pytest.raises(RuntimeError):
+            m(torch.zeros(1, 3, 32, 32))              # no CPU fallback
+    if not os.path.isdir(os.path.join(REF, "models")):
+        return
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for name in ("pycocotools", "pycocotools.coco"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pycocotools.coco"].COCO = object
+    sys.modules["pycocotools"].coco = sys.modules["pycocotools.coco"]
+    import importlib
+    for modname, clsname in (("cpe_vit", "CPEViT"), ("cpvt", "CPVT"), ("cpvt_gap", "CPVTGAP")):
+        ref_cls = getattr(importlib.import_module("models.image_classification." + modname), clsname)
+        torch.manual_seed(77)
+        a = ref_cls(32, 4, 2, 4, 256, 512, 0.1, 0.1, 10).state_dict()
+        torch.manual_seed(77)
+        b = getattr(ours, clsname)(32, 4, 2, 4, 256, 512, 0.1, 0.1, 10).state_dict()
+        assert list(a.keys()) == list(b.keys()), clsname
+        for k in a:
+            assert torch.equal(a[k], b[k]), (clsname, k)
+
+
 def test_known_answers_from_reference_init():
     """KAT-1/3/4: zero head => logits 0 and loss ln(C); key sets and parameter counts."""
     gd = load("kat.pt")

@@ -163,6 +163,30 @@ def vit_hidden_dropout_case(name, cfg, batch, seed, p):
     print(name, "loss", loss.item(), "dropout calls", len(rd.shapes))
 
 
+def cpe_case(name, which, cfg, batch, seed):
+    """CPEViT (cpe_vit.py) / CPVT (cpvt.py) / CPVTGAP (cpvt_gap.py) forward + backward; identity-ish seeded PEG weights."""
+    import importlib
+    mod = importlib.import_module({"CPEViT": "models.image_classification.cpe_vit", "CPVT": "models.image_classification.cpvt",
+                                   "CPVTGAP": "models.image_classification.cpvt_gap"}[which])
+    m = getattr(mod, which)(cfg["image_size"], cfg["patch_size"], cfg["num_layers"], cfg["num_heads"], cfg["hidden_dim"], cfg["mlp_dim"],
+                            0.0, 0.0, cfg["num_classes"])
+    sd = O.seeded_state_dict(O.cpe_param_shapes(**cfg, peg_blocks=which != "CPEViT"), seed)
+    assert set(sd) == set(m.state_dict()), set(sd) ^ set(m.state_dict())
+    m.load_state_dict(sd)
+    m.train()
+    images, labels = O.seeded_images(batch, cfg["image_size"], seed + 1), O.seeded_labels(batch, cfg["num_classes"], seed + 2)
+    logits = m(images)
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    with torch.no_grad():
+        feats = m.forward_features(images)
+    norms, full = grads_summary(m.named_parameters())
+    torch.save({"which": which, "cfg": cfg, "batch": batch, "seed": seed, "logits": logits.detach(), "loss": loss.item(),
+                "features_cls": feats[:, 0].clone(), "features_norm": feats.norm().item(), "grad_norms": norms, "grads_small": full},
+               os.path.join(OUT, name))
+    print(name, "loss", loss.item())
+
+
 def kat_case(name):
     torch.manual_seed(123)
     args = dict(get_args("vit_tiny_cifar10"))
@@ -194,3 +218,6 @@ if __name__ == "__main__":
     detr_dropout_case("detr_enc_dropout_d256.pt", 256, 4, 512, 2, 70, 2, 141, 0.1)
     detr_dropout_case("detr_enc_prenorm_dropout_d256.pt", 256, 4, 512, 2, 70, 2, 151, 0.2, pre_norm=True)
     vit_hidden_dropout_case("vit_tiny_hidden_dropout_b4.pt", dict(TINY, num_layers=3), 4, 161, 0.1)
+    cpe_case("cpe_vit_tiny_b4.pt", "CPEViT", dict(TINY, num_layers=3), 4, 171)
+    cpe_case("cpvt_tiny_b4.pt", "CPVT", dict(TINY, num_layers=3), 4, 181)
+    cpe_case("cpvt_gap_tiny_b4.pt", "CPVTGAP", dict(TINY, num_layers=2), 4, 191)

@@ -63,6 +63,11 @@ SIGNATURES = {
                              c_int32, c_int32, c_void_p]),
     "vb_cross_entropy": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_float, c_void_p, c_int64, c_void_p,
                                  c_int64, c_float, c_void_p, c_void_p]),
+    "vb_dwconv3x3_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                 c_void_p]),
+    "vb_dwconv3x3_bwd_data": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p]),
+    "vb_dwconv3x3_bwd_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "vb_distill_loss": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_float,
                                 c_float, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_float,
                                 c_void_p, c_void_p]),

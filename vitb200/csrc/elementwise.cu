@@ -51,7 +51,7 @@ __global__ void token_rows_kernel(float* __restrict__ x, const float* __restrict
         const int t = r % n_prefix;
         const long long b = r / n_prefix;
         const float* tok = t == 0 ? tok0 : tok1;
-        x[(b * S + t) * D + c] = tok[c] + pos[(long long)t * D + c];
+        x[(b * S + t) * D + c] = tok[c] + (pos ? pos[(long long)t * D + c] : 0.f);
     }
 }
 
@@ -202,7 +202,7 @@ extern "C" int vb_token_rows(float* x, const float* tok0, const float* tok1, con
                              int32_t n_prefix, void* stream) {
     using namespace vb;
     if (int rc = check_arch()) return rc;
-    VB_REQUIRE(x && tok0 && pos && n_prefix >= 1 && n_prefix <= 2 && (n_prefix == 1 || tok1), "token_rows: bad arguments");
+    VB_REQUIRE(x && tok0 && n_prefix >= 1 && n_prefix <= 2 && (n_prefix == 1 || tok1), "token_rows: bad arguments");
     token_rows_kernel<<<grid_for((long long)B * n_prefix * D, 256), 256, 0, as_stream(stream)>>>(x, tok0, tok1, pos, B, S, D, n_prefix);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;

@@ -10,6 +10,7 @@ What is rebound:
   models.image_classification.vanilla_vit.{ViT, Encoder, EncoderBlock, MLPBlock, MLP}   (vanilla_vit.py:22-215)
   models.object_detection.transformer.{TransformerEncoderLayer, TransformerEncoder}      (transformer.py:98-115,192-247)
   timm.models.deit.VisionTransformerDistilled (a shim module, since timm is what deit.py:4 imports)
+  models.image_classification.{cpe_vit.CPEViT, cpvt.CPVT, cpvt_gap.CPVTGAP} (+ their ConditionalPositionalEncoding)
 The rebound ``ViT`` subclasses the reference's ``BaseTransformer`` (base.py:12) and borrows the reference's
 ``ViT.train_model`` function object (vanilla_vit.py:217), so the training loop that runs is the reference's own code.
 Nothing is copied from the reference tree.
@@ -112,5 +113,23 @@ def install(reference_root, stub_missing=True):
         ref_t2t.MLPBlock, ref_t2t.MLP = our_vit.MLPBlock, our_vit.MLP
     except Exception:   # optional: its other imports (token_performer, load_data) may be unavailable
         pass
-    return {"ViT": ViT, "TransformerEncoder": our_detr.TransformerEncoder, "TransformerEncoderLayer": our_detr.TransformerEncoderLayer,
+    # CPE-ViT / CPVT / CPVT-GAP: the model classes are rebound and keep the reference's own train_model functions
+    # (cpe_vit.py:214, cpvt.py:215, cpvt_gap.py:216); their helper classes are parameter containers here.
+    from . import cpvt as our_cpvt
+    rebound = {}
+    for modname, clsname in (("cpe_vit", "CPEViT"), ("cpvt", "CPVT"), ("cpvt_gap", "CPVTGAP")):
+        try:
+            ref_mod = importlib.import_module("models.image_classification." + modname)
+        except Exception:   # optional siblings: their data-loader imports may be unavailable
+            continue
+        ref_cls = getattr(ref_mod, clsname)
+        new_cls = type(clsname, (getattr(our_cpvt, clsname),), {"__doc__": getattr(our_cpvt, clsname).__doc__})
+        tm = ref_cls.__dict__.get("train_model")
+        if tm is not None:
+            new_cls.train_model = tm
+        new_cls.__module__ = ref_mod.__name__
+        setattr(ref_mod, clsname, new_cls)
+        ref_mod.ConditionalPositionalEncoding = our_cpvt.ConditionalPositionalEncoding
+        rebound[clsname] = new_cls
+    return {**rebound, "ViT": ViT, "TransformerEncoder": our_detr.TransformerEncoder, "TransformerEncoderLayer": our_detr.TransformerEncoderLayer,
             "VisionTransformerDistilled": our_deit.VisionTransformerDistilled}

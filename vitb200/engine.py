@@ -231,14 +231,24 @@ class VitEngine(FlatParams):
         self._drop_counter = None
         # gradient-production order: heads + final norm, blocks L-1..0, embedding
         seg0 = ["head_w", "head_b"] + (["headd_w", "headd_b"] if self.two_heads else []) + ["lnf_w", "lnf_b"]
-        emb = ["pos", "cls"] + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
+        # Conditional positional encodings: globals "cpe_w"/"cpe_b" = the depthwise conv applied to the token stream
+        # right after the class-token cat (cpe_vit.py:143,197; cpvt.py:144,199); per-layer "peg_w"/"peg_b" = CPVT's PEG at the end of
+        # every block (cpvt.py:80,93-96); "pos" is optional then (CPVT's Encoder has no learned position embedding: cpvt.py:99-113).
+        self.has_cpe = "cpe_w" in globals_
+        self.has_peg = bool(layers) and "peg_w" in layers[0]
+        self.has_pos = "pos" in globals_
+        assert not (self.has_cpe or self.has_peg) or (n_prefix == 1 and not self.tokens_mode), "CPE / PEG: class-token ViT only"
+        assert self.has_pos or self.has_cpe, "a model without a position embedding needs a CPE"
+        emb = (["pos"] if self.has_pos else []) + (["cpe_w", "cpe_b"] if self.has_cpe else []) + ["cls"] \
+            + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
         if self.tokens_mode:
             seg0, emb = ["lnf_w", "lnf_b"], ["pos"]
+        roles = (("peg_w", "peg_b") if self.has_peg else ()) + LAYER_ROLES
         self._order = [(("g", r), globals_[r]) for r in seg0]
         for li in range(num_layers - 1, -1, -1):
-            self._order += [((li, r), layers[li][r]) for r in LAYER_ROLES]
+            self._order += [((li, r), layers[li][r]) for r in roles]
         self._order += [(("g", r), globals_[r]) for r in emb]
-        self._layout([len(seg0)] + [len(LAYER_ROLES)] * num_layers + [len(emb)])
+        self._layout([len(seg0)] + [len(roles)] * num_layers + [len(emb)])
 
     # ------------------------------------------------------------------ dropout -----------------------------------
     EMBED_SITE = 4000
@@ -280,6 +290,13 @@ class VitEngine(FlatParams):
                 "h2": e(M, D), "a": e(M, Fd) if training else None, "g": e(M, Fd),
                 "mean1": e(M, dtype=f32), "rstd1": e(M, dtype=f32), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32),
             })
+        if self.has_cpe:
+            ws["xt"] = e(B, S, D, dtype=f32)       # tokens before the CPE (its wgrad needs them)
+        if self.has_peg:
+            for lb in ws["layer"]:
+                lb["x2"] = e(B, S, D, dtype=f32)   # x1 + mlp(ln_2(x1)): the PEG's input
+        if training and (self.has_cpe or self.has_peg):
+            ws["d_res"] = e(B, S, D, dtype=f32)    # conv^T of the stream gradient
         ws["y_all"] = None  # allocated on demand (forward_features)
         ws["y_tok_f32"] = e(B * max(self.n_prefix, 1), D, dtype=f32)
         ws["y_tok"] = e(B * max(self.n_prefix, 1), D)
@@ -317,11 +334,19 @@ class VitEngine(FlatParams):
         else:  # never hit by the reference configs (3*p*p is a multiple of 8 for p % 4 == 0)
             raise RuntimeError("patch matrix pitch must be a multiple of 8")
         x0 = ws["x"][0]
-        pos = self.f(("g", "pos")).view(1, self.S, self.D)
-        ops.gemm(pat, self.w(("g", "conv_w")), x0, epilogue=ops.EPI_RESIDUAL, bias=self.f(("g", "conv_b")), aux=pos,
-                 c_row_offset=self.n_prefix, aux_broadcast=True)
-        ops.token_rows(x0, self.f(("g", "cls")), self.f(("g", "dist")) if self.n_prefix == 2 else None, pos.view(self.S, self.D),
-                       self.n_prefix)
+        if self.has_cpe:
+            # cat(cls, conv_proj(patches)) -> CPE -> (+ pos_embedding, cpe_vit.py:112): the pos add rides on the depthwise-conv kernel
+            xt = ws["xt"]
+            ops.gemm(pat, self.w(("g", "conv_w")), xt, bias=self.f(("g", "conv_b")), c_row_offset=self.n_prefix)
+            ops.token_rows(xt, self.f(("g", "cls")), None, None, self.n_prefix)
+            ops.dwconv_fwd(xt, self.f(("g", "cpe_w")), self.f(("g", "cpe_b")), x0, n_prefix=self.n_prefix,
+                           pos=self.f(("g", "pos")) if self.has_pos else None)
+        else:
+            pos = self.f(("g", "pos")).view(1, self.S, self.D)
+            ops.gemm(pat, self.w(("g", "conv_w")), x0, epilogue=ops.EPI_RESIDUAL, bias=self.f(("g", "conv_b")), aux=pos,
+                     c_row_offset=self.n_prefix, aux_broadcast=True)
+            ops.token_rows(x0, self.f(("g", "cls")), self.f(("g", "dist")) if self.n_prefix == 2 else None, pos.view(self.S, self.D),
+                           self.n_prefix)
         if ws.get("p_drop", 0.0) > 0:
             x02 = x0.view(ws["M"], self.D)
             ops.dropout_f32(x02, ws["p_drop"], ws["drop_seed"], self.EMBED_SITE, dst=x02)
@@ -346,12 +371,15 @@ class VitEngine(FlatParams):
                           mean=buf["mean2"] if training else None, rstd=buf["rstd2"] if training else None)
         ops.gemm(buf["h2"], self.w((li, "fc1_w")), buf["a"] if training else None, C2=buf["g"], epilogue=ops.EPI_GELU,
                  bias=self.f((li, "fc1_b")))
+        x2 = buf["x2"].view(M, D) if self.has_peg else xout2    # CPVT: x2 = x1 + y feeds the PEG; otherwise it is the block output
         if pd > 0:   # mlp.2: the same mask scales gelu(x) and the saved gelu'(x), so the backward epilogue stays a single multiply
             ops.dropout_bf16_pair(buf["g"], buf["a"], pd, ws["drop_seed"], self.drop_site(li, 1))
             ops.gemm(buf["g"], self.w((li, "fc2_w")), ws["tmp32"], bias=self.f((li, "fc2_b")))
-            ops.dropout_f32(ws["tmp32"], pd, ws["drop_seed"], self.drop_site(li, 2), aux=x12, dst=xout2)   # mlp.4 + residual (:83)
+            ops.dropout_f32(ws["tmp32"], pd, ws["drop_seed"], self.drop_site(li, 2), aux=x12, dst=x2)   # mlp.4 + residual (:83)
         else:
-            ops.gemm(buf["g"], self.w((li, "fc2_w")), xout2, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "fc2_b")), aux=x12)
+            ops.gemm(buf["g"], self.w((li, "fc2_w")), x2, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "fc2_b")), aux=x12)
+        if self.has_peg:   # cpvt.py:93-96: x = x + y; x = peg(x); return x + y   (y = x2 - x1 inside the kernel)
+            ops.dwconv_fwd(buf["x2"], self.f((li, "peg_w")), self.f((li, "peg_b")), x_out, n_prefix=self.n_prefix, sub=buf["x1"])
 
     def forward(self, images, *, training, want):
         """want: 'logits' (head(s) on the prefix token rows) or 'features' ([B,S,D] fp32 after the final norm).
@@ -416,13 +444,15 @@ class VitEngine(FlatParams):
             # from the forward's seed); its column sum is that layer's bias gradient
             ops.dropout_f32(d2, pd, seed, self.drop_site(layer, site), dst_bf16=d_bf)
             ops.colsum_bf16(d_bf, self.gview(bias_key))
+        peg = self.has_peg
+        fuse_tail = pd == 0 and not peg   # the LayerNorm backward also emits the bf16 operand + fc2 bias gradient of the block behind it
         if want == "features":
             gy = grads[0]
             if gy.dtype != torch.float32 or not gy.is_contiguous():
                 gy = gy.contiguous().float()
             ops.layernorm_bwd(gy.view(M, D), x_last.view(M, D), ws["meanf"], ws["rstdf"], self.f(("g", "lnf_w")), dx=d2,
-                              dx_bf16=d_bf if pd == 0 else None, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
-                              dx_colsum=self.gview(last_b2) if pd == 0 else None)
+                              dx_bf16=d_bf if fuse_tail else None, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
+                              dx_colsum=self.gview(last_b2) if fuse_tail else None)
         else:
             d.zero_()
             d_bf.zero_()
@@ -446,15 +476,26 @@ class VitEngine(FlatParams):
                 d_rows = d[:, t, :]
                 db_rows = d_bf.view(B, S, D)[:, t, :]
                 ops.layernorm_bwd(ws["dy_tok"][sl], xr, ws["meanf"][sl], ws["rstdf"][sl], self.f(("g", "lnf_w")), dx=d_rows,
-                                  dx_bf16=db_rows if pd == 0 else None, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
-                                  dx_colsum=self.gview(last_b2) if pd == 0 else None)
-        if pd > 0:
+                                  dx_bf16=db_rows if fuse_tail else None, dgamma=self.gview(("g", "lnf_w")), dbeta=self.gview(("g", "lnf_b")),
+                                  dx_colsum=self.gview(last_b2) if fuse_tail else None)
+        if pd > 0 and not peg:
             masked_operand(L - 1, 2, last_b2)
         self._seg_done(0)
         for li in range(L - 1, -1, -1):
             buf = ws["layer"][li]
             x_in = ws["x"][li].view(M, D)
-            if li == L - 1 and want == "logits" and self.n_prefix == 1 and pd == 0:
+            d_res = d2
+            if peg:
+                # cpvt.py:93-96 backward: out = peg(x2) + y, x2 = x1 + y  =>  d x2 = conv^T(d out), d y = d out + d x2, d x1 (residual) = d x2
+                d_res = ws["d_res"].view(M, D)
+                ops.dwconv_bwd_weight(d, buf["x2"], self.gview((li, "peg_w")).view(-1), self.gview((li, "peg_b")), n_prefix=self.n_prefix)
+                if pd > 0:   # y = dropout(fc2 output): the GEMM operand is keep * (d out + d x2) / (1 - p)
+                    ops.dwconv_bwd_data(d, self.f((li, "peg_w")), n_prefix=self.n_prefix, dx=ws["d_res"], sum_f32=ws["tmp32"])
+                    ops.dropout_f32(ws["tmp32"], pd, seed, self.drop_site(li, 2), dst_bf16=d_bf)
+                else:
+                    ops.dwconv_bwd_data(d, self.f((li, "peg_w")), n_prefix=self.n_prefix, dx=ws["d_res"], sum_bf16=d_bf)
+                ops.colsum_bf16(d_bf, self.gview((li, "fc2_b")))
+            if li == L - 1 and want == "logits" and self.n_prefix == 1 and pd == 0 and not peg:
                 # ViT.forward only consumes x[:, 0] (vanilla_vit.py:212): the gradient entering the last block is non-zero
                 # on the class-token rows only, so its MLP / out-proj backward runs on B rows instead of B*S.  The rows are
                 # addressed in place through strided views (row pitch S * width); nothing is gathered.
@@ -481,7 +522,7 @@ class VitEngine(FlatParams):
                 self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"))
                 ops.colsum_bf16(ws["da"], self.gview((li, "fc1_b")))
                 ops.gemm(ws["da"], self.w((li, "fc1_w")), dh, b_major=1)
-                ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d2, dx=d2,
+                ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d_res, dx=d2,
                                   dx_bf16=d_bf if pd == 0 else None, dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")),
                                   dx_colsum=self.gview((li, "proj_b")) if pd == 0 else None)
                 if pd > 0:
@@ -500,9 +541,9 @@ class VitEngine(FlatParams):
             ops.gemm(dqkv, self.w((li, "qkv_w")), dh, b_major=1)
             prev_b2 = self.gview((li - 1, "fc2_b")) if li > 0 else None
             ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "ln1_w")), dres=d2, dx=d2,
-                              dx_bf16=d_bf if (li > 0 and pd == 0) else None, dgamma=self.gview((li, "ln1_w")), dbeta=self.gview((li, "ln1_b")),
-                              dx_colsum=prev_b2 if pd == 0 else None)
-            if pd > 0 and li > 0:
+                              dx_bf16=d_bf if (li > 0 and fuse_tail) else None, dgamma=self.gview((li, "ln1_w")), dbeta=self.gview((li, "ln1_b")),
+                              dx_colsum=prev_b2 if fuse_tail else None)
+            if pd > 0 and li > 0 and not peg:
                 masked_operand(li - 1, 2, (li - 1, "fc2_b"))
             self._seg_done(L - li)
         # ---- embedding ----
@@ -512,8 +553,18 @@ class VitEngine(FlatParams):
             ops.embed_bwd(d, ws["possum"], None, self.gview(("g", "pos")).view(-1), None, None, None, 0)
             self._seg_done(L + 1)
             return d
-        ops.embed_bwd(d, ws["possum"], ws["dxp"], self.gview(("g", "pos")).view(-1), self.gview(("g", "cls")).view(-1),
-                      self.gview(("g", "dist")).view(-1) if self.n_prefix == 2 else None, self.gview(("g", "conv_b")), self.n_prefix)
+        if self.has_cpe:
+            # x0 = CPE(cat(cls, conv_proj)) (+ pos): d pos = sum_b d; CPE weight gradients from (d, saved tokens); then the class-token /
+            # conv-bias / conv-weight gradients from conv^T(d)
+            if self.has_pos:
+                ops.embed_bwd(d, ws["possum"], None, self.gview(("g", "pos")).view(-1), None, None, None, self.n_prefix)
+            ops.dwconv_bwd_weight(d, ws["xt"], self.gview(("g", "cpe_w")).view(-1), self.gview(("g", "cpe_b")), n_prefix=self.n_prefix)
+            ops.dwconv_bwd_data(d, self.f(("g", "cpe_w")), n_prefix=self.n_prefix, dx=ws["d_res"])
+            ops.embed_bwd(ws["d_res"], ws["possum"], ws["dxp"], None, self.gview(("g", "cls")).view(-1), None, self.gview(("g", "conv_b")),
+                          self.n_prefix)
+        else:
+            ops.embed_bwd(d, ws["possum"], ws["dxp"], self.gview(("g", "pos")).view(-1), self.gview(("g", "cls")).view(-1),
+                          self.gview(("g", "dist")).view(-1) if self.n_prefix == 2 else None, self.gview(("g", "conv_b")), self.n_prefix)
         pat = ws["patches"].view(B * self.P, self.Kp_ld)[:, :self.Kp]
         self._wgrad(ws["dxp"], pat, ("g", "conv_w"))
         self._seg_done(L + 1)

@@ -197,8 +197,8 @@ def patchify(images, out, patch):
 def token_rows(x, tok0, tok1, pos, n_prefix):
     lib = _lib.load()
     B, S, D = x.shape
-    assert x.is_contiguous() and pos.is_contiguous()
-    _lib.check(lib.vb_token_rows(x.data_ptr(), tok0.data_ptr(), _p(tok1), pos.data_ptr(), B, S, D, n_prefix, _stream()), "vb_token_rows")
+    assert x.is_contiguous() and (pos is None or pos.is_contiguous())
+    _lib.check(lib.vb_token_rows(x.data_ptr(), tok0.data_ptr(), _p(tok1), _p(pos), B, S, D, n_prefix, _stream()), "vb_token_rows")
 
 
 def colsum_bf16(x, out_accum):
@@ -214,6 +214,40 @@ def embed_bwd(dx, possum, dx_patches, dpos, dtok0, dtok1, dbias, n_prefix):
     assert dx.is_contiguous() and dx.dtype == torch.float32
     _lib.check(lib.vb_embed_bwd(dx.data_ptr(), possum.data_ptr(), _p(dx_patches), _p(dpos), _p(dtok0), _p(dtok1), _p(dbias),
                                 B, S, D, n_prefix, _stream()), "vb_embed_bwd")
+
+
+def dwconv_fwd(x, w, bias, out, *, n_prefix, pos=None, sub=None):
+    """out = [prefix rows of x | depthwise 3x3 conv over the patch-token grid + bias] (+ pos broadcast) (+ x - sub); fp32 [B, S, D]."""
+    lib = _lib.load()
+    B, S, D = x.shape
+    G = int(round((S - n_prefix) ** 0.5))
+    for t in (x, out, sub):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape == x.shape)
+    assert w.is_contiguous() and w.numel() == D * 9 and (pos is None or (pos.is_contiguous() and pos.numel() == S * D))
+    _lib.check(lib.vb_dwconv3x3_fwd(x.data_ptr(), w.data_ptr(), _p(bias), _p(pos), _p(sub), out.data_ptr(), B, S, D, n_prefix, G, _stream()),
+               "vb_dwconv3x3_fwd")
+
+
+def dwconv_bwd_data(dy, w, *, n_prefix, dx=None, sum_f32=None, sum_bf16=None):
+    """dx = [dy | conv^T(dy)]; sum_* = dy + dx."""
+    lib = _lib.load()
+    B, S, D = dy.shape
+    G = int(round((S - n_prefix) ** 0.5))
+    assert dy.dtype == torch.float32 and dy.is_contiguous()
+    for t in (dx, sum_f32, sum_bf16):
+        assert t is None or (t.is_contiguous() and t.numel() == dy.numel())
+    _lib.check(lib.vb_dwconv3x3_bwd_data(dy.data_ptr(), w.data_ptr(), _p(dx), _p(sum_f32), _p(sum_bf16), B, S, D, n_prefix, G, _stream()),
+               "vb_dwconv3x3_bwd_data")
+
+
+def dwconv_bwd_weight(dy, x, dw, db, *, n_prefix):
+    lib = _lib.load()
+    B, S, D = dy.shape
+    G = int(round((S - n_prefix) ** 0.5))
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous() and x.shape == dy.shape
+    assert dw.dtype == torch.float32 and dw.numel() == D * 9
+    _lib.check(lib.vb_dwconv3x3_bwd_weight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), _p(db), B, S, D, n_prefix, G, _stream()),
+               "vb_dwconv3x3_bwd_weight")
 
 
 def cross_entropy(logits, labels, loss_accum, *, weight, dlogits_bf16=None, dlogits_f32=None, grad_scale=1.0, correct_accum=None):
