@@ -134,7 +134,7 @@ typedef struct VbAttnDesc {
     int64_t lddq, lddk, lddv;
     /* attention dropout (nn.MultiheadAttention(dropout=p), vanilla_vit.py:67): P is multiplied by keep / (1 - p) before P V;
      * the mask is regenerated in backward from (*dropout_seed, dropout_stream, element).  p = 0 disables.  Only the tcgen05
-     * kernels (S <= 208, no key-padding mask) implement it; other shapes return VB_ERR_UNSUPPORTED when p > 0. */
+     * kernels (S <= 208, batch-first, no key-padding mask) and the 64x64-tile mma.sync kernels (everything else) implement it. */
     float dropout_p;
     uint32_t dropout_stream;
     const uint32_t* dropout_seed; /* device pointer */
@@ -143,6 +143,11 @@ typedef struct VbAttnDesc {
      * in registers (warp butterfly + atomicAdd) and leaves the dk part untouched: sum_k dS[q,k] = 0 makes the key-bias gradient
      * exactly zero (softmax ignores a constant key offset).  The other paths run the column-sum kernel on dq, dk, dv. */
     float* dqkv_colsum;
+    /* number of keys / values when it differs from the number of queries S (cross-attention of the DETR decoder layer,
+     * transformer.py:145-147: 100 queries against the S-token memory); 0 = self-attention.  key_padding_mask is then [B,S_kv], lse and
+     * delta stay [B,H,S].  Served by the 64x64-tile mma.sync kernels. */
+    int32_t S_kv;
+    int32_t reserved0;
 } VbAttnDesc;
 VB_API int vb_attention_fwd(const VbAttnDesc* desc, void* stream);
 VB_API int vb_attention_bwd(const VbAttnDesc* desc, void* stream);

@@ -116,3 +116,59 @@ def test_attention_backward_fused_bias_gradient():
         assert ((cs[sl] - ref[sl]).norm() / ref[sl].norm()).item() < 3e-3     # fp32 sums of the unrounded accumulators vs bf16 outputs
     assert cs[D:2 * D].abs().max().item() == 0.0
     assert ref[D:2 * D].norm().item() < 2e-2 * ref[:D].norm().item()          # and it is (numerically) zero in the outputs too
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Sq,Sk,N,H,masked,p", [(100, 300, 3, 8, True, 0.0), (100, 1050, 2, 4, True, 0.0), (37, 70, 2, 4, False, 0.0),
+                                                (100, 200, 2, 4, True, 0.15), (70, 70, 2, 4, True, 0.15)])
+def test_cross_attention_kernels(Sq, Sk, N, H, masked, p):
+    """vb_attention_fwd/bwd with S_kv != S (the DETR decoder's cross-attention, transformer.py:145-147: query = tgt + query_pos against
+    key = memory + pos, value = memory, memory_key_padding_mask) on sequence-first layouts, against the explicit softmax path in fp32 on
+    the same bf16-rounded inputs; with attention dropout the kernels' own keep mask is replayed.  Tolerance: bf16 outputs, 2e-2."""
+    import math
+    import torch
+    from vitb200 import ops
+    D = H * 64
+    g = torch.Generator().manual_seed(3)
+    q = (torch.randn(Sq, N, D, generator=g) * 0.7).bfloat16()
+    k = (torch.randn(Sk, N, D, generator=g) * 0.7).bfloat16()
+    v = torch.randn(Sk, N, D, generator=g).bfloat16()
+    do = torch.randn(Sq, N, D, generator=g).bfloat16()
+    kpm = None
+    if masked:
+        valid = torch.randint(Sk // 2, Sk + 1, (N,), generator=g)
+        kpm = torch.arange(Sk)[None, :] >= valid[:, None]
+    qc, kc, vc, doc = (t.cuda().view(-1, D) for t in (q, k, v, do))
+    o = torch.empty(Sq * N, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(N, H, Sq, device="cuda")
+    delta = torch.empty(N, H, Sq, device="cuda")
+    dq, dk, dv = torch.empty_like(qc), torch.empty_like(kc), torch.empty_like(vc)
+    seed = torch.full((1,), 1234, device="cuda", dtype=torch.int32)
+    drop = (p, seed, 77) if p > 0 else None
+    kw = dict(B=N, H=H, S=Sq, S_kv=Sk, tok_stride=N, batch_stride=1, key_padding_mask=kpm.cuda().to(torch.uint8) if masked else None,
+              dropout=drop)
+    ops.attention_fwd(qc, kc, vc, o, lse, **kw)
+    ops.attention_bwd(qc, kc, vc, o, lse, doc, dq, dk, dv, delta, **kw)
+    keep = None
+    if p > 0:
+        keep = ops.dropout_mask(N * H * Sq * Sk, p, seed, 77, "cuda").view(N, H, Sq, Sk).cpu().float()
+        assert abs(keep.mean().item() - (1 - p)) < 0.02
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = qf.view(Sq, N, H, 64).permute(1, 2, 0, 3)
+    kh = kf.view(Sk, N, H, 64).permute(1, 2, 0, 3)
+    vh = vf.view(Sk, N, H, 64).permute(1, 2, 0, 3)
+    sc = (qh @ kh.transpose(-1, -2)) / math.sqrt(64)
+    if masked:
+        sc = sc.masked_fill(kpm[:, None, None, :], float("-inf"))
+    P = torch.softmax(sc, dim=-1)
+    if keep is not None:
+        P = P * keep / (1 - p)
+    ref = (P @ vh).permute(2, 0, 1, 3).reshape(Sq, N, D)
+    ref.backward(do.float())
+
+    def err(a, b):
+        return ((a.float().cpu().view(b.shape) - b).norm() / b.norm()).item()
+    assert err(o, ref.detach()) < 2e-2
+    assert err(dq, qf.grad) < 2e-2 and err(dk, kf.grad) < 2e-2 and err(dv, vf.grad) < 2e-2
+    lse_ref = torch.logsumexp(sc, dim=-1) / math.log(2.0)
+    assert (lse.cpu() - lse_ref).abs().max().item() < 2e-2

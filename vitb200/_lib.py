@@ -45,6 +45,7 @@ class VbAttnDesc(Structure):
         ("lddq", c_int64), ("lddk", c_int64), ("lddv", c_int64),
         ("dropout_p", c_float), ("dropout_stream", c_uint32), ("dropout_seed", c_void_p),
         ("dqkv_colsum", c_void_p),
+        ("S_kv", c_int32), ("reserved0", c_int32),
     ]
 
 

@@ -25,7 +25,8 @@ struct AttnParams {
     __nv_bfloat16* o; long long ldo;
     float* lse;                // [B, H, S], log2 domain: lse2 = max + log2(sum)
     const uint8_t* kpm;        // [B, S], 1 = key is padding; may be null
-    int B, H, S;
+    int B, H, S;              // S = number of queries
+    int Sk;                   // number of keys / values (= S for self-attention; cross-attention: transformer.py:145-147)
     long long tok_stride, batch_stride;
     float scale, scale_log2;   // 1/sqrt(hd), scale * log2(e)
     // backward
@@ -163,11 +164,11 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
     const long long row_base = (long long)b * p.batch_stride;
-    const int nkv = (p.S + TILE - 1) / TILE;
+    const int nkv = (p.Sk + TILE - 1) / TILE;
 
     load_tile(smem_addr(sQ), p.q, p.ldq, p.tok_stride, row_base, q0, p.S, h);
-    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, 0, p.S, h);
-    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, 0, p.S, h);
+    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, 0, p.Sk, h);
+    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, 0, p.Sk, h);
     cp_async_commit();
 
     uint32_t qf[4][4];
@@ -176,14 +177,14 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     const uint32_t drop_key = DROP ? dropout_key(*p.drop_seed, p.drop_stream) : 0u;
-    const uint32_t drop_row0 = (((uint32_t)b * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.S + (uint32_t)(q0 + warp * 16 + (lane >> 2))) * (uint32_t)p.S;
-    const uint32_t drop_row1 = drop_row0 + 8u * (uint32_t)p.S;
+    const uint32_t drop_row0 = (((uint32_t)b * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.S + (uint32_t)(q0 + warp * 16 + (lane >> 2))) * (uint32_t)p.Sk;
+    const uint32_t drop_row1 = drop_row0 + 8u * (uint32_t)p.Sk;
 
     for (int j = 0; j < nkv; ++j) {
         const int buf = j & 1;
         if (j + 1 < nkv) {
-            load_tile(smem_addr(sK + (buf ^ 1) * TILE_BYTES), p.k, p.ldk, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
-            load_tile(smem_addr(sV + (buf ^ 1) * TILE_BYTES), p.v, p.ldv, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
+            load_tile(smem_addr(sK + (buf ^ 1) * TILE_BYTES), p.k, p.ldk, p.tok_stride, row_base, (j + 1) * TILE, p.Sk, h);
+            load_tile(smem_addr(sV + (buf ^ 1) * TILE_BYTES), p.v, p.ldv, p.tok_stride, row_base, (j + 1) * TILE, p.Sk, h);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -204,8 +205,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int key = kbase + nt * 8 + e;
-                bool dead = key >= p.S;
-                if (!dead && p.kpm) dead = p.kpm[(long long)b * p.S + key] != 0;
+                bool dead = key >= p.Sk;
+                if (!dead && p.kpm) dead = p.kpm[(long long)b * p.Sk + key] != 0;
                 s[nt][e] = dead ? -INFINITY : s[nt][e] * p.scale_log2;
                 s[nt][e + 2] = dead ? -INFINITY : s[nt][e + 2] * p.scale_log2;
             }
@@ -329,8 +330,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
             sDelta[buf * TILE + threadIdx.x] = s < p.S ? delta[s] : 0.f;
         }
     };
-    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, k0, p.S, h);
-    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, k0, p.S, h);
+    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, k0, p.Sk, h);
+    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, k0, p.Sk, h);
     load_q_block(0, 0);
     cp_async_commit();
 
@@ -340,10 +341,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
     for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
     // key validity of this thread's two rows
     const int key0 = k0 + warp * 16 + (lane >> 2), key1 = key0 + 8;
-    bool dead0 = key0 >= p.S, dead1 = key1 >= p.S;
+    bool dead0 = key0 >= p.Sk, dead1 = key1 >= p.Sk;
     if (p.kpm) {
-        if (!dead0) dead0 = p.kpm[(long long)b * p.S + key0] != 0;
-        if (!dead1) dead1 = p.kpm[(long long)b * p.S + key1] != 0;
+        if (!dead0) dead0 = p.kpm[(long long)b * p.Sk + key0] != 0;
+        if (!dead1) dead1 = p.kpm[(long long)b * p.Sk + key1] != 0;
     }
 
     const uint32_t drop_key = DROP ? dropout_key(*p.drop_seed, p.drop_stream) : 0u;
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
                 const float p1 = (qdead || dead1) ? 0.f : exp2f(st[nt][e + 2] * p.scale_log2 - l);
                 float kp0 = 1.f, kp1 = 1.f;
                 if (DROP) {   // dV sees keep * P / (1 - p); dS = P o (keep * dP / (1 - p) - delta)
-                    const uint32_t qrow = (drop_head + (uint32_t)(j * TILE + qi)) * (uint32_t)p.S;
+                    const uint32_t qrow = (drop_head + (uint32_t)(j * TILE + qi)) * (uint32_t)p.Sk;
                     kp0 = dropout_keep(drop_key, qrow + (uint32_t)key0, p.drop_thresh) ? p.drop_inv_keep : 0.f;
                     kp1 = dropout_keep(drop_key, qrow + (uint32_t)key1, p.drop_thresh) ? p.drop_inv_keep : 0.f;
                 }
@@ -394,8 +395,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnParams p) 
         mma_p_tile(dk, dpt, sQb);   // dK += dS^T Q
         __syncthreads();
     }
-    store_rows(sK, warp * 16, dk, p.scale, p.dk, p.lddk, p.tok_stride, row_base, k0, p.S, h);
-    store_rows(sV, warp * 16, dv, 1.0f, p.dv, p.lddv, p.tok_stride, row_base, k0, p.S, h);
+    store_rows(sK, warp * 16, dk, p.scale, p.dk, p.lddk, p.tok_stride, row_base, k0, p.Sk, h);
+    store_rows(sV, warp * 16, dv, 1.0f, p.dv, p.lddv, p.tok_stride, row_base, k0, p.Sk, h);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -412,12 +413,12 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
     const long long row_base = (long long)b * p.batch_stride;
-    const int nkv = (p.S + TILE - 1) / TILE;
+    const int nkv = (p.Sk + TILE - 1) / TILE;
 
     load_tile(smem_addr(sQ), p.q, p.ldq, p.tok_stride, row_base, q0, p.S, h);
     load_tile(smem_addr(sdO), p.dout, p.lddo, p.tok_stride, row_base, q0, p.S, h);
-    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, 0, p.S, h);
-    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, 0, p.S, h);
+    load_tile(smem_addr(sK), p.k, p.ldk, p.tok_stride, row_base, 0, p.Sk, h);
+    load_tile(smem_addr(sV), p.v, p.ldv, p.tok_stride, row_base, 0, p.Sk, h);
     cp_async_commit();
 
     const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
@@ -427,8 +428,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
     const float dl0 = r0 < p.S ? delta[r0] : 0.f, dl1 = r1 < p.S ? delta[r1] : 0.f;
 
     const uint32_t drop_key = DROP ? dropout_key(*p.drop_seed, p.drop_stream) : 0u;
-    const uint32_t drop_row0 = (((uint32_t)b * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.S + (uint32_t)r0) * (uint32_t)p.S;
-    const uint32_t drop_row1 = drop_row0 + 8u * (uint32_t)p.S;
+    const uint32_t drop_row0 = (((uint32_t)b * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.S + (uint32_t)r0) * (uint32_t)p.Sk;
+    const uint32_t drop_row1 = drop_row0 + 8u * (uint32_t)p.Sk;
     uint32_t qf[4][4], dof[4][4];
     float dq[8][4];
 #pragma unroll
@@ -437,8 +438,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
     for (int j = 0; j < nkv; ++j) {
         const int buf = j & 1;
         if (j + 1 < nkv) {
-            load_tile(smem_addr(sK + (buf ^ 1) * TILE_BYTES), p.k, p.ldk, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
-            load_tile(smem_addr(sV + (buf ^ 1) * TILE_BYTES), p.v, p.ldv, p.tok_stride, row_base, (j + 1) * TILE, p.S, h);
+            load_tile(smem_addr(sK + (buf ^ 1) * TILE_BYTES), p.k, p.ldk, p.tok_stride, row_base, (j + 1) * TILE, p.Sk, h);
+            load_tile(smem_addr(sV + (buf ^ 1) * TILE_BYTES), p.v, p.ldv, p.tok_stride, row_base, (j + 1) * TILE, p.Sk, h);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -461,8 +462,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int key = kbase + nt * 8 + e;
-                bool dead = key >= p.S;
-                if (!dead && p.kpm) dead = p.kpm[(long long)b * p.S + key] != 0;
+                bool dead = key >= p.Sk;
+                if (!dead && p.kpm) dead = p.kpm[(long long)b * p.Sk + key] != 0;
                 const float p0 = dead ? 0.f : exp2f(s[nt][e] * p.scale_log2 - lse0);
                 const float p1 = dead ? 0.f : exp2f(s[nt][e + 2] * p.scale_log2 - lse1);
                 float kp0 = 1.f, kp1 = 1.f;
@@ -913,6 +914,7 @@ static AttnParams to_params(const VbAttnDesc* d) {
     p.o = (__nv_bfloat16*)d->o; p.ldo = d->ldo;
     p.lse = d->lse; p.kpm = d->key_padding_mask;
     p.B = d->B; p.H = d->H; p.S = d->S;
+    p.Sk = d->S_kv > 0 ? d->S_kv : d->S;
     p.tok_stride = d->tok_stride; p.batch_stride = d->batch_stride;
     p.scale = 0.125f;
     p.scale_log2 = 0.125f * 1.4426950408889634f;
@@ -956,6 +958,7 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (int rc = check_arch()) return rc;
     if (int rc = check_common(d)) return rc;
     const AttnParams p = to_params(d);
+    if (p.Sk != p.S) return launch_generic_fwd(d, p, as_stream(stream));   // cross-attention: query and key counts differ
     if (d->S <= 256) {
         int tc = attention_fwd_tc3(d, as_stream(stream));
         if (tc <= 0) return tc;
@@ -978,11 +981,11 @@ extern "C" int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t c
 static int bwd_colsums(const VbAttnDesc* d, void* stream) {
     if (d->dqkv_colsum == nullptr) return VB_OK;
     const int cols = d->H * 64;
-    const long long rows = (long long)d->B * d->S;
+    const long long rows = (long long)d->B * d->S, rows_kv = (long long)d->B * (d->S_kv > 0 ? d->S_kv : d->S);
     // token rows are contiguous for both layouts the engine uses (batch-first: b*S + s; sequence-first: s*N + b)
     if (int rc = vb_colsum_bf16(d->dq, d->lddq, (int)rows, cols, d->dqkv_colsum, stream)) return rc;
-    if (int rc = vb_colsum_bf16(d->dk, d->lddk, (int)rows, cols, d->dqkv_colsum + cols, stream)) return rc;
-    return vb_colsum_bf16(d->dv, d->lddv, (int)rows, cols, d->dqkv_colsum + 2 * cols, stream);
+    if (int rc = vb_colsum_bf16(d->dk, d->lddk, (int)rows_kv, cols, d->dqkv_colsum + cols, stream)) return rc;
+    return vb_colsum_bf16(d->dv, d->lddv, (int)rows_kv, cols, d->dqkv_colsum + 2 * cols, stream);
 }
 
 extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
@@ -996,7 +999,8 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     // S <= 208 without a key-padding mask (every ViT / DeiT config): five-product tcgen05 backward (attention_bwd_tc.cu).
     // VITB200_ATTN_TC_BWD=0 selects the mma.sync kernels below (A/B comparisons).
     const char* tc_env = getenv("VITB200_ATTN_TC_BWD");
-    if (d->S <= 208 && d->tok_stride == 1 && d->key_padding_mask == nullptr && !(tc_env && tc_env[0] == '0')) {
+    const bool cross = p.Sk != p.S;
+    if (!cross && d->S <= 208 && d->tok_stride == 1 && d->key_padding_mask == nullptr && !(tc_env && tc_env[0] == '0')) {
         attn_delta_kernel<<<delta_grid((long long)d->B * d->S * d->H), 256, 0, st>>>(p);
         VB_CUDA_CHECK(cudaGetLastError());
         const int tc = attention_bwd_tc5(d, st);
@@ -1004,7 +1008,7 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     }
     const bool drop = d->dropout_p > 0.f;
     if (drop) VB_REQUIRE(d->dropout_p < 1.f && d->dropout_seed, "attention_bwd: dropout needs 0 <= p < 1 and a device seed");
-    if (d->S <= 256 && !drop) {
+    if (d->S <= 256 && !drop && !cross) {
         const int n_mt = (d->S + 15) / 16;
         int rc;
         if (n_mt <= 6) rc = launch_short_bwd<3>(p, st);
@@ -1025,13 +1029,13 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     const long long nwarps = (long long)d->B * d->S * d->H;
     attn_delta_kernel<<<delta_grid(nwarps), 256, 0, st>>>(p);
     VB_CUDA_CHECK(cudaGetLastError());
-    dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
+    dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B), grid_kv((p.Sk + TILE - 1) / TILE, d->H, d->B);
     if (drop) {
-        attn_bwd_dkdv_kernel<true><<<grid, 128, smem, st>>>(p);
+        attn_bwd_dkdv_kernel<true><<<grid_kv, 128, smem, st>>>(p);
         VB_CUDA_CHECK(cudaGetLastError());
         attn_bwd_dq_kernel<true><<<grid, 128, 6 * TILE_BYTES, st>>>(p);
     } else {
-        attn_bwd_dkdv_kernel<false><<<grid, 128, smem, st>>>(p);
+        attn_bwd_dkdv_kernel<false><<<grid_kv, 128, smem, st>>>(p);
         VB_CUDA_CHECK(cudaGetLastError());
         attn_bwd_dq_kernel<false><<<grid, 128, 6 * TILE_BYTES, st>>>(p);
     }

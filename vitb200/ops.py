@@ -113,9 +113,10 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, dx=None, dx_bf16=None,
     _lib.check(rc, "vb_layernorm_bwd")
 
 
-def _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, kpm):
+def _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, kpm, S_kv=0):
     d = _lib.VbAttnDesc()
     d.B, d.H, d.S, d.head_dim = B, H, S, 64
+    d.S_kv = S_kv if S_kv != S else 0
     d.tok_stride, d.batch_stride = tok_stride, batch_stride
     d.q, d.k, d.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     d.ldq, d.ldk, d.ldv = q.stride(0), k.stride(0), v.stride(0)
@@ -131,19 +132,19 @@ def _attn_dropout(d, dropout):
         d.dropout_p, d.dropout_seed, d.dropout_stream = float(dropout[0]), dropout[1].data_ptr(), int(dropout[2])
 
 
-def attention_fwd(q, k, v, o, lse, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None, dropout=None):
-    """q/k/v/o: bf16 2-D views [tokens, H*64] (any row pitch); lse: fp32 [B,H,S] or None."""
+def attention_fwd(q, k, v, o, lse, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None, dropout=None, S_kv=0):
+    """q/k/v/o: bf16 2-D views [tokens, H*64] (any row pitch); lse: fp32 [B,H,S] or None.  S_kv: number of keys when != S (cross-attention)."""
     lib = _lib.load()
-    d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask)
+    d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask, S_kv)
     _attn_dropout(d, dropout)
     _lib.check(lib.vb_attention_fwd(ctypes.byref(d), _stream()), "vb_attention_fwd")
 
 
 def attention_bwd(q, k, v, o, lse, dout, dq, dk, dv, delta, *, B, H, S, tok_stride, batch_stride, key_padding_mask=None, dropout=None,
-                  dqkv_colsum=None):
+                  dqkv_colsum=None, S_kv=0):
     """dqkv_colsum: optional fp32 [3*H*64] accumulator of the column sums of dq|dk|dv (bias gradient of the packed in-projection)."""
     lib = _lib.load()
-    d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask)
+    d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask, S_kv)
     _attn_dropout(d, dropout)
     if dqkv_colsum is not None:
         assert dqkv_colsum.dtype == torch.float32 and dqkv_colsum.is_contiguous() and dqkv_colsum.numel() == 3 * H * 64
