@@ -56,7 +56,7 @@ class ExplicitDropout:
         self.masks, self.p_hidden, self.p_attn = masks, p_hidden, p_attn
 
     def __call__(self, key, x):
-        p = self.p_attn if (isinstance(key, tuple) and key[1] == 3) else self.p_hidden
+        p = self.p_attn if (isinstance(key, tuple) and key[1] in (3, 4)) else self.p_hidden   # 3 / 4: attention weights (self / cross)
         if p == 0 or key not in self.masks:
             return x
         return x * self.masks[key].reshape(x.shape).to(x.dtype) / (1.0 - p)
@@ -324,6 +324,79 @@ def detr_encoder_forward(sd, src, *, nhead, num_layers, normalize_before=False, 
 
 
 # ------------------------------------------------------------------------------------------------------------
+# DETR transformer decoder — transformer.py:66-95 (TransformerDecoder), :118-189 (TransformerDecoderLayer).
+# The reference layer registers its cross-attention as ``multi_head_attn`` (:122) but calls ``self.multihead_attn`` (:148,:172), so it
+# raises AttributeError as written; the restatement below is the forward the code spells out with that name resolved, and it is
+# pinned against the live reference with exactly that alias added (tools/make_golden.py::decoder_case).
+# ------------------------------------------------------------------------------------------------------------
+def detr_decoder_param_shapes(d_model, dim_feedforward, num_layers, with_norm=True):
+    D, Fd = d_model, dim_feedforward
+    sh = {}
+    for i in range(num_layers):
+        p = f"layers.{i}."
+        for a in ("self_attn", "multi_head_attn"):
+            sh.update({p + a + ".in_proj_weight": (3 * D, D), p + a + ".in_proj_bias": (3 * D,),
+                       p + a + ".out_proj.weight": (D, D), p + a + ".out_proj.bias": (D,)})
+        sh.update({p + "linear1.weight": (Fd, D), p + "linear1.bias": (Fd,), p + "linear2.weight": (D, Fd), p + "linear2.bias": (D,)})
+        for n in ("norm1", "norm2", "norm3"):
+            sh.update({p + n + ".weight": (D,), p + n + ".bias": (D,)})
+    if with_norm:
+        sh.update({"norm.weight": (D,), "norm.bias": (D,)})
+    return sh
+
+
+def _mha_seq_first(q_in, k_in, v_in, sd, p, nhead, key_padding_mask, attn_drop=None):
+    """nn.MultiheadAttention (sequence-first) with distinct query / key / value inputs: three projections from the packed
+    in_proj_weight (torch/nn/functional.py:5866-5873), explicit softmax path (functional.py:6630-6666)."""
+    Sq, N, D = q_in.shape
+    Sk = k_in.shape[0]
+    hd = D // nhead
+    w, b = sd[p + "in_proj_weight"], sd[p + "in_proj_bias"]
+    q = F.linear(q_in, w[:D], b[:D]).view(Sq, N, nhead, hd).permute(1, 2, 0, 3)
+    k = F.linear(k_in, w[D:2 * D], b[D:2 * D]).view(Sk, N, nhead, hd).permute(1, 2, 0, 3)
+    v = F.linear(v_in, w[2 * D:], b[2 * D:]).view(Sk, N, nhead, hd).permute(1, 2, 0, 3)
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    if key_padding_mask is not None:
+        sc = sc.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    P = torch.softmax(sc, dim=-1)
+    if attn_drop is not None:
+        P = attn_drop(P)
+    o = (P @ v).permute(2, 0, 1, 3).reshape(Sq, N, D)
+    return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+
+
+def detr_decoder_forward(sd, tgt, memory, *, nhead, num_layers, activation="relu", memory_key_padding_mask=None, pos=None, query_pos=None,
+                         return_intermediate=False, eps=1e-5, drop=None):
+    """TransformerDecoder.forward over TransformerDecoderLayer.forward_post — transformer.py:74-95, 138-156.  Returns [1, Q, N, D], or
+    [L, Q, N, D] with return_intermediate.  ``drop``: ExplicitDropout with masks[(layer, site)]; sites 0 = dropout1, 1 = dropout,
+    2 = dropout3, 3 = self-attention weights, 4 = cross-attention weights, 5 = dropout2."""
+    act = F.relu if activation == "relu" else F.gelu
+    D = tgt.shape[-1]
+    dz = (lambda key, t: t) if drop is None else drop
+    wp = lambda t, p_: t if p_ is None else t + p_
+    has_norm = "norm.weight" in sd
+    fnorm = lambda t: F.layer_norm(t, (D,), sd["norm.weight"], sd["norm.bias"], eps)
+    x, inter = tgt, []
+    for i in range(num_layers):
+        p = f"layers.{i}."
+        ad = (lambda site: None) if drop is None else (lambda site, i=i: (lambda P: drop((i, site), P)))
+        qk = wp(x, query_pos)
+        x = x + dz((i, 0), _mha_seq_first(qk, qk, x, sd, p + "self_attn.", nhead, None, ad(3)))                  # :142-144
+        x = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+        c = _mha_seq_first(wp(x, query_pos), wp(memory, pos), memory, sd, p + "multi_head_attn.", nhead, memory_key_padding_mask, ad(4))
+        x = x + dz((i, 5), c)                                                                                   # :145-150
+        x = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+        y = F.linear(dz((i, 1), act(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))), sd[p + "linear2.weight"],
+                     sd[p + "linear2.bias"])
+        x = F.layer_norm(x + dz((i, 2), y), (D,), sd[p + "norm3.weight"], sd[p + "norm3.bias"], eps)            # :152-155
+        if return_intermediate:
+            inter.append(fnorm(x))                                                                              # :84-85
+    if return_intermediate:
+        return torch.stack(inter)        # :87-93: the last entry is norm(output) either way
+    return (fnorm(x) if has_norm else x).unsqueeze(0)
+
+
+# ------------------------------------------------------------------------------------------------------------
 # Seeded weights / inputs shared by the golden generator, the tests, smoke() and bench.py
 # ------------------------------------------------------------------------------------------------------------
 def seeded_state_dict(shapes, seed, std=0.02):
@@ -334,7 +407,7 @@ def seeded_state_dict(shapes, seed, std=0.02):
     sd = {}
     for k, shp in shapes.items():
         t = torch.randn(*shp, generator=g, dtype=torch.float32) * std
-        is_norm_w = k.endswith("weight") and any(s in k for s in ("ln_1.", "ln_2.", "ln.", "norm1.", "norm2.", "norm."))
+        is_norm_w = k.endswith("weight") and any(s in k for s in ("ln_1.", "ln_2.", "ln.", "norm1.", "norm2.", "norm3.", "norm."))
         if is_norm_w:
             t = t + 1.0
         if k.endswith("in_proj_weight") or k.endswith("qkv.weight") or k.endswith(".0.weight") or k.endswith(".3.weight") or \

@@ -24,6 +24,11 @@ m = ViT(**args)
 assert hasattr(m, "train_model") and m.train_model.__func__.__module__ == "models.image_classification.vanilla_vit"
 assert m.device in ("cuda", "cpu", "mps")
 assert TransformerEncoder is vitb200.detr.TransformerEncoder
+from models.object_detection.transformer import Transformer, TransformerDecoder
+assert TransformerDecoder is vitb200.detr.TransformerDecoder
+t = Transformer(d_model=256, nhead=4, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=512)   # the reference's own wrapper
+assert type(t.encoder) is vitb200.detr.TransformerEncoder and type(t.decoder) is vitb200.detr.TransformerDecoder
+assert "decoder.layers.0.multi_head_attn.in_proj_weight" in t.state_dict() and "decoder.norm.weight" in t.state_dict()
 from models.image_classification import deit   # imports timm.models.deit.VisionTransformerDistilled through the shim
 assert deit.VisionTransformerDistilled.__module__ == "vitb200.deit"
 from models.image_classification import t2t_vit

@@ -191,6 +191,45 @@ def test_cpe_module_keys_and_seed_parity():
             assert torch.equal(a[k], b[k]), (clsname, k)
 
 
+@pytest.mark.parametrize("name", ["detr_dec_d256.pt", "detr_dec_dropout_d256.pt"])
+def test_oracle_detr_decoder_matches_reference_golden(name):
+    """TransformerDecoder / TransformerDecoderLayer.forward_post (transformer.py:66-95, 138-156) against the live
+    reference run with the ``multihead_attn`` alias (tools/make_golden.py::decoder_case); with dropout the masks drawn inside the
+    reference are replayed — call order inside a layer: self-attention weights (site 3), dropout1 (0), cross-attention weights (4),
+    dropout2 (5), dropout (1), dropout3 (2)."""
+    gd = load(name)
+    d, h, ffn, L, Q, S, N, seed, p = gd["d_model"], gd["nhead"], gd["ffn"], gd["layers"], gd["Q"], gd["S"], gd["N"], gd["seed"], gd["p"]
+    drop = None
+    if p > 0:
+        drawn = _replayed_masks(seed + 2, gd["mask_shapes"], p)
+        assert len(drawn) == 6 * L and gd["mask_shapes"][0] == (N * h, Q, Q) and gd["mask_shapes"][2] == (N * h, Q, S)
+        masks = {}
+        for i in range(L):
+            for j, site in enumerate((3, 0, 4, 5, 1, 2)):
+                masks[(i, site)] = drawn[6 * i + j]
+        drop = O.ExplicitDropout(masks, p, p)
+    sd = {k: v.requires_grad_(True) for k, v in O.seeded_state_dict(O.detr_decoder_param_shapes(d, ffn, L), seed).items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    tgt = torch.randn(Q, N, d, generator=g, requires_grad=True)
+    memory = torch.randn(S, N, d, generator=g, requires_grad=True)
+    pos = torch.randn(S, N, d, generator=g, requires_grad=True)
+    qpos = torch.randn(Q, N, d, generator=g, requires_grad=True)
+    valid = torch.randint(S // 2, S + 1, (N,), generator=g)
+    kpm = torch.arange(S)[None, :] >= valid[:, None]
+    out = O.detr_decoder_forward(sd, tgt, memory, nhead=h, num_layers=L, memory_key_padding_mask=kpm, pos=pos, query_pos=qpos,
+                                 return_intermediate=gd["return_intermediate"], drop=drop)
+    gout = torch.randn(out.shape, generator=g)
+    out.backward(gout)
+    assert out.shape == gd["out"].shape and rel_l2(out, gd["out"]) < 1e-5
+    for t, key in ((tgt, "dtgt_norm"), (memory, "dmem_norm"), (pos, "dpos_norm"), (qpos, "dqpos_norm")):
+        assert abs(t.grad.norm().item() - gd[key]) < 1e-4 * gd[key], key
+    assert rel_l2(memory.grad[0], gd["dmem_row0"]) < 1e-4
+    for k, n in gd["grad_norms"].items():
+        assert abs(sd[k].grad.norm().item() - n) <= 1e-4 * max(n, 1e-6), k
+    for k, gr in gd["grads_small"].items():
+        assert rel_l2(sd[k].grad, gr) < 1e-4, k
+
+
 def test_known_answers_from_reference_init():
     """KAT-1/3/4: zero head => logits 0 and loss ln(C); key sets and parameter counts."""
     gd = load("kat.pt")
@@ -244,6 +283,12 @@ def test_deit_and_detr_module_keys():
     assert enc.layers[0] is not enc.layers[1] and enc.layers[0].linear1.weight is not enc.layers[1].linear1.weight
     with pytest.raises(RuntimeError):
         TransformerEncoderLayer(512, 8, 2048, 0.1, "swish", False)
+    from vitb200.detr import TransformerDecoder, TransformerDecoderLayer
+    dec = TransformerDecoder(TransformerDecoderLayer(512, 8, 2048, 0.1, "relu", False), 6, torch.nn.LayerNorm(512), return_intermediate=True)
+    sh = O.detr_decoder_param_shapes(512, 2048, 6)
+    assert set(sh) == set(dec.state_dict().keys())
+    assert all(tuple(dec.state_dict()[k].shape) == tuple(v) for k, v in sh.items())
+    assert dec.layers[0].multihead_attn is dec.layers[0].multi_head_attn
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree not present (GPU box)")

@@ -438,3 +438,334 @@ class TransformerEncoder(nn.Module):
             return _DetrFn.apply(eng, kpm, src, pos, *params)
         out, _ = eng.forward(src, pos, kpm, training=False)
         return out.clone()
+
+
+# ======================================================================================================================
+# DETR transformer DECODER: TransformerDecoderLayer / TransformerDecoder, transformer.py:66-95, 118-189.
+#
+# As written the reference layer cannot run: __init__ registers the cross-attention as ``multi_head_attn`` (transformer.py:122) while
+# forward_post / forward_pre call ``self.multihead_attn`` (:148, :172).  Decision: the state_dict key is the one
+# __init__ creates (``multi_head_attn.*``) and the forward is the one the code spells out with that attribute resolved — the oracle is
+# pinned against the live reference with exactly that alias added (tools/make_golden.py).  Post-norm layers (the reference default,
+# transformer.py:27-28); sequence-first tensors; the decoder's own norm and ``return_intermediate`` as at :78-95.
+# ======================================================================================================================
+DEC_ROLES = ("norm3_w", "norm3_b", "lin2_w", "lin2_b", "lin1_w", "lin1_b", "norm2_w", "norm2_b", "cout_w", "cout_b", "cin_w", "cin_b",
+             "norm1_w", "norm1_b", "out_w", "out_b", "in_w", "in_b")
+
+
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.multi_head_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        if activation not in ("relu", "gelu"):
+            raise RuntimeError(F"activation should be relu/gelu, not {activation}.")
+        self.activation_name = activation
+        self.normalize_before = normalize_before
+        self.d_model, self.nhead, self.dim_feedforward, self.dropout_p = d_model, nhead, dim_feedforward, dropout
+
+    @property
+    def multihead_attn(self):          # the name the reference's forward uses (transformer.py:148,172)
+        return self.multi_head_attn
+
+    def roles(self):
+        return {"norm1_w": self.norm1.weight, "norm1_b": self.norm1.bias, "norm2_w": self.norm2.weight, "norm2_b": self.norm2.bias,
+                "norm3_w": self.norm3.weight, "norm3_b": self.norm3.bias, "lin1_w": self.linear1.weight, "lin1_b": self.linear1.bias,
+                "lin2_w": self.linear2.weight, "lin2_b": self.linear2.bias,
+                "in_w": self.self_attn.in_proj_weight, "in_b": self.self_attn.in_proj_bias,
+                "out_w": self.self_attn.out_proj.weight, "out_b": self.self_attn.out_proj.bias,
+                "cin_w": self.multi_head_attn.in_proj_weight, "cin_b": self.multi_head_attn.in_proj_bias,
+                "cout_w": self.multi_head_attn.out_proj.weight, "cout_b": self.multi_head_attn.out_proj.bias}
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None,
+                query_pos=None):
+        dec = self.__dict__.get("_solo")
+        if dec is None:
+            dec = TransformerDecoder.__new__(TransformerDecoder)
+            nn.Module.__init__(dec)
+            dec.layers = nn.ModuleList([self])
+            dec.num_layers, dec.norm, dec.return_intermediate = 1, None, False
+            dec.__dict__["_engine"] = None
+            self.__dict__["_solo"] = dec
+        return dec(tgt, memory, tgt_mask, memory_mask, tgt_key_padding_mask, memory_key_padding_mask, pos, query_pos)[0]
+
+    __deepcopy__ = TransformerEncoderLayer.__deepcopy__
+
+
+class DetrDecoderEngine(DetrEngine):
+    """Kernel sequencing for L post-norm decoder layers: self-attention over the Q object queries, cross-attention of the queries
+    against the S-token encoder memory (vb_attention with S_kv), feed-forward; three LayerNorms; six dropout sites per layer
+    (0 = dropout1, 1 = dropout, 2 = dropout3, 3 = self-attention weights, 4 = cross-attention weights, 5 = dropout2)."""
+
+    def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5, return_intermediate=False):
+        assert d_model % 128 == 0 and d_model // nhead == 64, "vitb200 kernels need d_model % 128 == 0 and head_dim == 64"
+        self.D, self.H, self.F, self.L, self.eps = d_model, nhead, dim_feedforward, len(layers), eps
+        self.act, self.pre_norm, self.has_norm = activation, False, norm is not None
+        self.return_intermediate = bool(return_intermediate) and self.has_norm
+        self.p_drop, self._drop_counter = 0.0, None
+        self._order, seg = [], []
+        if self.has_norm:
+            self._order += [(("g", "norm_w"), norm.weight), (("g", "norm_b"), norm.bias)]
+            seg.append(2)
+        for li in range(self.L - 1, -1, -1):
+            r = layers[li].roles()
+            self._order += [((li, k), r[k]) for k in DEC_ROLES]
+            seg.append(len(DEC_ROLES))
+        self._layout(seg)
+
+    def workspace(self, Q, S, N, training):
+        key = (Q, S, N, training)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev, D, Fd, H = self.flat.device, self.D, self.F, self.H
+        Mq, Ms = Q * N, S * N
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *shape, dtype=bf: torch.empty(*shape, device=dev, dtype=dtype)
+        ws = {"Q": Q, "S": S, "N": N, "M": Mq, "Ms": Ms, "layer": []}
+        for _ in range(self.L):    # intermediates may be returned, so every layer keeps its own buffers in both modes
+            ws["layer"].append({
+                "x_bf": e(Mq, D), "qk_bf": e(Mq, D), "sqk": e(Mq, 2 * D), "sv": e(Mq, D), "so": e(Mq, D), "slse": e(N, H, Q, dtype=f32),
+                "u1": e(Mq, D, dtype=f32), "t1": e(Mq, D, dtype=f32), "t1_bf": e(Mq, D), "t1q_bf": e(Mq, D),
+                "mean1": e(Mq, dtype=f32), "rstd1": e(Mq, dtype=f32),
+                "cq": e(Mq, D), "ck": e(Ms, D), "cv": e(Ms, D), "co": e(Mq, D), "clse": e(N, H, Q, dtype=f32),
+                "u2": e(Mq, D, dtype=f32), "t2": e(Mq, D, dtype=f32), "x1_bf": e(Mq, D), "mean2": e(Mq, dtype=f32), "rstd2": e(Mq, dtype=f32),
+                "a": e(Mq, Fd), "u3": e(Mq, D, dtype=f32), "mean3": e(Mq, dtype=f32), "rstd3": e(Mq, dtype=f32),
+                "t3": e(Mq, D, dtype=f32)})
+        ws["m_bf"], ws["mk_bf"] = e(Ms, D), e(Ms, D)
+        n_out = self.L if self.return_intermediate else 1
+        ws["y"] = e(n_out, Mq, D, dtype=f32)
+        ws["meanf"], ws["rstdf"] = e(n_out, Mq, dtype=f32), e(n_out, Mq, dtype=f32)
+        if training:
+            for k in ("dT", "dU", "dU2", "dqpos"):
+                ws[k] = e(Mq, D, dtype=f32)
+            ws["dU_bf"], ws["dh"], ws["dh2"] = e(Mq, D), e(Mq, D), e(Mq, D)
+            ws["da"] = e(Mq, Fd)
+            ws["dsqk"], ws["dsv"], ws["dcq"] = e(Mq, 2 * D), e(Mq, D), e(Mq, D)
+            ws["dck"], ws["dcv"], ws["dmk"], ws["dmv"] = e(Ms, D), e(Ms, D), e(Ms, D), e(Ms, D)
+            ws["delta"] = e(N, H, Q, dtype=f32)
+            ws["dmem"], ws["dpos"] = e(Ms, D, dtype=f32), e(Ms, D, dtype=f32)
+        self._ws[key] = ws
+        return ws
+
+    def forward(self, tgt, memory, mem_kpm, pos, query_pos, training):
+        self.ensure_bound()
+        Q, N, D = tgt.shape
+        S = memory.shape[0]
+        ws = self.workspace(Q, S, N, training)
+        self.refresh_bf16()
+        Mq, Ms, H = ws["M"], ws["Ms"], self.H
+        t0 = tgt.contiguous().float().view(Mq, D)
+        mem = memory.contiguous().float().view(Ms, D)
+        pos2 = pos.contiguous().float().view(Ms, D) if pos is not None else None
+        qpos = query_pos.contiguous().float().view(Mq, D) if query_pos is not None else None
+        ws["has_pos"], ws["has_qpos"], ws["kpm"] = pos2 is not None, qpos is not None, mem_kpm
+        pd = ws["p_drop"] = float(self.p_drop)
+        if pd > 0:
+            self._begin_dropout(ws)
+        site = self.drop_site
+        seed = ws.get("drop_seed")
+        ops.add_cast_bf16(mem, None, ws["m_bf"])                     # value operand of every layer's cross-attention
+        ops.add_cast_bf16(mem, pos2, ws["mk_bf"])                    # key operand: memory + pos (transformer.py:146)
+        b0 = ws["layer"][0]
+        ops.add_cast_bf16(t0, None, b0["x_bf"])
+        ops.add_cast_bf16(t0, qpos, b0["qk_bf"])
+        x = t0
+        for li in range(self.L):
+            buf = ws["layer"][li]
+            # ---- self-attention over the queries: q = k = tgt + query_pos, v = tgt (transformer.py:142-143) ----
+            in_w, in_b = self.w((li, "in_w")), self.f((li, "in_b"))
+            ops.gemm(buf["qk_bf"], in_w[:2 * D], buf["sqk"], bias=in_b[:2 * D])
+            ops.gemm(buf["x_bf"], in_w[2 * D:], buf["sv"], bias=in_b[2 * D:])
+            ops.attention_fwd(buf["sqk"][:, :D], buf["sqk"][:, D:], buf["sv"], buf["so"], buf["slse"] if training else None, B=N, H=H, S=Q,
+                              tok_stride=N, batch_stride=1, dropout=(pd, seed, site(li, 3)) if pd > 0 else None)
+            self._linear_residual(ws, buf["so"], "out_w", "out_b", li, 0, x, buf["u1"], pd)                       # :144
+            ops.layernorm_fwd(buf["u1"], self.f((li, "norm1_w")), self.f((li, "norm1_b")), self.eps, y_f32=buf["t1"], y_bf16=buf["t1_bf"],
+                              mean=buf["mean1"], rstd=buf["rstd1"], add=qpos, y2_bf16=buf["t1q_bf"] if qpos is not None else None)
+            # ---- cross-attention: query = tgt + query_pos, key = memory + pos, value = memory (:145-147) ----
+            cw, cb = self.w((li, "cin_w")), self.f((li, "cin_b"))
+            ops.gemm(buf["t1q_bf"] if qpos is not None else buf["t1_bf"], cw[:D], buf["cq"], bias=cb[:D])
+            ops.gemm(ws["mk_bf"], cw[D:2 * D], buf["ck"], bias=cb[D:2 * D])
+            ops.gemm(ws["m_bf"], cw[2 * D:], buf["cv"], bias=cb[2 * D:])
+            ops.attention_fwd(buf["cq"], buf["ck"], buf["cv"], buf["co"], buf["clse"] if training else None, B=N, H=H, S=Q, S_kv=S,
+                              tok_stride=N, batch_stride=1, key_padding_mask=mem_kpm,
+                              dropout=(pd, seed, site(li, 4)) if pd > 0 else None)
+            self._linear_residual(ws, buf["co"], "cout_w", "cout_b", li, 5, buf["t1"], buf["u2"], pd)             # :150
+            ops.layernorm_fwd(buf["u2"], self.f((li, "norm2_w")), self.f((li, "norm2_b")), self.eps, y_f32=buf["t2"], y_bf16=buf["x1_bf"],
+                              mean=buf["mean2"], rstd=buf["rstd2"])
+            # ---- feed-forward (:152-154) ----
+            act_out = self._ffn_fwd(ws, buf, li, pd)
+            self._linear_residual(ws, act_out, "lin2_w", "lin2_b", li, 2, buf["t2"], buf["u3"], pd)
+            nbuf = ws["layer"][li + 1] if li + 1 < self.L else None
+            ops.layernorm_fwd(buf["u3"], self.f((li, "norm3_w")), self.f((li, "norm3_b")), self.eps, y_f32=buf["t3"],
+                              y_bf16=nbuf["x_bf"] if nbuf else None, mean=buf["mean3"], rstd=buf["rstd3"],
+                              add=qpos if nbuf else None, y2_bf16=nbuf["qk_bf"] if (nbuf and qpos is not None) else None)
+            if nbuf and qpos is None:
+                ops.add_cast_bf16(buf["t3"], None, nbuf["qk_bf"])
+            x = buf["t3"]
+        if not self.has_norm:
+            return x.view(1, Q, N, D), ws                            # output.unsqueeze(0) (:95)
+        outs = range(self.L) if self.return_intermediate else [self.L - 1]
+        for j, li in enumerate(outs):                                # self.norm(output) per returned layer (:83-88)
+            ops.layernorm_fwd(ws["layer"][li]["t3"], self.f(("g", "norm_w")), self.f(("g", "norm_b")), self.eps, y_f32=ws["y"][j],
+                              mean=ws["meanf"][j], rstd=ws["rstdf"][j])
+        return ws["y"].view(-1, Q, N, D), ws
+
+    def backward(self, ws, grad_out):
+        self.prepare_grads()
+        Q, S, N, Mq, Ms, D, H, L = ws["Q"], ws["S"], ws["N"], ws["M"], ws["Ms"], self.D, self.H, self.L
+        g_all = grad_out.contiguous().float().view(-1, Mq, D)
+        dT, dU, dU2, dU_bf, dh, dh2 = ws["dT"], ws["dU"], ws["dU2"], ws["dU_bf"], ws["dh"], ws["dh2"]
+        dmem, dpos, dqpos = ws["dmem"], ws["dpos"], ws["dqpos"]
+        dmem.zero_()
+        dpos.zero_()
+        dqpos.zero_()
+        pd, kpm = ws["p_drop"], ws["kpm"]
+        seed = ws.get("drop_seed")
+        site = self.drop_site
+        drelu = dict(drelu_scale=1.0 / (1.0 - pd)) if (pd > 0 and self.act == "relu") else {}
+        fuse = pd == 0
+        seg = 0
+        have_next = False     # dT holds the gradient that layer li + 1 sends to this layer's output
+        for li in range(L - 1, -1, -1):
+            buf = ws["layer"][li]
+            # ---- gradient of this layer's output t3: from the next layer and / or through the decoder norm ----
+            if self.has_norm and (self.return_intermediate or li == L - 1):
+                j = li if self.return_intermediate else 0
+                ops.layernorm_bwd(g_all[j], buf["t3"], ws["meanf"][j], ws["rstdf"][j], self.f(("g", "norm_w")), dres=dT if have_next else None,
+                                  dx=dT, dgamma=self.gview(("g", "norm_w")), dbeta=self.gview(("g", "norm_b")))
+                if not self.return_intermediate:
+                    self._seg_done(0)
+            elif not self.has_norm and li == L - 1:
+                dT.copy_(g_all[0])
+            # ---- feed-forward: t3 = norm3(u3), u3 = t2 + dropout3(linear2(dropout(act(linear1(t2))))) ----
+            ops.layernorm_bwd(dT, buf["u3"], buf["mean3"], buf["rstd3"], self.f((li, "norm3_w")), dx=dU, dx_bf16=dU_bf if fuse else None,
+                              dgamma=self.gview((li, "norm3_w")), dbeta=self.gview((li, "norm3_b")),
+                              dx_colsum=self.gview((li, "lin2_b")) if fuse else None)
+            if pd > 0:
+                self._masked_operand(ws, dU, dU_bf, li, 2, (li, "lin2_b"))
+            act_out = buf["a"] if self.act == "relu" else buf["g"]
+            self._wgrad(dU_bf, act_out, (li, "lin2_w"))
+            ops.gemm(dU_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU if self.act == "relu" else ops.EPI_DGELU,
+                     aux=buf["a"], **drelu)
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
+            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
+            # ---- cross-attention: t2 = norm2(u2), u2 = t1 + dropout2(out_proj(attn(t1 + qpos, memory + pos, memory))) ----
+            ops.layernorm_bwd(dU, buf["u2"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dx=dU2, dx_bf16=dU_bf if fuse else None,
+                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")),
+                              dx_colsum=self.gview((li, "cout_b")) if fuse else None, dy_add=dh)
+            if pd > 0:
+                self._masked_operand(ws, dU2, dU_bf, li, 5, (li, "cout_b"))
+            self._wgrad(dU_bf, buf["co"], (li, "cout_w"))
+            ops.gemm(dU_bf, self.w((li, "cout_w")), dh, b_major=1)                                   # dO of the cross-attention
+            ops.attention_bwd(buf["cq"], buf["ck"], buf["cv"], buf["co"], buf["clse"], dh, ws["dcq"], ws["dck"], ws["dcv"], ws["delta"],
+                              B=N, H=H, S=Q, S_kv=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm,
+                              dropout=(pd, seed, site(li, 4)) if pd > 0 else None)
+            cw, gcb = self.w((li, "cin_w")), self.gview((li, "cin_b"))
+            self._wgrad(ws["dcq"], buf["t1q_bf"] if ws["has_qpos"] else buf["t1_bf"], (li, "cin_w"), rows=(0, D))
+            self._wgrad(ws["dck"], ws["mk_bf"], (li, "cin_w"), rows=(D, 2 * D))
+            self._wgrad(ws["dcv"], ws["m_bf"], (li, "cin_w"), rows=(2 * D, 3 * D))
+            ops.colsum_bf16(ws["dcq"], gcb[:D])
+            ops.colsum_bf16(ws["dck"], gcb[D:2 * D])
+            ops.colsum_bf16(ws["dcv"], gcb[2 * D:])
+            ops.gemm(ws["dcq"], cw[:D], dh, b_major=1)                                               # d(t1 + query_pos)
+            ops.gemm(ws["dck"], cw[D:2 * D], ws["dmk"], b_major=1)                                   # d(memory + pos)
+            ops.gemm(ws["dcv"], cw[2 * D:], ws["dmv"], b_major=1)                                    # d memory through the values
+            ops.add3(dmem, ws["dmk"], ws["dmv"], dmem, dpos)                                         # d memory += ..; d pos += dmk
+            ops.add3(dqpos, dh, None, dqpos, None)
+            # ---- self-attention: t1 = norm1(u1), u1 = t0 + dropout1(out_proj(attn(t0 + qpos, t0 + qpos, t0))) ----
+            ops.layernorm_bwd(dU2, buf["u1"], buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dx=dU, dx_bf16=dU_bf if fuse else None,
+                              dgamma=self.gview((li, "norm1_w")), dbeta=self.gview((li, "norm1_b")),
+                              dx_colsum=self.gview((li, "out_b")) if fuse else None, dy_add=dh)
+            if pd > 0:
+                self._masked_operand(ws, dU, dU_bf, li, 0, (li, "out_b"))
+            self._wgrad(dU_bf, buf["so"], (li, "out_w"))
+            ops.gemm(dU_bf, self.w((li, "out_w")), dh, b_major=1)                                    # dO of the self-attention
+            dsqk, dsv = ws["dsqk"], ws["dsv"]
+            ops.attention_bwd(buf["sqk"][:, :D], buf["sqk"][:, D:], buf["sv"], buf["so"], buf["slse"], dh, dsqk[:, :D], dsqk[:, D:], dsv,
+                              ws["delta"], B=N, H=H, S=Q, tok_stride=N, batch_stride=1, dropout=(pd, seed, site(li, 3)) if pd > 0 else None)
+            in_w, gb = self.w((li, "in_w")), self.gview((li, "in_b"))
+            self._wgrad(dsqk, buf["qk_bf"], (li, "in_w"), rows=(0, 2 * D))
+            self._wgrad(dsv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
+            ops.colsum_bf16(dsqk, gb[:2 * D])
+            ops.colsum_bf16(dsv, gb[2 * D:])
+            ops.gemm(dsqk, in_w[:2 * D], dh, b_major=1)                                              # d(t0 + query_pos) through q and k
+            ops.gemm(dsv, in_w[2 * D:], dh2, b_major=1)                                              # d t0 through v
+            ops.add3(dU, dh, dh2, dT, dqpos)                                                         # d t0 = dU + dh + dh2; d qpos += dh
+            have_next = True
+            if not self.return_intermediate:
+                self._seg_done(seg + (1 if self.has_norm else 0))
+            seg += 1
+        if self.return_intermediate:     # the shared norm's gradient is complete only now: release the segments in order
+            for i in range(L + 1):
+                self._seg_done(i)
+        return (dT.view(Q, N, D), dmem.view(S, N, D), dpos.view(S, N, D) if ws["has_pos"] else None,
+                dqpos.view(Q, N, D) if ws["has_qpos"] else None)
+
+
+class _DetrDecFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, kpm, tgt, memory, pos, query_pos, *params):
+        out, ws = engine.forward(tgt, memory, kpm, pos, query_pos, training=True)
+        ctx.engine, ctx.ws, ctx.n_params = engine, ws, len(params)
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dt, dm, dp, dq = ctx.engine.backward(ctx.ws, grad_out)
+        need = ctx.needs_input_grad
+        return (None, None, dt.clone() if need[2] else None, dm.clone() if need[3] else None,
+                dp.clone() if (dp is not None and need[4]) else None, dq.clone() if (dq is not None and need[5]) else None) + (None,) * ctx.n_params
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, decoder_layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(decoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.return_intermediate = return_intermediate
+        self.__dict__["_engine"] = None
+
+    def _get_engine(self):
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            l0 = self.layers[0]
+            if l0.normalize_before:
+                raise NotImplementedError("vitb200: the DETR decoder is implemented for post-norm layers (normalize_before=False, the "
+                                          "reference default, transformer.py:27-28)")
+            if self.return_intermediate and self.norm is None:
+                raise TypeError("return_intermediate needs the decoder norm (transformer.py:85 calls self.norm unconditionally)")
+            eng = DetrDecoderEngine(list(self.layers), self.norm, l0.d_model, l0.nhead, l0.dim_feedforward, l0.activation_name,
+                                    eps=float(l0.norm1.eps), return_intermediate=self.return_intermediate)
+            self.__dict__["_engine"] = eng
+        return eng
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None, memory_key_padding_mask=None, pos=None,
+                query_pos=None):
+        if tgt_mask is not None or memory_mask is not None or tgt_key_padding_mask is not None:
+            raise NotImplementedError("vitb200: tgt_mask / memory_mask / tgt_key_padding_mask are not supported; DETR passes None for all "
+                                      "three (transformer.py:60)")
+        eng = self._get_engine()
+        eng.p_drop = float(self.layers[0].dropout_p) if self.training else 0.0
+        kpm = None
+        if memory_key_padding_mask is not None:
+            kpm = memory_key_padding_mask.to(device=tgt.device, dtype=torch.uint8).contiguous()
+        params = [p for _, p in eng._order]
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or tgt.requires_grad or memory.requires_grad
+                                                  or (pos is not None and pos.requires_grad)
+                                                  or (query_pos is not None and query_pos.requires_grad))
+        if needs_grad:
+            return _DetrDecFn.apply(eng, kpm, tgt, memory, pos, query_pos, *params)
+        out, _ = eng.forward(tgt, memory, kpm, pos, query_pos, training=False)
+        return out.clone()

@@ -9,6 +9,7 @@
 What is rebound:
   models.image_classification.vanilla_vit.{ViT, Encoder, EncoderBlock, MLPBlock, MLP}   (vanilla_vit.py:22-215)
   models.object_detection.transformer.{TransformerEncoderLayer, TransformerEncoder}      (transformer.py:98-115,192-247)
+  models.object_detection.transformer.{TransformerDecoderLayer, TransformerDecoder}      (transformer.py:66-95,118-189)
   timm.models.deit.VisionTransformerDistilled (a shim module, since timm is what deit.py:4 imports)
   models.image_classification.{cpe_vit.CPEViT, cpvt.CPVT, cpvt_gap.CPVTGAP} (+ their ConditionalPositionalEncoding)
 The rebound ``ViT`` subclasses the reference's ``BaseTransformer`` (base.py:12) and borrows the reference's
@@ -66,6 +67,9 @@ def install(reference_root, stub_missing=True):
     ref_vit.MLP = our_vit.MLP
     ref_tr.TransformerEncoderLayer = our_detr.TransformerEncoderLayer
     ref_tr.TransformerEncoder = our_detr.TransformerEncoder
+    # the decoder: the reference layer cannot run as written (transformer.py:122 vs :148); ours resolves the name
+    ref_tr.TransformerDecoderLayer = our_detr.TransformerDecoderLayer
+    ref_tr.TransformerDecoder = our_detr.TransformerDecoder
 
     # timm shim for models/image_classification/deit.py:4-5
     have_timm = True
