@@ -445,8 +445,8 @@ class TransformerEncoder(nn.Module):
 #
 # As written the reference layer cannot run: __init__ registers the cross-attention as ``multi_head_attn`` (transformer.py:122) while
 # forward_post / forward_pre call ``self.multihead_attn`` (:148, :172).  Decision: the state_dict key is the one
-# __init__ creates (``multi_head_attn.*``) and the forward is the one the code spells out with that attribute resolved — the oracle is
-# pinned against the live reference with exactly that alias added (tools/make_golden.py).  Post-norm layers (the reference default,
+# __init__ creates (``multi_head_attn.*``) and the forward is the one the code spells out with that attribute resolved — the parity fixtures
+# come from the live reference run with exactly that alias added (tools/make_golden.py).  Post-norm layers (the reference default,
 # transformer.py:27-28); sequence-first tensors; the decoder's own norm and ``return_intermediate`` as at :78-95.
 # ======================================================================================================================
 DEC_ROLES = ("norm3_w", "norm3_b", "lin2_w", "lin2_b", "lin1_w", "lin1_b", "norm2_w", "norm2_b", "cout_w", "cout_b", "cin_w", "cin_b",
