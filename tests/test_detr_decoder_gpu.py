@@ -109,3 +109,39 @@ def test_decoder_layer_standalone_and_errors():
         TransformerDecoder(TransformerDecoderLayer(256, 4, 512, 0.0, "relu", True), 1).cuda()(t, m)
     with pytest.raises(NotImplementedError):
         TransformerDecoder(layer, 1).cuda()(t, m, tgt_mask=torch.zeros(10, 10, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_detr_autograd_graph_replay_matches_eager(monkeypatch):
+    """Encoder and decoder autograd nodes replayed from CUDA graphs (FlatParams.graphed) against the eager kernel sequence: same kernels,
+    same buffers; fp32 split-K / atomic sums are order-dependent, hence 1e-4 rather than bit equality."""
+    from vitb200.detr import TransformerDecoder, TransformerDecoderLayer, TransformerEncoder, TransformerEncoderLayer
+
+    def run(mode):
+        monkeypatch.setenv("VITB200_AUTOGRAD_GRAPH", mode)
+        torch.manual_seed(5)
+        enc = TransformerEncoder(TransformerEncoderLayer(256, 4, 512, 0.0, "relu", False), 2).cuda().train()
+        dec = TransformerDecoder(TransformerDecoderLayer(256, 4, 512, 0.0, "relu", False), 2, torch.nn.LayerNorm(256), True).cuda().train()
+        opt = torch.optim.SGD(list(enc.parameters()) + list(dec.parameters()), lr=0.01)
+        g = torch.Generator().manual_seed(6)
+        qpos = torch.randn(30, 2, 256, generator=g).cuda().requires_grad_(True)
+        losses = []
+        for _ in range(4):
+            src, pos = torch.randn(90, 2, 256, generator=g).cuda(), torch.randn(90, 2, 256, generator=g).cuda()
+            kpm = (torch.arange(90)[None, :] >= torch.tensor([[90], [70]])).cuda()
+            opt.zero_grad()
+            mem = enc(src, src_key_padding_mask=kpm, pos=pos)
+            hs = dec(torch.zeros_like(qpos), mem, memory_key_padding_mask=kpm, pos=pos, query_pos=qpos)
+            loss = hs.float().square().mean()
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        captured = {k[0][0] for e in (enc, dec) for k, v in e._get_engine().__dict__.get("_train_graphs", {}).items() if isinstance(v, tuple)}
+        return losses, [p.detach().clone() for p in list(enc.parameters()) + list(dec.parameters())], qpos.grad.clone(), captured
+    le, pe, qe, ce = run("0")
+    lg, pg, qg, cg = run("1")
+    assert ce == set() and cg == {"enc_fwd", "enc_bwd", "dec_fwd", "dec_bwd"}, (ce, cg)
+    assert all(abs(a - b) <= 1e-4 * max(1.0, abs(a)) for a, b in zip(le, lg)), (le, lg)
+    # zero-initialised biases whose gradient is rounding noise (the key bias: exactly zero in exact arithmetic) need an absolute floor
+    assert all((a - b).norm().item() <= 1e-4 * a.norm().item() + 1e-6 * a.numel() ** 0.5 for a, b in zip(pe, pg))
+    assert rel_l2(qg, qe) < 2e-2      # a bf16-path gradient after four steps of (order-dependent) fp32 sums: bf16 resolution, not 1e-4

@@ -186,3 +186,46 @@ def test_small_batch_inference_graph_replay_matches_eager(monkeypatch):
     with torch.no_grad():
         again = m(xs[0])
     assert torch.equal(again, shifted)
+
+
+def _loop(monkeypatch, mode, steps=5, p=0.0):
+    """The reference's loop body (base.py:53-57) with torch.optim.SGD; returns losses and the final parameters."""
+    from vitb200.vit import ViT
+    monkeypatch.setenv("VITB200_AUTOGRAD_GRAPH", mode)
+    torch.manual_seed(11)
+    m = ViT(32, 4, 2, 4, 256, 512, p, p, 10)
+    with torch.no_grad():
+        m.heads.head.weight.normal_(std=0.05)
+    m = m.cuda().train()
+    init = [p_.detach().clone() for p_ in m.parameters()]
+    opt = torch.optim.SGD(m.parameters(), lr=0.002)
+    g = torch.Generator().manual_seed(12)
+    losses = []
+    for _ in range(steps):
+        x, y = torch.randn(8, 3, 32, 32, generator=g).cuda(), torch.randint(0, 10, (8,), generator=g).cuda()
+        opt.zero_grad()                      # set_to_none=True: p.grad is rebuilt as a view of the flat buffer every step
+        loss = torch.nn.functional.cross_entropy(m(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    return losses, [p_.detach().clone() for p_ in m.parameters()], m, init
+
+
+@pytest.mark.gpu
+def test_autograd_path_graph_replay_matches_eager(monkeypatch):
+    """Forward and backward of the autograd node are replayed from CUDA graphs for launch-bound sizes (engine.forward_train /
+    backward_train): the same kernels on the same buffers as the eager sequence."""
+    le, pe, _, init = _loop(monkeypatch, "0")
+    lg, pg, m, _ = _loop(monkeypatch, "1")
+    # same kernels on the same buffers; split-K reduce-adds and atomic column sums make fp32 sums order-dependent, hence 1e-4 not 0
+    assert all(abs(a - b) <= 1e-3 * max(1.0, abs(a)) for a, b in zip(le, lg)), (le, lg)
+    # the accumulated UPDATES agree to bf16-path resolution (the two trajectories see order-dependent fp32 sums; the key bias, whose
+    # gradient is exactly zero in exact arithmetic, is pure rounding noise and gets an absolute floor)
+    bad = [(n, (a - b).norm().item(), (a - i).norm().item()) for (n, _), a, b, i in zip(m.named_parameters(), pe, pg, init)
+           if (a - b).norm().item() > 2e-2 * (a - i).norm().item() + 1e-7 * a.numel() ** 0.5]
+    assert not bad, bad
+    kinds = {k[0] for k, v in m._get_engine()._train_graphs.items() if isinstance(v, tuple)}
+    assert kinds == {"fwd", "bwd"}, kinds
+    # with dropout every replay draws new masks (the seed counter is bumped inside the graph)
+    ld = _loop(monkeypatch, "1", steps=4, p=0.2)[0]
+    assert len({round(v, 6) for v in ld}) == 4

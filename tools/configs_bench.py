@@ -71,7 +71,56 @@ def detr_encoder():
     print(f"cfg5 DETR encoder training S=1050 batch {N}: {ms:7.2f} ms/step {N / ms * 1e3:9.1f} images/s  ({N / ms * 159.55:.0f} TFLOP/s)", flush=True)
 
 
-for f in (deit_s, vit_l_inference, detr_encoder):
+def tiny_reference_loop():
+    """cfg1's model (utils/args.py:6-7: 32x32, patch 4, 7 layers, 256 wide) driven the way the reference's own loop drives it
+    (base.py:51-57: zero_grad / model(images) / CrossEntropyLoss / backward / torch.optim.Adam), with and without the CUDA-graph replay
+    of the autograd node."""
+    from vitb200.vit import ViT
+    B = 256
+    for mode in ("0", "1"):
+        os.environ["VITB200_AUTOGRAD_GRAPH"] = mode
+        m = ViT(32, 4, 7, 4, 256, 512, 0.1, 0.1, 10).to(dev).train()
+        with torch.no_grad():
+            m.heads.head.weight.normal_(std=0.02)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+        crit = torch.nn.CrossEntropyLoss()
+        x, y = torch.randn(B, 3, 32, 32, device=dev), torch.randint(0, 10, (B,), device=dev)
+
+        def step():
+            opt.zero_grad()
+            loss = crit(m(x), y)
+            loss.backward()
+            opt.step()
+        ms = timed(step, warm=4, iters=20)
+        print(f"cfg1 tiny ViT (CIFAR shape, dropout 0.1) reference-style loop, batch {B}, autograd graphs {'on ' if mode == '1' else 'off'}: "
+              f"{ms:6.2f} ms/step {B / ms * 1e3:9.1f} images/s", flush=True)
+    os.environ.pop("VITB200_AUTOGRAD_GRAPH", None)
+
+
+def detr_decoder():
+    from vitb200.detr import TransformerDecoder, TransformerDecoderLayer
+    Q, S, N = 100, 1050, 4
+    dec = TransformerDecoder(TransformerDecoderLayer(512, 8, 2048, 0.0, "relu", False), 6, torch.nn.LayerNorm(512), return_intermediate=True).to(dev).train()
+    tgt = torch.zeros(Q, N, 512, device=dev)
+    mem = torch.randn(S, N, 512, device=dev, requires_grad=True)
+    pos, qpos = torch.randn(S, N, 512, device=dev), torch.randn(Q, N, 512, device=dev, requires_grad=True)
+    mask = torch.zeros(N, S, dtype=torch.bool, device=dev)
+    mask[:, 900:] = True
+    opt = torch.optim.Adam(dec.parameters(), lr=1e-4)
+
+    def step():
+        opt.zero_grad()
+        out = dec(tgt, mem, memory_key_padding_mask=mask, pos=pos, query_pos=qpos)
+        out.float().square().mean().backward()
+        opt.step()
+    ms = timed(step)
+    print(f"DETR decoder training Q=100 S=1050 batch {N} (6 layers, intermediates): {ms:7.2f} ms/step {N / ms * 1e3:9.1f} images/s", flush=True)
+
+
+only = sys.argv[1:]
+for f in (tiny_reference_loop, deit_s, vit_l_inference, detr_encoder, detr_decoder):
+    if only and f.__name__ not in only:
+        continue
     try:
         f()
     except Exception as e:  # keep going: each config is independent

@@ -396,13 +396,22 @@ class DetrEngine(FlatParams):
 class _DetrFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, kpm, src, pos, *params):
-        out, ws = engine.forward(src, pos, kpm, training=True)
+        engine.ensure_bound()
+        S, N = src.shape[0], src.shape[1]
+
+        def fresh():
+            engine.bf16_fresh = False     # a captured forward must contain the fp32 -> bf16 parameter cast
+        out, ws = engine.graphed(("enc_fwd", float(engine.p_drop)), S * N, [src, pos, kpm],
+                                 lambda s_, p_, k_: engine.forward(s_, p_, k_, training=True), before_capture=fresh)
         ctx.engine, ctx.ws, ctx.n_params, ctx.has_pos = engine, ws, len(params), pos is not None
         return out.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        dsrc, dpos = ctx.engine.backward(ctx.ws, grad_out)
+        eng, ws = ctx.engine, ctx.ws
+        eng.prepare_grads()               # p.grad bookkeeping stays outside a captured backward
+        dsrc, dpos = eng.graphed(("enc_bwd", ws["S"], ws["N"], ws["p_drop"], ws["pos"] is not None, ws["kpm"] is not None), ws["M"],
+                                 [grad_out], lambda g_: eng.backward(ws, g_))
         return (None, None, dsrc.clone(), dpos.clone() if (ctx.has_pos and ctx.needs_input_grad[3]) else None) + (None,) * ctx.n_params
 
 
@@ -716,13 +725,22 @@ class DetrDecoderEngine(DetrEngine):
 class _DetrDecFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, kpm, tgt, memory, pos, query_pos, *params):
-        out, ws = engine.forward(tgt, memory, kpm, pos, query_pos, training=True)
+        engine.ensure_bound()
+
+        def fresh():
+            engine.bf16_fresh = False
+        out, ws = engine.graphed(("dec_fwd", float(engine.p_drop)), (tgt.shape[0] + memory.shape[0]) * tgt.shape[1],
+                                 [tgt, memory, kpm, pos, query_pos],
+                                 lambda t_, m_, k_, p_, q_: engine.forward(t_, m_, k_, p_, q_, training=True), before_capture=fresh)
         ctx.engine, ctx.ws, ctx.n_params = engine, ws, len(params)
         return out.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        dt, dm, dp, dq = ctx.engine.backward(ctx.ws, grad_out)
+        eng, ws = ctx.engine, ctx.ws
+        eng.prepare_grads()
+        dt, dm, dp, dq = eng.graphed(("dec_bwd", ws["Q"], ws["S"], ws["N"], ws["p_drop"], ws["has_pos"], ws["has_qpos"], ws["kpm"] is not None),
+                                     ws["M"] + ws["Ms"], [grad_out], lambda g_: eng.backward(ws, g_))
         need = ctx.needs_input_grad
         return (None, None, dt.clone() if need[2] else None, dm.clone() if need[3] else None,
                 dp.clone() if (dp is not None and need[4]) else None, dq.clone() if (dq is not None and need[5]) else None) + (None,) * ctx.n_params

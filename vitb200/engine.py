@@ -85,7 +85,8 @@ class FlatParams:
         for key, p in self._order:
             p.grad = None
         self._ws.clear()
-        self.__dict__.setdefault("_infer_graphs", {}).clear()   # captured inference graphs hold the old buffers' addresses
+        self.__dict__.setdefault("_infer_graphs", {}).clear()   # captured graphs hold the old buffers' addresses
+        self.__dict__.setdefault("_train_graphs", {}).clear()
         self.bf16_fresh = False
         self._sms = torch.cuda.get_device_properties(device).multi_processor_count
 
@@ -147,6 +148,105 @@ class FlatParams:
         static_in.copy_(x)
         graph.replay()
         return outs
+
+    # ------------------------------------------------------------------ launch-bound training through autograd -------
+    # The reference's own loops (base.py:51-57) drive the model through autograd: forward and backward are two calls with the loss in
+    # between, so the Trainer's whole-step graph does not apply.  For small problems (the repo's CIFAR configs: 65 tokens x 256 dims)
+    # those calls are launch-bound, so each is replayed from its own CUDA graph: first call per shape eager, second captured, later
+    # calls copy the batch / the output gradients into static buffers and replay.  Off when a data-parallel reducer is attached (its
+    # collectives are issued from Python between kernels).  VITB200_AUTOGRAD_GRAPH=0 / 1 forces it off / on for every size.
+    AUTOGRAD_GRAPH_MAX_TOKENS = int(os.environ.get("VITB200_AUTOGRAD_GRAPH_MAX_TOKENS", "20000"))
+
+    def _autograd_graph_ok(self, tokens):
+        mode = os.environ.get("VITB200_AUTOGRAD_GRAPH", "auto")
+        if mode == "0" or self.grad_segment_hook is not None or torch.cuda.is_current_stream_capturing():
+            return False
+        return mode == "1" or tokens <= self.AUTOGRAD_GRAPH_MAX_TOKENS
+
+    def graphed(self, key, tokens, inputs, fn, before_capture=None):
+        """``fn(*inputs)`` — eagerly the first time a (key, input shapes) combination is seen, captured into a CUDA graph the second
+        time, replayed afterwards with the inputs copied into the graph's static buffers.  ``inputs`` are tensors or None; the result of
+        ``fn`` must only reference persistent workspace buffers.  Falls back to the eager call when graphs do not apply."""
+        if not self._autograd_graph_ok(tokens) or any(t is not None and not t.is_cuda for t in inputs):
+            return fn(*inputs)
+        graphs = self.__dict__.setdefault("_train_graphs", {})
+        full_key = (key, tuple(None if t is None else (tuple(t.shape), t.dtype) for t in inputs))
+        ent = graphs.get(full_key)
+        if ent is None:
+            graphs[full_key] = "warm"
+            return fn(*inputs)
+        if ent == "warm":
+            static = [None if t is None else torch.empty(t.shape, device=t.device, dtype=t.dtype) for t in inputs]
+            for st, t in zip(static, inputs):
+                if t is not None:
+                    st.copy_(t)
+            torch.cuda.synchronize(self.flat.device)
+            if before_capture is not None:
+                before_capture()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                res = fn(*static)
+            ent = graphs[full_key] = (graph, static, res)
+        graph, static, res = ent
+        for st, t in zip(static, inputs):
+            if t is not None:
+                st.copy_(t)
+        graph.replay()
+        return res
+
+    def forward_train(self, x, *, want):
+        """forward(x, training=True, want=want) for the autograd node; returns (outputs, ws)."""
+        self.ensure_bound()
+        if not (x.is_cuda and self._autograd_graph_ok(x.shape[0] * self.S)):
+            return self.forward(x, training=True, want=want)
+        graphs = self.__dict__.setdefault("_train_graphs", {})
+        key = ("fwd", tuple(x.shape), want, float(self.p_drop), float(self.p_attn))
+        ent = graphs.get(key)
+        if ent is None:
+            graphs[key] = "warm"
+            return self.forward(x, training=True, want=want)
+        if ent == "warm":
+            static_in = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+            static_in.copy_(x)
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            self.bf16_fresh = False      # the captured forward must contain the fp32 -> bf16 parameter cast
+            with torch.cuda.graph(graph):
+                outs, ws = self.forward(static_in, training=True, want=want)
+            ent = graphs[key] = (graph, static_in, outs, ws)
+        graph, static_in, outs, ws = ent
+        static_in.copy_(x)
+        graph.replay()
+        self.bf16_fresh = False          # the replay cast the parameters itself; a pending "fresh" mark must not outlive it
+        return outs, ws
+
+    def backward_train(self, ws, grads, *, want):
+        """backward(ws, grads, want=want) for the autograd node (graph replay under the same conditions as forward_train)."""
+        if not self._autograd_graph_ok(ws["M"]) or any(g is not None and not g.is_cuda for g in grads):
+            return self.backward(ws, grads, want=want)
+        graphs = self.__dict__.setdefault("_train_graphs", {})
+        key = ("bwd", ws["B"], want, tuple(None if g is None else tuple(g.shape) for g in grads), ws.get("p_drop", 0.0), ws.get("p_attn", 0.0))
+        ent = graphs.get(key)
+        if ent is None:
+            graphs[key] = "warm"
+            return self.backward(ws, grads, want=want)
+        self.prepare_grads()             # p.grad bookkeeping (and the zeroing it may need) stays outside the graph
+        if ent == "warm":
+            static_g = [None if g is None else torch.empty(g.shape, device=g.device, dtype=torch.float32) for g in grads]
+            for sg, g in zip(static_g, grads):
+                if g is not None:
+                    sg.copy_(g)
+            torch.cuda.synchronize(self.flat.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                res = self.backward(ws, static_g, want=want)
+            ent = graphs[key] = (graph, static_g, res)
+        graph, static_g, res = ent
+        for sg, g in zip(static_g, grads):
+            if g is not None:
+                sg.copy_(g)
+        graph.replay()
+        return res
 
     def refresh_bf16(self):
         # a fused optimizer step (trainer.FusedAdam) leaves the shadow up to date and sets bf16_fresh

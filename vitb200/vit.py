@@ -139,7 +139,9 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine, want, images, *params):
-        outs, ws = engine.forward(images, training=True, want=want)
+        if images.dtype != torch.float32 or not images.is_contiguous():
+            images = images.contiguous().float()
+        outs, ws = engine.forward_train(images, want=want)
         ctx.engine, ctx.ws, ctx.want, ctx.n_params = engine, ws, want, len(params)
         ctx.set_materialize_grads(False)
         res = tuple(o.clone() for o in outs)
@@ -147,7 +149,7 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        ctx.engine.backward(ctx.ws, list(grads), want=ctx.want)
+        ctx.engine.backward_train(ctx.ws, list(grads), want=ctx.want)
         return (None, None, None) + (None,) * ctx.n_params
 
 
