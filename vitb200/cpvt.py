@@ -17,7 +17,7 @@ from typing import Callable
 import torch
 from torch import nn
 
-from .engine import VitEngine
+from .engine import VitEngine, getstate_without_engine
 from .vit import EncoderBlock as _VitBlock
 from .vit import _norm_eps, run_engine
 
@@ -117,6 +117,8 @@ class _CpeBase(nn.Module):
                             eps=_norm_eps(self.encoder.ln), globals_=g, layers=[b.roles() for b in blocks])
             self.__dict__["_engine"] = eng
         return eng
+
+    __getstate__ = getstate_without_engine
 
     def __deepcopy__(self, memo):
         import copy

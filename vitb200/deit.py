@@ -12,7 +12,7 @@ import math
 import torch
 from torch import nn
 
-from .engine import VitEngine
+from .engine import VitEngine, getstate_without_engine
 from .vit import run_engine
 
 
@@ -78,6 +78,8 @@ class VisionTransformerDistilled(nn.Module):
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
         self.__dict__["_engine"] = None
+
+    __getstate__ = getstate_without_engine
 
     def set_distilled_training(self, enable=True):
         self.distilled_training = enable

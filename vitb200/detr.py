@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .engine import FlatParams
+from .engine import FlatParams, getstate_without_engine
 from .vit import _EncoderFn  # noqa: F401  (same single-node autograd pattern)
 
 DETR_ROLES = ("norm2_w", "norm2_b", "lin2_w", "lin2_b", "lin1_w", "lin1_b", "norm1_w", "norm1_b", "out_w", "out_b", "in_w", "in_b")
@@ -54,6 +54,8 @@ class TransformerEncoderLayer(nn.Module):
             enc.__dict__["_engine"] = None
             self.__dict__["_solo"] = enc
         return enc(src, mask=src_mask, src_key_padding_mask=src_key_padding_mask, pos=pos)
+
+    __getstate__ = getstate_without_engine
 
     def __deepcopy__(self, memo):
         solo = self.__dict__.pop("_solo", None)
@@ -416,6 +418,8 @@ class _DetrFn(torch.autograd.Function):
 
 
 class TransformerEncoder(nn.Module):
+    __getstate__ = getstate_without_engine
+
     def __init__(self, encoder_layer, num_layers, norm=None):
         super().__init__()
         self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
@@ -508,6 +512,7 @@ class TransformerDecoderLayer(nn.Module):
         return dec(tgt, memory, tgt_mask, memory_mask, tgt_key_padding_mask, memory_key_padding_mask, pos, query_pos)[0]
 
     __deepcopy__ = TransformerEncoderLayer.__deepcopy__
+    __getstate__ = getstate_without_engine
 
 
 class DetrDecoderEngine(DetrEngine):
@@ -747,6 +752,8 @@ class _DetrDecFn(torch.autograd.Function):
 
 
 class TransformerDecoder(nn.Module):
+    __getstate__ = getstate_without_engine
+
     def __init__(self, decoder_layer, num_layers, norm=None, return_intermediate=False):
         super().__init__()
         self.layers = nn.ModuleList([copy.deepcopy(decoder_layer) for _ in range(num_layers)])

@@ -36,6 +36,16 @@ def pick_split_k(tiles, k_blocks, sms):
     return best
 
 
+def getstate_without_engine(module):
+    """``__getstate__`` of the drop-in modules: the engine (flat buffers' bookkeeping, workspaces, captured CUDA graphs) is a cache that
+    is rebuilt lazily, so pickling (torch.save(model)) and copying never see it."""
+    d = module.__dict__.copy()
+    if "_engine" in d:
+        d["_engine"] = None
+    d.pop("_solo", None)
+    return d
+
+
 class FlatParams:
     """Flat fp32 parameter / gradient buffers (+ bf16 shadow) that a module's nn.Parameters are views of.
 

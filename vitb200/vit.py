@@ -15,7 +15,7 @@ from typing import Callable, List, Optional
 import torch
 from torch import nn
 
-from .engine import VitEngine
+from .engine import VitEngine, getstate_without_engine
 
 
 class MLP(torch.nn.Sequential):
@@ -118,6 +118,8 @@ class Encoder(nn.Module):
             return _TokensFn.apply(eng, x, *params)
         outs, _ = eng.forward(x, training=(eng.p_drop > 0 or eng.p_attn > 0), want="features")
         return outs[0].clone()
+
+    __getstate__ = getstate_without_engine
 
     def __deepcopy__(self, memo):
         import copy
@@ -235,6 +237,8 @@ class ViT(nn.Module):
                             layers=[b.roles() for b in blocks])
             self.__dict__["_engine"] = eng
         return eng
+
+    __getstate__ = getstate_without_engine
 
     def __deepcopy__(self, memo):
         import copy
