@@ -11,7 +11,9 @@ Parity status: PINNED against the reference itself.  tools/make_golden.py import
 tests/golden/; tests/test_oracle.py checks this restatement against those fixtures (and, when /root/reference
 is present, against the live reference).  Exception: the DeiT *model class* lives in timm, which is absent
  — its block arithmetic is the pinned ViT arithmetic, only key names / token order are restated
-from timm's public semantics ("parity unpinned" for those names).
+from timm's public semantics ("parity unpinned" for those names).  The DETR decoder layer cannot run as written
+(transformer.py:122 registers ``multi_head_attn``, :148 calls ``self.multihead_attn``); its restatement is pinned against the live
+reference run with exactly that one alias added (tools/make_golden.py::decoder_case).
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 """
