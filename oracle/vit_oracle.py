@@ -368,8 +368,8 @@ def _mha_seq_first(q_in, k_in, v_in, sd, p, nhead, key_padding_mask, attn_drop=N
 
 
 def detr_decoder_forward(sd, tgt, memory, *, nhead, num_layers, activation="relu", memory_key_padding_mask=None, pos=None, query_pos=None,
-                         return_intermediate=False, eps=1e-5, drop=None):
-    """TransformerDecoder.forward over TransformerDecoderLayer.forward_post — transformer.py:74-95, 138-156.  Returns [1, Q, N, D], or
+                         return_intermediate=False, eps=1e-5, drop=None, normalize_before=False):
+    """TransformerDecoder.forward over TransformerDecoderLayer.forward_post / forward_pre — transformer.py:74-95, 138-156, 158-178.  Returns [1, Q, N, D], or
     [L, Q, N, D] with return_intermediate.  ``drop``: ExplicitDropout with masks[(layer, site)]; sites 0 = dropout1, 1 = dropout,
     2 = dropout3, 3 = self-attention weights, 4 = cross-attention weights, 5 = dropout2."""
     act = F.relu if activation == "relu" else F.gelu
@@ -382,6 +382,19 @@ def detr_decoder_forward(sd, tgt, memory, *, nhead, num_layers, activation="relu
     for i in range(num_layers):
         p = f"layers.{i}."
         ad = (lambda site: None) if drop is None else (lambda site, i=i: (lambda P: drop((i, site), P)))
+        if normalize_before:                                                                                    # forward_pre :158-178
+            h = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+            qk = wp(h, query_pos)
+            x = x + dz((i, 0), _mha_seq_first(qk, qk, h, sd, p + "self_attn.", nhead, None, ad(3)))
+            h = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+            x = x + dz((i, 5), _mha_seq_first(wp(h, query_pos), wp(memory, pos), memory, sd, p + "multi_head_attn.", nhead,
+                                              memory_key_padding_mask, ad(4)))
+            h = F.layer_norm(x, (D,), sd[p + "norm3.weight"], sd[p + "norm3.bias"], eps)
+            x = x + dz((i, 2), F.linear(dz((i, 1), act(F.linear(h, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))),
+                                        sd[p + "linear2.weight"], sd[p + "linear2.bias"]))
+            if return_intermediate:
+                inter.append(fnorm(x))
+            continue
         qk = wp(x, query_pos)
         x = x + dz((i, 0), _mha_seq_first(qk, qk, x, sd, p + "self_attn.", nhead, None, ad(3)))                  # :142-144
         x = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)

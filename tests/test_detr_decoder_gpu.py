@@ -18,10 +18,10 @@ def _masks(eng, ws, Q, S, N, p):
     return m
 
 
-def _run(Q, S, N, d_model, nhead, ffn, layers, *, inter, masked=True, with_pos=True, p=0.0, act="relu", norm=True):
+def _run(Q, S, N, d_model, nhead, ffn, layers, *, inter, masked=True, with_pos=True, p=0.0, act="relu", norm=True, pre=False):
     from vitb200.detr import TransformerDecoder, TransformerDecoderLayer
     sd = O.seeded_state_dict(O.detr_decoder_param_shapes(d_model, ffn, layers, with_norm=norm), 61)
-    dec = TransformerDecoder(TransformerDecoderLayer(d_model, nhead, ffn, p, act, False), layers, torch.nn.LayerNorm(d_model) if norm else None,
+    dec = TransformerDecoder(TransformerDecoderLayer(d_model, nhead, ffn, p, act, pre), layers, torch.nn.LayerNorm(d_model) if norm else None,
                              return_intermediate=inter)
     dec.load_state_dict(sd)
     dec = dec.cuda().train()
@@ -46,7 +46,8 @@ def _run(Q, S, N, d_model, nhead, ffn, layers, *, inter, masked=True, with_pos=T
         for k, v in masks.items():
             assert abs(v.mean().item() - (1 - p)) < 0.03, (k, v.mean().item())
         drop = O.ExplicitDropout(masks, p, p)
-    kw = dict(nhead=nhead, num_layers=layers, activation=act, memory_key_padding_mask=kpm, return_intermediate=inter, drop=drop)
+    kw = dict(nhead=nhead, num_layers=layers, activation=act, memory_key_padding_mask=kpm, return_intermediate=inter, drop=drop,
+              normalize_before=pre)
 
     def oracle(autocast):
         osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -96,6 +97,14 @@ def test_decoder_dropout_replayed_masks(inter, act):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("inter,norm,p,act", [(True, True, 0.0, "relu"), (False, True, 0.0, "gelu"), (False, False, 0.0, "relu"),
+                                              (True, True, 0.1, "relu"), (False, True, 0.1, "relu")])
+def test_decoder_pre_norm(inter, norm, p, act):
+    """normalize_before=True: TransformerDecoderLayer.forward_pre (transformer.py:158-178)."""
+    _run(Q=40, S=130, N=2, d_model=256, nhead=4, ffn=512, layers=3, inter=inter, norm=norm, p=p, act=act, pre=True)
+
+
+@pytest.mark.gpu
 def test_decoder_layer_standalone_and_errors():
     from vitb200.detr import TransformerDecoder, TransformerDecoderLayer
     layer = TransformerDecoderLayer(256, 4, 512, 0.0, "relu", False).cuda()
@@ -105,8 +114,6 @@ def test_decoder_layer_standalone_and_errors():
     sd = {"layers.0." + k: v.cpu() for k, v in layer.state_dict().items()}
     ref = O.detr_decoder_forward(sd, t.cpu(), m.cpu(), nhead=4, num_layers=1)[0]
     assert rel_l2(y, ref) < 1.5e-2
-    with pytest.raises(NotImplementedError):
-        TransformerDecoder(TransformerDecoderLayer(256, 4, 512, 0.0, "relu", True), 1).cuda()(t, m)
     with pytest.raises(NotImplementedError):
         TransformerDecoder(layer, 1).cuda()(t, m, tgt_mask=torch.zeros(10, 10, device="cuda"))
 

@@ -191,7 +191,7 @@ def test_cpe_module_keys_and_seed_parity():
             assert torch.equal(a[k], b[k]), (clsname, k)
 
 
-@pytest.mark.parametrize("name", ["detr_dec_d256.pt", "detr_dec_dropout_d256.pt"])
+@pytest.mark.parametrize("name", ["detr_dec_d256.pt", "detr_dec_dropout_d256.pt", "detr_dec_prenorm_dropout_d256.pt"])
 def test_oracle_detr_decoder_matches_reference_golden(name):
     """TransformerDecoder / TransformerDecoderLayer.forward_post (transformer.py:66-95, 138-156) against the live
     reference run with the ``multihead_attn`` alias (tools/make_golden.py::decoder_case); with dropout the masks drawn inside the
@@ -217,7 +217,7 @@ def test_oracle_detr_decoder_matches_reference_golden(name):
     valid = torch.randint(S // 2, S + 1, (N,), generator=g)
     kpm = torch.arange(S)[None, :] >= valid[:, None]
     out = O.detr_decoder_forward(sd, tgt, memory, nhead=h, num_layers=L, memory_key_padding_mask=kpm, pos=pos, query_pos=qpos,
-                                 return_intermediate=gd["return_intermediate"], drop=drop)
+                                 return_intermediate=gd["return_intermediate"], drop=drop, normalize_before=gd.get("pre_norm", False))
     gout = torch.randn(out.shape, generator=g)
     out.backward(gout)
     assert out.shape == gd["out"].shape and rel_l2(out, gd["out"]) < 1e-5

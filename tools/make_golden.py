@@ -187,14 +187,14 @@ def cpe_case(name, which, cfg, batch, seed):
     print(name, "loss", loss.item())
 
 
-def decoder_case(name, d_model, nhead, ffn, layers, Q, S, N, seed, p=0.0, return_intermediate=False):
+def decoder_case(name, d_model, nhead, ffn, layers, Q, S, N, seed, p=0.0, return_intermediate=False, pre_norm=False):
     """TransformerDecoder over TransformerDecoderLayer.forward_post.  The reference layer registers ``multi_head_attn``
     (transformer.py:122) and calls ``self.multihead_attn`` (:148): the alias below is the ONE change that lets the reference's own
     forward run; everything else is the unmodified code."""
     from models.object_detection.transformer import TransformerDecoder as RefDec, TransformerDecoderLayer as RefDecLayer
     if not hasattr(RefDecLayer, "multihead_attn"):
         RefDecLayer.multihead_attn = property(lambda self: self.multi_head_attn)
-    dec = RefDec(RefDecLayer(d_model, nhead, ffn, p, "relu", False), layers, torch.nn.LayerNorm(d_model), return_intermediate=return_intermediate)
+    dec = RefDec(RefDecLayer(d_model, nhead, ffn, p, "relu", pre_norm), layers, torch.nn.LayerNorm(d_model), return_intermediate=return_intermediate)
     sd = O.seeded_state_dict(O.detr_decoder_param_shapes(d_model, ffn, layers), seed)
     assert set(sd) == set(dec.state_dict()), set(sd) ^ set(dec.state_dict())
     dec.load_state_dict(sd)
@@ -212,7 +212,7 @@ def decoder_case(name, d_model, nhead, ffn, layers, Q, S, N, seed, p=0.0, return
     out.backward(gout)
     norms, full = grads_summary(dec.named_parameters())
     torch.save({"d_model": d_model, "nhead": nhead, "ffn": ffn, "layers": layers, "Q": Q, "S": S, "N": N, "seed": seed, "p": p,
-                "return_intermediate": return_intermediate, "mask_shapes": rd.shapes, "out": out.detach(),
+                "return_intermediate": return_intermediate, "pre_norm": pre_norm, "mask_shapes": rd.shapes, "out": out.detach(),
                 "dtgt_norm": tgt.grad.norm().item(), "dmem_norm": memory.grad.norm().item(), "dpos_norm": pos.grad.norm().item(),
                 "dqpos_norm": qpos.grad.norm().item(), "dmem_row0": memory.grad[0].clone(), "grad_norms": norms, "grads_small": full},
                os.path.join(OUT, name))
@@ -252,6 +252,7 @@ if __name__ == "__main__":
     vit_hidden_dropout_case("vit_tiny_hidden_dropout_b4.pt", dict(TINY, num_layers=3), 4, 161, 0.1)
     decoder_case("detr_dec_d256.pt", 256, 4, 512, 2, 20, 70, 2, 201, return_intermediate=True)
     decoder_case("detr_dec_dropout_d256.pt", 256, 4, 512, 2, 20, 70, 2, 211, p=0.1)
+    decoder_case("detr_dec_prenorm_dropout_d256.pt", 256, 4, 512, 2, 20, 70, 2, 221, p=0.1, return_intermediate=True, pre_norm=True)
     cpe_case("cpe_vit_tiny_b4.pt", "CPEViT", dict(TINY, num_layers=3), 4, 171)
     cpe_case("cpvt_tiny_b4.pt", "CPVT", dict(TINY, num_layers=3), 4, 181)
     cpe_case("cpvt_gap_tiny_b4.pt", "CPVTGAP", dict(TINY, num_layers=2), 4, 191)

@@ -520,10 +520,10 @@ class DetrDecoderEngine(DetrEngine):
     against the S-token encoder memory (vb_attention with S_kv), feed-forward; three LayerNorms; six dropout sites per layer
     (0 = dropout1, 1 = dropout, 2 = dropout3, 3 = self-attention weights, 4 = cross-attention weights, 5 = dropout2)."""
 
-    def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5, return_intermediate=False):
+    def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5, return_intermediate=False, pre_norm=False):
         assert d_model % 128 == 0 and d_model // nhead == 64, "vitb200 kernels need d_model % 128 == 0 and head_dim == 64"
         self.D, self.H, self.F, self.L, self.eps = d_model, nhead, dim_feedforward, len(layers), eps
-        self.act, self.pre_norm, self.has_norm = activation, False, norm is not None
+        self.act, self.pre_norm, self.has_norm = activation, bool(pre_norm), norm is not None
         self.return_intermediate = bool(return_intermediate) and self.has_norm
         self.p_drop, self._drop_counter = 0.0, None
         self._order, seg = [], []
@@ -590,6 +590,9 @@ class DetrDecoderEngine(DetrEngine):
         seed = ws.get("drop_seed")
         ops.add_cast_bf16(mem, None, ws["m_bf"])                     # value operand of every layer's cross-attention
         ops.add_cast_bf16(mem, pos2, ws["mk_bf"])                    # key operand: memory + pos (transformer.py:146)
+        if self.pre_norm:
+            x = self._forward_pre_layers(ws, t0, qpos, mem_kpm, training, Q, S, N)
+            return self._finish_forward(ws, x, Q, N, D)
         b0 = ws["layer"][0]
         ops.add_cast_bf16(t0, None, b0["x_bf"])
         ops.add_cast_bf16(t0, qpos, b0["qk_bf"])
@@ -626,6 +629,9 @@ class DetrDecoderEngine(DetrEngine):
             if nbuf and qpos is None:
                 ops.add_cast_bf16(buf["t3"], None, nbuf["qk_bf"])
             x = buf["t3"]
+        return self._finish_forward(ws, x, Q, N, D)
+
+    def _finish_forward(self, ws, x, Q, N, D):
         if not self.has_norm:
             return x.view(1, Q, N, D), ws                            # output.unsqueeze(0) (:95)
         outs = range(self.L) if self.return_intermediate else [self.L - 1]
@@ -633,6 +639,135 @@ class DetrDecoderEngine(DetrEngine):
             ops.layernorm_fwd(ws["layer"][li]["t3"], self.f(("g", "norm_w")), self.f(("g", "norm_b")), self.eps, y_f32=ws["y"][j],
                               mean=ws["meanf"][j], rstd=ws["rstdf"][j])
         return ws["y"].view(-1, Q, N, D), ws
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # Pre-norm layers (normalize_before=True, TransformerDecoderLayer.forward_pre, transformer.py:158-178): tgt2 = norm1(tgt);
+    # q = k = tgt2 + query_pos; tgt += dropout1(self_attn(q, k, tgt2)); tgt2 = norm2(tgt); tgt += dropout2(cross(tgt2 + query_pos,
+    # memory + pos, memory)); tgt2 = norm3(tgt); tgt += dropout3(ffn(tgt2)).  The fp32 stream is t0 -> t1 -> t2 -> t3.
+    # ------------------------------------------------------------------------------------------------------------------
+    def _forward_pre_layers(self, ws, t0, qpos, mem_kpm, training, Q, S, N):
+        D, H = self.D, self.H
+        pd, seed, site = ws["p_drop"], ws.get("drop_seed"), self.drop_site
+        if "t0" not in ws:
+            ws["t0"] = torch.empty_like(ws["layer"][0]["t3"])
+        ws["t0"].copy_(t0)
+        x = ws["t0"]
+        for li in range(self.L):
+            buf = ws["layer"][li]
+            ops.layernorm_fwd(x, self.f((li, "norm1_w")), self.f((li, "norm1_b")), self.eps, y_bf16=buf["x_bf"], mean=buf["mean1"],
+                              rstd=buf["rstd1"], add=qpos, y2_bf16=buf["qk_bf"] if qpos is not None else None)
+            qk_in = buf["qk_bf"] if qpos is not None else buf["x_bf"]
+            in_w, in_b = self.w((li, "in_w")), self.f((li, "in_b"))
+            ops.gemm(qk_in, in_w[:2 * D], buf["sqk"], bias=in_b[:2 * D])
+            ops.gemm(buf["x_bf"], in_w[2 * D:], buf["sv"], bias=in_b[2 * D:])
+            ops.attention_fwd(buf["sqk"][:, :D], buf["sqk"][:, D:], buf["sv"], buf["so"], buf["slse"] if training else None, B=N, H=H, S=Q,
+                              tok_stride=N, batch_stride=1, dropout=(pd, seed, site(li, 3)) if pd > 0 else None)
+            self._linear_residual(ws, buf["so"], "out_w", "out_b", li, 0, x, buf["t1"], pd)
+            ops.layernorm_fwd(buf["t1"], self.f((li, "norm2_w")), self.f((li, "norm2_b")), self.eps, y_bf16=buf["t1_bf"], mean=buf["mean2"],
+                              rstd=buf["rstd2"], add=qpos, y2_bf16=buf["t1q_bf"] if qpos is not None else None)
+            cw, cb = self.w((li, "cin_w")), self.f((li, "cin_b"))
+            ops.gemm(buf["t1q_bf"] if qpos is not None else buf["t1_bf"], cw[:D], buf["cq"], bias=cb[:D])
+            ops.gemm(ws["mk_bf"], cw[D:2 * D], buf["ck"], bias=cb[D:2 * D])
+            ops.gemm(ws["m_bf"], cw[2 * D:], buf["cv"], bias=cb[2 * D:])
+            ops.attention_fwd(buf["cq"], buf["ck"], buf["cv"], buf["co"], buf["clse"] if training else None, B=N, H=H, S=Q, S_kv=S,
+                              tok_stride=N, batch_stride=1, key_padding_mask=mem_kpm, dropout=(pd, seed, site(li, 4)) if pd > 0 else None)
+            self._linear_residual(ws, buf["co"], "cout_w", "cout_b", li, 5, buf["t1"], buf["t2"], pd)
+            ops.layernorm_fwd(buf["t2"], self.f((li, "norm3_w")), self.f((li, "norm3_b")), self.eps, y_bf16=buf["x1_bf"], mean=buf["mean3"],
+                              rstd=buf["rstd3"])
+            act_out = self._ffn_fwd(ws, buf, li, pd)
+            self._linear_residual(ws, act_out, "lin2_w", "lin2_b", li, 2, buf["t2"], buf["t3"], pd)
+            x = buf["t3"]
+        return x
+
+    def _backward_pre_layers(self, ws, g_all):
+        Q, S, N, Mq, D, H, L = ws["Q"], ws["S"], ws["N"], ws["M"], self.D, self.H, self.L
+        d, d_bf, dh, dh2 = ws["dT"], ws["dU_bf"], ws["dh"], ws["dh2"]     # d: fp32 gradient of the stream, updated in place
+        dmem, dpos, dqpos = ws["dmem"], ws["dpos"], ws["dqpos"]
+        pd, kpm, seed, site = ws["p_drop"], ws["kpm"], ws.get("drop_seed"), self.drop_site
+        drelu = dict(drelu_scale=1.0 / (1.0 - pd)) if (pd > 0 and self.act == "relu") else {}
+        fuse = pd == 0
+        have_next = False
+        for li in range(L - 1, -1, -1):
+            buf = ws["layer"][li]
+            x_in = ws["layer"][li - 1]["t3"] if li > 0 else ws["t0"]
+            gets_norm = self.has_norm and (self.return_intermediate or li == L - 1)
+            lin2_b = self.gview((li, "lin2_b"))
+            if gets_norm:      # the decoder norm's backward also emits this layer's bf16 operand and linear2 bias gradient
+                j = li if self.return_intermediate else 0
+                ops.layernorm_bwd(g_all[j], buf["t3"], ws["meanf"][j], ws["rstdf"][j], self.f(("g", "norm_w")), dres=d if have_next else None,
+                                  dx=d, dx_bf16=d_bf if fuse else None, dgamma=self.gview(("g", "norm_w")), dbeta=self.gview(("g", "norm_b")),
+                                  dx_colsum=lin2_b if fuse else None)
+                if not self.return_intermediate:
+                    self._seg_done(0)
+            elif not have_next:
+                d.copy_(g_all[0])
+                if fuse:
+                    ops.cast_bf16(d.view(-1), d_bf.view(-1))
+                    ops.colsum_bf16(d_bf, lin2_b)
+            if pd > 0:
+                self._masked_operand(ws, d, d_bf, li, 2, (li, "lin2_b"))
+            # ---- feed-forward ----
+            act_out = buf["a"] if self.act == "relu" else buf["g"]
+            self._wgrad(d_bf, act_out, (li, "lin2_w"))
+            ops.gemm(d_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU if self.act == "relu" else ops.EPI_DGELU,
+                     aux=buf["a"], **drelu)
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
+            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
+            ops.layernorm_bwd(dh, buf["t2"], buf["mean3"], buf["rstd3"], self.f((li, "norm3_w")), dres=d, dx=d, dx_bf16=d_bf if fuse else None,
+                              dgamma=self.gview((li, "norm3_w")), dbeta=self.gview((li, "norm3_b")),
+                              dx_colsum=self.gview((li, "cout_b")) if fuse else None)
+            if pd > 0:
+                self._masked_operand(ws, d, d_bf, li, 5, (li, "cout_b"))
+            # ---- cross-attention ----
+            self._wgrad(d_bf, buf["co"], (li, "cout_w"))
+            ops.gemm(d_bf, self.w((li, "cout_w")), dh, b_major=1)
+            ops.attention_bwd(buf["cq"], buf["ck"], buf["cv"], buf["co"], buf["clse"], dh, ws["dcq"], ws["dck"], ws["dcv"], ws["delta"],
+                              B=N, H=H, S=Q, S_kv=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm,
+                              dropout=(pd, seed, site(li, 4)) if pd > 0 else None)
+            cw, gcb = self.w((li, "cin_w")), self.gview((li, "cin_b"))
+            self._wgrad(ws["dcq"], buf["t1q_bf"] if ws["has_qpos"] else buf["t1_bf"], (li, "cin_w"), rows=(0, D))
+            self._wgrad(ws["dck"], ws["mk_bf"], (li, "cin_w"), rows=(D, 2 * D))
+            self._wgrad(ws["dcv"], ws["m_bf"], (li, "cin_w"), rows=(2 * D, 3 * D))
+            ops.colsum_bf16(ws["dcq"], gcb[:D])
+            ops.colsum_bf16(ws["dck"], gcb[D:2 * D])
+            ops.colsum_bf16(ws["dcv"], gcb[2 * D:])
+            ops.gemm(ws["dcq"], cw[:D], dh, b_major=1)
+            ops.gemm(ws["dck"], cw[D:2 * D], ws["dmk"], b_major=1)
+            ops.gemm(ws["dcv"], cw[2 * D:], ws["dmv"], b_major=1)
+            ops.add3(dmem, ws["dmk"], ws["dmv"], dmem, dpos)
+            ops.add3(dqpos, dh, None, dqpos, None)
+            ops.layernorm_bwd(dh, buf["t1"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dres=d, dx=d, dx_bf16=d_bf if fuse else None,
+                              dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")),
+                              dx_colsum=self.gview((li, "out_b")) if fuse else None)
+            if pd > 0:
+                self._masked_operand(ws, d, d_bf, li, 0, (li, "out_b"))
+            # ---- self-attention ----
+            self._wgrad(d_bf, buf["so"], (li, "out_w"))
+            ops.gemm(d_bf, self.w((li, "out_w")), dh, b_major=1)
+            dsqk, dsv = ws["dsqk"], ws["dsv"]
+            ops.attention_bwd(buf["sqk"][:, :D], buf["sqk"][:, D:], buf["sv"], buf["so"], buf["slse"], dh, dsqk[:, :D], dsqk[:, D:], dsv,
+                              ws["delta"], B=N, H=H, S=Q, tok_stride=N, batch_stride=1, dropout=(pd, seed, site(li, 3)) if pd > 0 else None)
+            in_w, gb = self.w((li, "in_w")), self.gview((li, "in_b"))
+            self._wgrad(dsqk, buf["qk_bf"] if ws["has_qpos"] else buf["x_bf"], (li, "in_w"), rows=(0, 2 * D))
+            self._wgrad(dsv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
+            ops.colsum_bf16(dsqk, gb[:2 * D])
+            ops.colsum_bf16(dsv, gb[2 * D:])
+            ops.gemm(dsqk, in_w[:2 * D], dh, b_major=1)       # d(norm1(t0) + query_pos)
+            ops.gemm(dsv, in_w[2 * D:], dh2, b_major=1)       # d norm1(t0) through the values
+            ops.add3(dqpos, dh, None, dqpos, None)
+            # the previous layer's operand / linear2 bias gradient come from here unless its own decoder-norm backward emits them
+            prev_fused = fuse and li > 0 and not (self.has_norm and self.return_intermediate)
+            ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dres=d, dx=d, dx_bf16=d_bf if prev_fused else None,
+                              dgamma=self.gview((li, "norm1_w")), dbeta=self.gview((li, "norm1_b")),
+                              dx_colsum=self.gview((li - 1, "lin2_b")) if prev_fused else None, dy_add=dh2)
+            have_next = True
+            if not self.return_intermediate:
+                self._seg_done((L - 1 - li) + (1 if self.has_norm else 0))
+        if self.return_intermediate:
+            for i in range(L + 1):
+                self._seg_done(i)
+        return d
 
     def backward(self, ws, grad_out):
         self.prepare_grads()
@@ -649,6 +784,10 @@ class DetrDecoderEngine(DetrEngine):
         drelu = dict(drelu_scale=1.0 / (1.0 - pd)) if (pd > 0 and self.act == "relu") else {}
         fuse = pd == 0
         seg = 0
+        if self.pre_norm:
+            d = self._backward_pre_layers(ws, g_all)
+            return (d.view(Q, N, D), dmem.view(S, N, D), dpos.view(S, N, D) if ws["has_pos"] else None,
+                    dqpos.view(Q, N, D) if ws["has_qpos"] else None)
         have_next = False     # dT holds the gradient that layer li + 1 sends to this layer's output
         for li in range(L - 1, -1, -1):
             buf = ws["layer"][li]
@@ -766,13 +905,10 @@ class TransformerDecoder(nn.Module):
         eng = self.__dict__.get("_engine")
         if eng is None:
             l0 = self.layers[0]
-            if l0.normalize_before:
-                raise NotImplementedError("vitb200: the DETR decoder is implemented for post-norm layers (normalize_before=False, the "
-                                          "reference default, transformer.py:27-28)")
             if self.return_intermediate and self.norm is None:
                 raise TypeError("return_intermediate needs the decoder norm (transformer.py:85 calls self.norm unconditionally)")
             eng = DetrDecoderEngine(list(self.layers), self.norm, l0.d_model, l0.nhead, l0.dim_feedforward, l0.activation_name,
-                                    eps=float(l0.norm1.eps), return_intermediate=self.return_intermediate)
+                                    eps=float(l0.norm1.eps), return_intermediate=self.return_intermediate, pre_norm=l0.normalize_before)
             self.__dict__["_engine"] = eng
         return eng
 
