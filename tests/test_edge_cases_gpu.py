@@ -1,0 +1,112 @@
+"""-m gpu: edge cases of the module contract: batch 1, ragged last batches, non-contiguous / non-fp32 inputs, the
+reference's shape assertions, fully padded DETR samples."""
+import pytest
+import torch
+
+from helpers import O, rel_l2
+
+CFG = dict(image_size=32, patch_size=4, num_layers=2, num_heads=4, hidden_dim=256, mlp_dim=512, num_classes=10)
+KW = dict(patch_size=4, num_layers=2, num_heads=4)
+
+
+def _model(train=True):
+    from vitb200.vit import ViT
+    sd = O.seeded_state_dict(O.vit_param_shapes(**CFG), 71)
+    m = ViT(32, 4, 2, 4, 256, 512, 0.0, 0.0, 10)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    return (m.train() if train else m.eval()), sd
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [1, 2, 5])
+def test_tiny_batches_train(batch):
+    """A loader's ragged last batch (len(dataset) % batch_size; base.py:51 does not drop it)."""
+    m, sd = _model()
+    x, y = O.seeded_images(batch, 32, 72), O.seeded_labels(batch, 10, 73)
+    out = m(x.cuda())
+    torch.nn.functional.cross_entropy(out, y.cuda()).backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.vit_forward(ref_sd, x, **KW)
+    torch.nn.functional.cross_entropy(ref, y).backward()
+    # 1.5e-2 is the bound for tensors with hundreds of entries; ten bf16-path logits of ONE sample scatter more (measured 1.7e-2)
+    assert out.shape == (batch, 10) and rel_l2(out, ref) < (2.5e-2 if batch == 1 else 1.5e-2)
+    worst = max(((rel_l2(p.grad, ref_sd[n].grad), n) for n, p in m.named_parameters()))
+    assert worst[0] < (4e-2 if batch == 1 else 3e-2), worst
+
+
+@pytest.mark.gpu
+def test_alternating_batch_sizes_reuse_their_workspaces():
+    m, sd = _model()
+    for b in (8, 3, 8, 3, 1, 8):
+        x = O.seeded_images(b, 32, 80 + b)
+        out = m(x.cuda())
+        out.sum().backward()
+        assert rel_l2(out, O.vit_forward(sd, x, **KW)) < 1.5e-2
+
+
+@pytest.mark.gpu
+def test_input_layouts_and_dtypes():
+    m, sd = _model(train=False)
+    x = O.seeded_images(4, 32, 74)
+    ref = O.vit_forward(sd, x, **KW)
+    with torch.no_grad():
+        a = m(x.cuda().to(memory_format=torch.channels_last))                 # non-contiguous NCHW view
+        b = m(x.cuda().double())                                             # fp64 batch
+        c = m(x.cuda()[:, :, :, :].expand(4, 3, 32, 32))
+        h = m(x.cuda().half())                                               # fp16 batch: rounded inputs, same path
+    assert rel_l2(a, ref) < 1.5e-2 and rel_l2(b, ref) < 1.5e-2 and rel_l2(c, ref) < 1.5e-2
+    assert rel_l2(h, O.vit_forward(sd, x.half().float(), **KW)) < 1.5e-2
+
+
+@pytest.mark.gpu
+def test_reference_shape_assertions():
+    m, _ = _model(train=False)
+    with pytest.raises(Exception):
+        m(torch.zeros(2, 3, 16, 16, device="cuda"))                           # vanilla_vit.py:190-191
+    with pytest.raises(Exception):
+        m(torch.zeros(2, 3, 32, 16, device="cuda"))
+    with pytest.raises(Exception):
+        m(torch.zeros(2, 1, 32, 32, device="cuda"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 3, 32, 32))                                          # host tensor into a CUDA model: loud error, no fallback
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.train()(torch.zeros(2, 3, 32, 32))
+    m.eval()
+    from vitb200.detr import TransformerDecoder, TransformerDecoderLayer, TransformerEncoder, TransformerEncoderLayer
+    enc2 = TransformerEncoder(TransformerEncoderLayer(256, 4, 512, 0.0, "relu", False), 1).cuda()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc2(torch.zeros(10, 2, 256))
+    with pytest.raises(RuntimeError):
+        enc2(torch.zeros(10, 2, 128, device="cuda"))                          # wrong d_model
+    with pytest.raises(RuntimeError):
+        enc2(torch.zeros(10, 2, 256, device="cuda"), src_key_padding_mask=torch.zeros(2, 9, dtype=torch.bool, device="cuda"))
+    dec2 = TransformerDecoder(TransformerDecoderLayer(256, 4, 512, 0.0, "relu", False), 1).cuda()
+    with pytest.raises(RuntimeError):
+        dec2(torch.zeros(5, 2, 256, device="cuda"), torch.zeros(10, 3, 256, device="cuda"))     # batch mismatch
+    torch.cuda.synchronize()                                                  # nothing illegal was launched
+    enc = m.encoder
+    with pytest.raises(Exception):
+        enc(torch.zeros(2, 65, device="cuda"))                                # vanilla_vit.py:103: 3-D input expected
+
+
+@pytest.mark.gpu
+def test_detr_encoder_fully_padded_sample_is_finite_elsewhere():
+    """A sample whose keys are ALL padding: the reference's softmax over an all -inf row is NaN for that sample only; here that
+    sample's attention output is defined as zero (l = 0 -> 0), and the other samples are unaffected either way."""
+    from vitb200.detr import TransformerEncoder, TransformerEncoderLayer
+    sd = O.seeded_state_dict(O.detr_param_shapes(256, 512, 2, False), 75)
+    enc = TransformerEncoder(TransformerEncoderLayer(256, 4, 512, 0.0, "relu", False), 2)
+    enc.load_state_dict(sd)
+    enc = enc.cuda().eval()
+    g = torch.Generator().manual_seed(76)
+    src, pos = torch.randn(70, 3, 256, generator=g), torch.randn(70, 3, 256, generator=g)
+    kpm = torch.zeros(3, 70, dtype=torch.bool)
+    kpm[1, :] = True
+    kpm[2, 50:] = True
+    with torch.no_grad():
+        out = enc(src.cuda(), src_key_padding_mask=kpm.cuda(), pos=pos.cuda())
+    ref = O.detr_encoder_forward(sd, src, nhead=4, num_layers=2, src_key_padding_mask=kpm, pos=pos)
+    assert torch.isfinite(out).all()
+    for b in (0, 2):
+        assert rel_l2(out[:, b], ref[:, b]) < 1.5e-2

@@ -1,5 +1,5 @@
 """Per-op GPU time of one eager ViT-B/16 training step (CUDA events around every C-ABI call), after warm-up.
-Usage: python tools/step_profile.py [batch]"""
+Usage: python tools/step_profile.py [batch] [vit_b16 | deit_s | vit_l16]"""
 import collections
 import os
 import sys
@@ -12,10 +12,19 @@ from vitb200.trainer import Trainer
 from vitb200.vit import ViT
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+which = sys.argv[2] if len(sys.argv) > 2 else "vit_b16"
 torch.manual_seed(0)
-model = ViT(224, 16, 12, 12, 768, 3072, 0.0, 0.0, 1000)
-with torch.no_grad():
-    model.heads.head.weight.normal_(std=0.02)
+if which == "deit_s":     # BASELINE.json configs[2]: DeiT-S/16 with distillation token (student step, plain CE on the class head here)
+    from vitb200.deit import VisionTransformerDistilled
+    model = VisionTransformerDistilled(img_size=224, patch_size=16, depth=12, num_heads=6, embed_dim=384, mlp_ratio=4, num_classes=1000)
+elif which == "vit_l16":
+    model = ViT(224, 16, 24, 16, 1024, 4096, 0.0, 0.0, 1000)
+    with torch.no_grad():
+        model.heads.head.weight.normal_(std=0.02)
+else:
+    model = ViT(224, 16, 12, 12, 768, 3072, 0.0, 0.0, 1000)
+    with torch.no_grad():
+        model.heads.head.weight.normal_(std=0.02)
 model = model.cuda().train()
 tr = Trainer(model, use_cuda_graph=False)
 images = torch.randn(B, 3, 224, 224, device="cuda")
@@ -62,6 +71,6 @@ for tag, a, b in rec:
     cnt[tag] += 1
 total = s0.elapsed_time(s1)
 ksum = sum(tot.values())
-print(f"step {total:.2f} ms, sum of bracketed ops {ksum:.2f} ms, batch {B}")
+print(f"{which}: step {total:.2f} ms, sum of bracketed ops {ksum:.2f} ms, batch {B}")
 for k, v in tot.most_common():
     print(f"  {k:34s} n={cnt[k]:3d} {v:8.3f} ms {100 * v / total:5.1f}%")

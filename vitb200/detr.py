@@ -166,7 +166,12 @@ class DetrEngine(FlatParams):
 
     def forward(self, src, pos, kpm, training):
         self.ensure_bound()
+        for t, name in ((src, "src"), (pos, "pos"), (kpm, "src_key_padding_mask")):
+            self.check_input(t, name)
         S, N, D = src.shape
+        if D != self.D or (pos is not None and pos.shape != src.shape) or (kpm is not None and tuple(kpm.shape) != (N, S)):
+            raise RuntimeError(f"vitb200: expected src [S, N, {self.D}], pos of the same shape and src_key_padding_mask [N, S]; got "
+                               f"{tuple(src.shape)}, {None if pos is None else tuple(pos.shape)}, {None if kpm is None else tuple(kpm.shape)}")
         ws = self.workspace(S, N, training)
         self.refresh_bf16()
         M, H = ws["M"], self.H
@@ -573,8 +578,14 @@ class DetrDecoderEngine(DetrEngine):
 
     def forward(self, tgt, memory, mem_kpm, pos, query_pos, training):
         self.ensure_bound()
+        for t, name in ((tgt, "tgt"), (memory, "memory"), (pos, "pos"), (query_pos, "query_pos"), (mem_kpm, "memory_key_padding_mask")):
+            self.check_input(t, name)
         Q, N, D = tgt.shape
         S = memory.shape[0]
+        if D != self.D or tuple(memory.shape[1:]) != (N, D) or (pos is not None and pos.shape != memory.shape) \
+                or (query_pos is not None and query_pos.shape != tgt.shape) or (mem_kpm is not None and tuple(mem_kpm.shape) != (N, S)):
+            raise RuntimeError(f"vitb200: expected tgt/query_pos [Q, N, {self.D}], memory/pos [S, N, {self.D}], memory_key_padding_mask "
+                               f"[N, S]; got tgt {tuple(tgt.shape)}, memory {tuple(memory.shape)}")
         ws = self.workspace(Q, S, N, training)
         self.refresh_bf16()
         Mq, Ms, H = ws["M"], ws["Ms"], self.H

@@ -100,6 +100,12 @@ class FlatParams:
         self.bf16_fresh = False
         self._sms = torch.cuda.get_device_properties(device).multi_processor_count
 
+    def check_input(self, t, name="input"):
+        """Inputs must live on the engine's CUDA device: the kernels take raw device pointers (a host tensor would be an illegal access)."""
+        if t is not None and (not t.is_cuda or t.device != self.flat.device):
+            raise RuntimeError(f"vitb200: {name} is on {t.device} but the model is on {self.flat.device}; move it there first "
+                               "(there is no CPU fallback)")
+
     def ensure_bound(self):
         p0 = self._order[0][1]
         if not p0.is_cuda:
@@ -136,6 +142,7 @@ class FlatParams:
     def forward_inference(self, x, *, want):
         """forward(x, training=False, want=want) for a no-grad caller; CUDA-graph replay for small batches."""
         self.ensure_bound()
+        self.check_input(x, "the input batch")
         if os.environ.get("VITB200_INFER_GRAPH", "1") == "0" or x.shape[0] > self.INFER_GRAPH_MAX_BATCH or not x.is_cuda \
                 or torch.cuda.is_current_stream_capturing():
             return self.forward(x, training=False, want=want)[0]
@@ -207,6 +214,7 @@ class FlatParams:
     def forward_train(self, x, *, want):
         """forward(x, training=True, want=want) for the autograd node; returns (outputs, ws)."""
         self.ensure_bound()
+        self.check_input(x, "the input batch")
         if not (x.is_cuda and self._autograd_graph_ok(x.shape[0] * self.S)):
             return self.forward(x, training=True, want=want)
         graphs = self.__dict__.setdefault("_train_graphs", {})
@@ -495,6 +503,7 @@ class VitEngine(FlatParams):
         """want: 'logits' (head(s) on the prefix token rows) or 'features' ([B,S,D] fp32 after the final norm).
         Returns (outputs, ws) where outputs is a list of fp32 tensors (views into the workspace)."""
         self.ensure_bound()
+        self.check_input(images, "the input batch")
         if images.dtype != torch.float32 or not images.is_contiguous():
             images = images.contiguous().float()
         B = images.shape[0]
