@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .engine import FlatParams, getstate_without_engine
+from .engine import FlatParams, WorkspaceLease, getstate_without_engine
 from .vit import _EncoderFn  # noqa: F401  (same single-node autograd pattern)
 
 DETR_ROLES = ("norm2_w", "norm2_b", "lin2_w", "lin2_b", "lin1_w", "lin1_b", "norm1_w", "norm1_b", "out_w", "out_b", "in_w", "in_b")
@@ -138,7 +138,7 @@ class DetrEngine(FlatParams):
 
     def workspace(self, S, N, training):
         key = (S, N, training)
-        ws = self._ws.get(key)
+        ws = self._free_workspace(key)
         if ws is not None:
             return ws
         dev, D, Fd, M = self.flat.device, self.D, self.F, S * N
@@ -161,7 +161,7 @@ class DetrEngine(FlatParams):
             ws["dqk"], ws["dv"] = e(M, 2 * D), e(M, D)
             ws["delta"] = e(N, self.H, S, dtype=f32)
             ws["dpos"] = e(M, D, dtype=f32)
-        self._ws[key] = ws
+        self._ws[key].append(ws)
         return ws
 
     def forward(self, src, pos, kpm, training):
@@ -409,17 +409,22 @@ class _DetrFn(torch.autograd.Function):
         def fresh():
             engine.bf16_fresh = False     # a captured forward must contain the fp32 -> bf16 parameter cast
         out, ws = engine.graphed(("enc_fwd", float(engine.p_drop)), S * N, [src, pos, kpm],
-                                 lambda s_, p_, k_: engine.forward(s_, p_, k_, training=True), before_capture=fresh)
+                                 lambda s_, p_, k_: engine.forward(s_, p_, k_, training=True), before_capture=fresh,
+                                 busy=lambda res: res[1].get("leased"))
         ctx.engine, ctx.ws, ctx.n_params, ctx.has_pos = engine, ws, len(params), pos is not None
+        ctx.lease = WorkspaceLease(ws)
         return out.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         eng, ws = ctx.engine, ctx.ws
         eng.prepare_grads()               # p.grad bookkeeping stays outside a captured backward
-        dsrc, dpos = eng.graphed(("enc_bwd", ws["S"], ws["N"], ws["p_drop"], ws["pos"] is not None, ws["kpm"] is not None), ws["M"],
+        dsrc, dpos = eng.graphed(("enc_bwd", id(ws), ws["p_drop"], ws["pos"] is not None, ws["kpm"] is not None), ws["M"],
                                  [grad_out], lambda g_: eng.backward(ws, g_))
-        return (None, None, dsrc.clone(), dpos.clone() if (ctx.has_pos and ctx.needs_input_grad[3]) else None) + (None,) * ctx.n_params
+        dsrc = dsrc.clone()
+        dpos = dpos.clone() if (ctx.has_pos and ctx.needs_input_grad[3]) else None
+        ctx.lease.release()
+        return (None, None, dsrc, dpos) + (None,) * ctx.n_params
 
 
 class TransformerEncoder(nn.Module):
@@ -543,7 +548,7 @@ class DetrDecoderEngine(DetrEngine):
 
     def workspace(self, Q, S, N, training):
         key = (Q, S, N, training)
-        ws = self._ws.get(key)
+        ws = self._free_workspace(key)
         if ws is not None:
             return ws
         dev, D, Fd, H = self.flat.device, self.D, self.F, self.H
@@ -573,7 +578,7 @@ class DetrDecoderEngine(DetrEngine):
             ws["dck"], ws["dcv"], ws["dmk"], ws["dmv"] = e(Ms, D), e(Ms, D), e(Ms, D), e(Ms, D)
             ws["delta"] = e(N, H, Q, dtype=f32)
             ws["dmem"], ws["dpos"] = e(Ms, D, dtype=f32), e(Ms, D, dtype=f32)
-        self._ws[key] = ws
+        self._ws[key].append(ws)
         return ws
 
     def forward(self, tgt, memory, mem_kpm, pos, query_pos, training):
@@ -886,19 +891,23 @@ class _DetrDecFn(torch.autograd.Function):
             engine.bf16_fresh = False
         out, ws = engine.graphed(("dec_fwd", float(engine.p_drop)), (tgt.shape[0] + memory.shape[0]) * tgt.shape[1],
                                  [tgt, memory, kpm, pos, query_pos],
-                                 lambda t_, m_, k_, p_, q_: engine.forward(t_, m_, k_, p_, q_, training=True), before_capture=fresh)
+                                 lambda t_, m_, k_, p_, q_: engine.forward(t_, m_, k_, p_, q_, training=True), before_capture=fresh,
+                                 busy=lambda res: res[1].get("leased"))
         ctx.engine, ctx.ws, ctx.n_params = engine, ws, len(params)
+        ctx.lease = WorkspaceLease(ws)
         return out.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         eng, ws = ctx.engine, ctx.ws
         eng.prepare_grads()
-        dt, dm, dp, dq = eng.graphed(("dec_bwd", ws["Q"], ws["S"], ws["N"], ws["p_drop"], ws["has_pos"], ws["has_qpos"], ws["kpm"] is not None),
+        dt, dm, dp, dq = eng.graphed(("dec_bwd", id(ws), ws["p_drop"], ws["has_pos"], ws["has_qpos"], ws["kpm"] is not None),
                                      ws["M"] + ws["Ms"], [grad_out], lambda g_: eng.backward(ws, g_))
         need = ctx.needs_input_grad
-        return (None, None, dt.clone() if need[2] else None, dm.clone() if need[3] else None,
-                dp.clone() if (dp is not None and need[4]) else None, dq.clone() if (dq is not None and need[5]) else None) + (None,) * ctx.n_params
+        res = (None, None, dt.clone() if need[2] else None, dm.clone() if need[3] else None,
+               dp.clone() if (dp is not None and need[4]) else None, dq.clone() if (dq is not None and need[5]) else None)
+        ctx.lease.release()
+        return res + (None,) * ctx.n_params
 
 
 class TransformerDecoder(nn.Module):

@@ -36,6 +36,24 @@ def pick_split_k(tiles, k_blocks, sms):
     return best
 
 
+class WorkspaceLease:
+    """Marks a workspace as holding the saved activations of a forward whose backward is still pending.  While the lease is alive
+    ``workspace()`` hands out another buffer set for the same shape, so a second forward (evaluation inside a training loop, two
+    forwards before one backward) cannot overwrite them — the semantics of PyTorch's saved tensors.  Released at the end of the
+    backward, or when the autograd node is freed without one."""
+
+    def __init__(self, ws):
+        self.ws = ws
+        ws["leased"] = True
+
+    def release(self):
+        if self.ws is not None:
+            self.ws["leased"] = False
+            self.ws = None
+
+    __del__ = release
+
+
 def getstate_without_engine(module):
     """``__getstate__`` of the drop-in modules: the engine (flat buffers' bookkeeping, workspaces, captured CUDA graphs) is a cache that
     is rebuilt lazily, so pickling (torch.save(model)) and copying never see it."""
@@ -99,6 +117,13 @@ class FlatParams:
         self.__dict__.setdefault("_train_graphs", {}).clear()
         self.bf16_fresh = False
         self._sms = torch.cuda.get_device_properties(device).multi_processor_count
+
+    def _free_workspace(self, key):
+        """The first buffer set of this shape that is not leased to a pending backward (None if there is none yet)."""
+        for ws in self._ws.setdefault(key, []):
+            if not ws.get("leased"):
+                return ws
+        return None
 
     def check_input(self, t, name="input"):
         """Inputs must live on the engine's CUDA device: the kernels take raw device pointers (a host tensor would be an illegal access)."""
@@ -180,10 +205,11 @@ class FlatParams:
             return False
         return mode == "1" or tokens <= self.AUTOGRAD_GRAPH_MAX_TOKENS
 
-    def graphed(self, key, tokens, inputs, fn, before_capture=None):
+    def graphed(self, key, tokens, inputs, fn, before_capture=None, busy=None):
         """``fn(*inputs)`` — eagerly the first time a (key, input shapes) combination is seen, captured into a CUDA graph the second
         time, replayed afterwards with the inputs copied into the graph's static buffers.  ``inputs`` are tensors or None; the result of
-        ``fn`` must only reference persistent workspace buffers.  Falls back to the eager call when graphs do not apply."""
+        ``fn`` must only reference persistent workspace buffers.  Falls back to the eager call when graphs do not apply, or when
+        ``busy(result)`` says the buffers the captured graph writes are leased to a pending backward."""
         if not self._autograd_graph_ok(tokens) or any(t is not None and not t.is_cuda for t in inputs):
             return fn(*inputs)
         graphs = self.__dict__.setdefault("_train_graphs", {})
@@ -205,6 +231,8 @@ class FlatParams:
                 res = fn(*static)
             ent = graphs[full_key] = (graph, static, res)
         graph, static, res = ent
+        if busy is not None and busy(res):
+            return fn(*inputs)
         for st, t in zip(static, inputs):
             if t is not None:
                 st.copy_(t)
@@ -229,10 +257,14 @@ class FlatParams:
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
             self.bf16_fresh = False      # the captured forward must contain the fp32 -> bf16 parameter cast
+            if self._free_workspace((x.shape[0], True)) is None:      # every buffer set is leased: stay eager, capture another time
+                return self.forward(x, training=True, want=want)
             with torch.cuda.graph(graph):
                 outs, ws = self.forward(static_in, training=True, want=want)
             ent = graphs[key] = (graph, static_in, outs, ws)
         graph, static_in, outs, ws = ent
+        if ws.get("leased"):             # its activations still wait for a backward: run eagerly on another buffer set
+            return self.forward(x, training=True, want=want)
         static_in.copy_(x)
         graph.replay()
         self.bf16_fresh = False          # the replay cast the parameters itself; a pending "fresh" mark must not outlive it
@@ -243,7 +275,7 @@ class FlatParams:
         if not self._autograd_graph_ok(ws["M"]) or any(g is not None and not g.is_cuda for g in grads):
             return self.backward(ws, grads, want=want)
         graphs = self.__dict__.setdefault("_train_graphs", {})
-        key = ("bwd", ws["B"], want, tuple(None if g is None else tuple(g.shape) for g in grads), ws.get("p_drop", 0.0), ws.get("p_attn", 0.0))
+        key = ("bwd", id(ws), want, tuple(None if g is None else tuple(g.shape) for g in grads), ws.get("p_drop", 0.0), ws.get("p_attn", 0.0))
         ent = graphs.get(key)
         if ent is None:
             graphs[key] = "warm"
@@ -389,7 +421,7 @@ class VitEngine(FlatParams):
     # ------------------------------------------------------------------ workspaces --------------------------------
     def workspace(self, B, training):
         key = (B, training)
-        ws = self._ws.get(key)
+        ws = self._free_workspace(key)
         if ws is not None:
             return ws
         dev = self.flat.device
@@ -434,7 +466,7 @@ class VitEngine(FlatParams):
             ws["stat_cls"] = [e(B, dtype=f32), e(B, dtype=f32)]
             ws["possum"] = e(S, D, dtype=f32)
             ws["dxp"] = e(B * self.P, D) if not self.tokens_mode else None
-        self._ws[key] = ws
+        self._ws[key].append(ws)
         return ws
 
     # ------------------------------------------------------------------ forward -----------------------------------

@@ -15,7 +15,7 @@ from typing import Callable, List, Optional
 import torch
 from torch import nn
 
-from .engine import VitEngine, getstate_without_engine
+from .engine import VitEngine, WorkspaceLease, getstate_without_engine
 
 
 class MLP(torch.nn.Sequential):
@@ -145,6 +145,7 @@ class _EncoderFn(torch.autograd.Function):
             images = images.contiguous().float()
         outs, ws = engine.forward_train(images, want=want)
         ctx.engine, ctx.ws, ctx.want, ctx.n_params = engine, ws, want, len(params)
+        ctx.lease = WorkspaceLease(ws)       # the saved activations live in ws until the backward has run
         ctx.set_materialize_grads(False)
         res = tuple(o.clone() for o in outs)
         return res if len(res) > 1 else res[0]
@@ -152,6 +153,7 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         ctx.engine.backward_train(ctx.ws, list(grads), want=ctx.want)
+        ctx.lease.release()
         return (None, None, None) + (None,) * ctx.n_params
 
 
@@ -162,12 +164,14 @@ class _TokensFn(torch.autograd.Function):
     def forward(ctx, engine, tokens, *params):
         outs, ws = engine.forward(tokens, training=True, want="features")
         ctx.engine, ctx.ws, ctx.n_params = engine, ws, len(params)
+        ctx.lease = WorkspaceLease(ws)
         return outs[0].clone()
 
     @staticmethod
     def backward(ctx, grad):
-        d = ctx.engine.backward(ctx.ws, [grad], want="features")
-        return (None, d.clone()) + (None,) * ctx.n_params
+        d = ctx.engine.backward(ctx.ws, [grad], want="features").clone()
+        ctx.lease.release()
+        return (None, d) + (None,) * ctx.n_params
 
 
 def run_engine(engine, images, want, params, module_training, dropout_ps):
