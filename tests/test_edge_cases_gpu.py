@@ -157,3 +157,28 @@ def test_detr_two_forwards_before_backward():
      + O.detr_encoder_forward(ref_sd, b, nhead=4, num_layers=2).square().mean()).backward()
     worst = max(((rel_l2(p.grad, ref_sd[n].grad), n) for n, p in enc.named_parameters()))
     assert worst[0] < 6e-2, worst      # post-norm DETR layers: the encoder tests' calibrated bound is ~5e-2 for the weights
+
+
+@pytest.mark.gpu
+def test_frozen_parameters_get_no_grad_and_are_not_updated():
+    """Fine-tuning the head on a frozen encoder: requires_grad=False parameters keep p.grad = None (as under autograd), so
+    optim.Adam(model.parameters()) (vanilla_vit.py:221) does not move them; the trainable ones still match the oracle."""
+    m, sd = _model()
+    for n, p in m.named_parameters():
+        if not n.startswith("heads."):
+            p.requires_grad_(False)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    x, y = O.seeded_images(6, 32, 97), O.seeded_labels(6, 10, 98)
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    for _ in range(2):
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(m(x.cuda()), y.cuda()).backward()
+        assert all((p.grad is None) == (not p.requires_grad) for p in m.parameters())
+        if _ == 0:
+            ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            torch.nn.functional.cross_entropy(O.vit_forward(ref_sd, x, **KW), y).backward()
+            for n in ("heads.head.weight", "heads.head.bias"):
+                assert rel_l2(dict(m.named_parameters())[n].grad, ref_sd[n].grad) < 3e-2
+        opt.step()
+    for n, p in m.named_parameters():
+        assert torch.equal(p, before[n]) == (not n.startswith("heads.")), n

@@ -306,29 +306,32 @@ class FlatParams:
         ops.cast_bf16(self.flat, self.flat_bf16)
 
     def prepare_grads(self):
-        """Makes every p.grad a view of the flat gradient buffer (zeroing it if grads were None)."""
+        """Makes p.grad of every TRAINABLE parameter a view of the flat gradient buffer (zeroing it if grads were None).  Frozen
+        parameters (requires_grad=False: fine-tuning a head on a frozen encoder) keep p.grad = None as under autograd, so an optimizer
+        built over model.parameters() leaves them alone; the kernels still write their slices of the flat buffer, which nobody reads."""
         base = self.flat_grad.data_ptr()
         need_zero = False
         foreign = []
-        for key, p in self._order:
+        trainable = [(key, p) for key, p in self._order if p.requires_grad]
+        for key, p in trainable:
             if p.grad is None:
                 need_zero = True
             elif p.grad.data_ptr() != base + 4 * self.offsets[key]:
                 foreign.append((key, p, p.grad))
         if need_zero or foreign:
-            all_none = all(p.grad is None for _, p in self._order)
+            all_none = all(p.grad is None for _, p in trainable)
             if all_none:
                 self.flat_grad.zero_()
             else:
                 # keep accumulated values of grads that already are views, zero the slices of the others
-                for key, p in self._order:
+                for key, p in trainable:
                     if p.grad is None:
                         o = self.offsets[key]
                         self.flat_grad[o:o + p.numel()].zero_()
             for key, p, gr in foreign:
                 o = self.offsets[key]
                 self.flat_grad[o:o + p.numel()].view(p.shape).copy_(gr)
-            for key, p in self._order:
+            for key, p in trainable:
                 o = self.offsets[key]
                 p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
 
