@@ -130,6 +130,9 @@ class FlatParams:
         if t is not None and (not t.is_cuda or t.device != self.flat.device):
             raise RuntimeError(f"vitb200: {name} is on {t.device} but the model is on {self.flat.device}; move it there first "
                                "(there is no CPU fallback)")
+        if torch.cuda.current_device() != self.flat.device.index:
+            raise RuntimeError(f"vitb200: the model lives on {self.flat.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                               "call torch.cuda.set_device(...) first (one process per GPU: the kernels launch on the current device)")
 
     def ensure_bound(self):
         p0 = self._order[0][1]
