@@ -182,3 +182,22 @@ def test_frozen_parameters_get_no_grad_and_are_not_updated():
         opt.step()
     for n, p in m.named_parameters():
         assert torch.equal(p, before[n]) == (not n.startswith("heads.")), n
+
+
+@pytest.mark.gpu
+def test_opt_in_split_k_inference_matches_default(monkeypatch):
+    """VITB200_INFER_SPLIT_K=1: residual GEMMs of small-batch eval forwards are split along K (reduce-add into residual + bias).  Same
+    numbers up to the fp32 summation order (and the bf16 re-quantisation that follows it)."""
+    import vitb200.engine as E
+    m, sd = _model(train=False)
+    x = O.seeded_images(3, 32, 99)
+    monkeypatch.setenv("VITB200_INFER_GRAPH", "0")
+    with torch.no_grad():
+        a = m(x.cuda())
+        fa = m.forward_features(x.cuda())
+        monkeypatch.setattr(E, "_INFER_SPLIT_K", True)
+        b = m(x.cuda())
+        fb = m.forward_features(x.cuda())
+    # a different fp32 summation order moves a few LayerNorm outputs across a bf16 rounding boundary: bf16-level, not 1e-6-level, agreement
+    assert rel_l2(b, a) < 5e-3 and rel_l2(fb, fa) < 5e-3
+    assert rel_l2(b, O.vit_forward(sd, x, **KW)) < 1.5e-2

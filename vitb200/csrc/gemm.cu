@@ -875,6 +875,7 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
         if (ep == VB_EPI_GELU && cd == VB_BF16) VB_LAUNCH(0, 0, VB_EPI_GELU, VB_BF16);
         if (ep == VB_EPI_RESIDUAL && cd == VB_F32) VB_LAUNCH(0, 0, VB_EPI_RESIDUAL, VB_F32);
         if (ep == VB_EPI_RELU && cd == VB_BF16) VB_LAUNCH(0, 0, VB_EPI_RELU, VB_BF16);
+        if (ep == VB_EPI_ACCUM && cd == VB_F32) VB_LAUNCH(0, 0, VB_EPI_ACCUM, VB_F32);   // split-K forward for latency-bound (small M) shapes
     } else if (am == 0 && bm == 1) {
         if (ep == VB_EPI_STORE && cd == VB_BF16) VB_LAUNCH(0, 1, VB_EPI_STORE, VB_BF16);
         if (ep == VB_EPI_STORE && cd == VB_F32) VB_LAUNCH(0, 1, VB_EPI_STORE, VB_F32);

@@ -14,6 +14,7 @@ import torch
 from . import ops
 
 import os
+_INFER_SPLIT_K = os.environ.get("VITB200_INFER_SPLIT_K", "0") == "1"
 _FUSED_QKV_COLSUM = os.environ.get("VITB200_FUSED_QKV_COLSUM", "1") != "0"   # A/B switch: in-kernel column sums of dq|dk|dv
 LAYER_ROLES = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
 _ALIGN = 64  # elements; keeps every parameter 256-byte (fp32) / 128-byte (bf16) aligned for TMA and float4 access
@@ -518,7 +519,15 @@ class VitEngine(FlatParams):
         pd, pa = ws.get("p_drop", 0.0), ws.get("p_attn", 0.0)
         ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"] if training else None, B=B, H=H, S=S,
                           tok_stride=1, batch_stride=S, dropout=(pa, ws["drop_seed"], self.drop_site(li, 3)) if pa > 0 else None)
-        if pd > 0:   # x1 = dropout(out_proj(o)) + x_in   (vanilla_vit.py:77-79)
+        # Small-batch inference: a residual GEMM over <= 4 row tiles occupies a handful of CTA pairs and walks K serially (fc2 of
+        # ViT-L: 4 pairs x 64 k-blocks), so it is split along K: out = residual + bias first, then split-K partial products are
+        # reduce-added into it (fp32, TMA reduce).
+        # Opt-in (VITB200_INFER_SPLIT_K=1): the reduce order of the partial sums is not fixed, so outputs differ in the last fp32 bit from
+        # call to call; the default keeps evaluation bit-reproducible.
+        split_small = _INFER_SPLIT_K and (not training) and pd == 0 and M <= 1024
+        if split_small:
+            self._residual_gemm_split_k(buf["o"], (li, "proj_w"), (li, "proj_b"), xin2, x12)
+        elif pd > 0:   # x1 = dropout(out_proj(o)) + x_in   (vanilla_vit.py:77-79)
             ops.gemm(buf["o"], self.w((li, "proj_w")), ws["tmp32"], bias=self.f((li, "proj_b")))
             ops.dropout_f32(ws["tmp32"], pd, ws["drop_seed"], self.drop_site(li, 0), aux=xin2, dst=x12)
         else:
@@ -528,7 +537,9 @@ class VitEngine(FlatParams):
         ops.gemm(buf["h2"], self.w((li, "fc1_w")), buf["a"] if training else None, C2=buf["g"], epilogue=ops.EPI_GELU,
                  bias=self.f((li, "fc1_b")))
         x2 = buf["x2"].view(M, D) if self.has_peg else xout2    # CPVT: x2 = x1 + y feeds the PEG; otherwise it is the block output
-        if pd > 0:   # mlp.2: the same mask scales gelu(x) and the saved gelu'(x), so the backward epilogue stays a single multiply
+        if split_small:
+            self._residual_gemm_split_k(buf["g"], (li, "fc2_w"), (li, "fc2_b"), x12, x2)
+        elif pd > 0:   # mlp.2: the same mask scales gelu(x) and the saved gelu'(x), so the backward epilogue stays a single multiply
             ops.dropout_bf16_pair(buf["g"], buf["a"], pd, ws["drop_seed"], self.drop_site(li, 1))
             ops.gemm(buf["g"], self.w((li, "fc2_w")), ws["tmp32"], bias=self.f((li, "fc2_b")))
             ops.dropout_f32(ws["tmp32"], pd, ws["drop_seed"], self.drop_site(li, 2), aux=x12, dst=x2)   # mlp.4 + residual (:83)
@@ -536,6 +547,15 @@ class VitEngine(FlatParams):
             ops.gemm(buf["g"], self.w((li, "fc2_w")), x2, epilogue=ops.EPI_RESIDUAL, bias=self.f((li, "fc2_b")), aux=x12)
         if self.has_peg:   # cpvt.py:93-96: x = x + y; x = peg(x); return x + y   (y = x2 - x1 inside the kernel)
             ops.dwconv_fwd(buf["x2"], self.f((li, "peg_w")), self.f((li, "peg_b")), x_out, n_prefix=self.n_prefix, sub=buf["x1"])
+
+    def _residual_gemm_split_k(self, A, wkey, bkey, residual, out):
+        """out = residual + bias + A W^T with the contraction split over the idle CTA pairs (VB_EPI_ACCUM into the pre-filled output)."""
+        W = self.w(wkey)
+        tiles = -(-A.shape[0] // 256) * -(-W.shape[0] // 256)
+        k_blocks = -(-W.shape[1] // 64)
+        split = max(1, min(k_blocks // 4, max(1, self._sms // 2) // tiles))
+        ops.add_rows_bcast(residual, self.f(bkey).view(1, -1), out)
+        ops.gemm(A, W, out, epilogue=ops.EPI_ACCUM, split_k=split)
 
     def forward(self, images, *, training, want):
         """want: 'logits' (head(s) on the prefix token rows) or 'features' ([B,S,D] fp32 after the final norm).
