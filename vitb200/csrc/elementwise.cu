@@ -24,20 +24,28 @@ __global__ void cast_kernel(const float4* __restrict__ src, uint2* __restrict__ 
 // ---- images [B,C,H,W] fp32 -> patch matrix [B, (H/p)*(W/p), C*p*p] bf16, k = c*p*p + i*p + j ---------------
 // (the K ordering of conv_proj.weight.reshape(D, -1): vanilla_vit.py:129,196)
 __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int p) {
-    const long long total4 = (long long)B * C * H * W / 4;
+    // One thread per 16 bytes of OUTPUT (8 consecutive pixels of one patch row): stores are fully coalesced along k, loads are 32-byte
+    // sectors of an image row (p % 8 == 0), or one thread per 8 bytes of output when only p % 4 == 0 holds.
     const int nw = W / p, np = (H / p) * nw, kdim = C * p * p;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
-        const long long e = t * 4;
-        const int x = e % W;
-        const long long r = e / W;
-        const int y = r % H;
-        const long long bc = r / H;
-        const int c = bc % C;
-        const long long b = bc / C;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(img) + t);
-        const int ph = y / p, i = y - ph * p, pw = x / p, j = x - pw * p;
-        const long long o = (b * np + ph * nw + pw) * kdim + c * p * p + i * p + j;
-        *reinterpret_cast<uint2*>(out + o) = pack4(v.x, v.y, v.z, v.w);
+    const int vec = (p % 8 == 0) ? 8 : 4;
+    const long long total = (long long)B * C * H * W / vec;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long o = t * vec;                   // flat output index = (b * np + patch) * kdim + k
+        const int k = (int)(o % kdim);
+        const long long bp = o / kdim;
+        const int patch = (int)(bp % np);
+        const long long b = bp / np;
+        const int c = k / (p * p), ij = k - c * p * p, i = ij / p, j = ij - i * p;
+        const int ph = patch / nw, pw = patch - ph * nw;
+        const float* src = img + ((b * C + c) * H + (ph * p + i)) * (long long)W + pw * p + j;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+        if (vec == 8) {
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            const uint2 lo = pack4(v0.x, v0.y, v0.z, v0.w), hi = pack4(v1.x, v1.y, v1.z, v1.w);
+            *reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+            *reinterpret_cast<uint2*>(out + o) = pack4(v0.x, v0.y, v0.z, v0.w);
+        }
     }
 }
 
@@ -107,11 +115,14 @@ __global__ void embed_bwd_reduce_kernel(const float* __restrict__ dx, float* __r
 }
 // pass 2: dpos += possum; dtok_t += possum[t] (t < n_prefix); dbias += sum_{s >= n_prefix} possum[s]
 __global__ void embed_bwd_finalize_kernel(const float* __restrict__ possum, float* __restrict__ dpos, float* __restrict__ dtok0,
-                                          float* __restrict__ dtok1, float* __restrict__ dbias, int S, int D, int n_prefix) {
+                                          float* __restrict__ dtok1, float* __restrict__ dbias, int S, int D, int n_prefix, int rows_per_block) {
+    // grid (ceil(D / 128), ceil(S / rows_per_block)): a thread owns one column of a few positions (the serial 197-step walk of a
+    // 6-block grid was latency-bound); the conv-bias partial sums of the position chunks meet in one atomicAdd per thread
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= D) return;
+    const int s0 = blockIdx.y * rows_per_block, s1 = min(S, s0 + rows_per_block);
     float bsum = 0.f;
-    for (int s = 0; s < S; ++s) {
+    for (int s = s0; s < s1; ++s) {
         const float v = possum[(long long)s * D + c];
         if (dpos) dpos[(long long)s * D + c] += v;
         if (s < n_prefix) {
@@ -121,7 +132,7 @@ __global__ void embed_bwd_finalize_kernel(const float* __restrict__ possum, floa
             bsum += v;
         }
     }
-    if (dbias) dbias[c] += bsum;
+    if (dbias && s1 > n_prefix) atomicAdd(dbias + c, bsum);
 }
 
 // ---- out[r, :] = x[r, :] + pos[r % period, :]  (Encoder.forward on caller-supplied tokens: input + pos_embedding, vanilla_vit.py:104)
@@ -192,8 +203,9 @@ extern "C" int vb_patchify(const float* images, void* patches_bf16, int32_t B, i
     VB_REQUIRE(images && patches_bf16 && B > 0 && C > 0 && patch > 0, "patchify: bad arguments");
     VB_REQUIRE(H % patch == 0 && W % patch == 0 && patch % 4 == 0, "patchify: H, W must be multiples of patch and patch of 4");
     VB_REQUIRE(((uintptr_t)images & 15) == 0 && ((uintptr_t)patches_bf16 & 7) == 0, "patchify: misaligned pointers");
-    const long long total4 = (long long)B * C * H * W / 4;
-    patchify_kernel<<<grid_for(total4, 256), 256, 0, as_stream(stream)>>>(images, reinterpret_cast<__nv_bfloat16*>(patches_bf16), B, C, H, W, patch);
+    const long long items = (long long)B * C * H * W / (patch % 8 == 0 ? 8 : 4);
+    VB_REQUIRE(patch % 8 != 0 || ((uintptr_t)patches_bf16 & 15) == 0, "patchify: output must be 16-byte aligned");
+    patchify_kernel<<<grid_for(items, 256), 256, 0, as_stream(stream)>>>(images, reinterpret_cast<__nv_bfloat16*>(patches_bf16), B, C, H, W, patch);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }
@@ -243,7 +255,8 @@ extern "C" int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_pat
     embed_bwd_reduce_kernel<<<dim3(S, chunks), threads, 0, st>>>(dx, possum_scratch, reinterpret_cast<__nv_bfloat16*>(dx_patches_bf16), B, S,
                                                                 D, n_prefix, bpc);
     VB_CUDA_CHECK(cudaGetLastError());
-    embed_bwd_finalize_kernel<<<(D + 127) / 128, 128, 0, st>>>(possum_scratch, dpos, dtok0, dtok1, dbias, S, D, n_prefix);
+    const int rpb = 8;
+    embed_bwd_finalize_kernel<<<dim3((D + 127) / 128, (S + rpb - 1) / rpb), 128, 0, st>>>(possum_scratch, dpos, dtok0, dtok1, dbias, S, D, n_prefix, rpb);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }
