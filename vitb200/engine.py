@@ -187,7 +187,7 @@ class FlatParams:
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
             self.bf16_fresh = False      # the captured forward must contain the fp32 -> bf16 parameter cast
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 outs, _ = self.forward(static_in, training=False, want=want)
             ent = graphs[key] = (graph, static_in, outs)
         graph, static_in, outs = ent
@@ -201,6 +201,8 @@ class FlatParams:
     # those calls are launch-bound, so each is replayed from its own CUDA graph: first call per shape eager, second captured, later
     # calls copy the batch / the output gradients into static buffers and replay.  Off when a data-parallel reducer is attached (its
     # collectives are issued from Python between kernels).  VITB200_AUTOGRAD_GRAPH=0 / 1 forces it off / on for every size.
+    # Captures use capture_error_mode="thread_local": a DataLoader pin-memory thread allocating while the autograd thread captures
+    # must not be failed by CUDA's global capture mode.
     AUTOGRAD_GRAPH_MAX_TOKENS = int(os.environ.get("VITB200_AUTOGRAD_GRAPH_MAX_TOKENS", "20000"))
 
     def _autograd_graph_ok(self, tokens):
@@ -231,7 +233,7 @@ class FlatParams:
             if before_capture is not None:
                 before_capture()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 res = fn(*static)
             ent = graphs[full_key] = (graph, static, res)
         graph, static, res = ent
@@ -263,7 +265,7 @@ class FlatParams:
             self.bf16_fresh = False      # the captured forward must contain the fp32 -> bf16 parameter cast
             if self._free_workspace((x.shape[0], True)) is None:      # every buffer set is leased: stay eager, capture another time
                 return self.forward(x, training=True, want=want)
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 outs, ws = self.forward(static_in, training=True, want=want)
             ent = graphs[key] = (graph, static_in, outs, ws)
         graph, static_in, outs, ws = ent
@@ -292,7 +294,7 @@ class FlatParams:
                     sg.copy_(g)
             torch.cuda.synchronize(self.flat.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 res = self.backward(ws, static_g, want=want)
             ent = graphs[key] = (graph, static_g, res)
         graph, static_g, res = ent

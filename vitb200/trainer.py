@@ -151,7 +151,7 @@ class Trainer:
                 return self._loss
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 self._step_body(s_img, s_lab)
             entry = (graph, s_img, s_lab)
             self._graphs[key] = entry
