@@ -222,7 +222,7 @@ def test_autograd_path_graph_replay_matches_eager(monkeypatch):
     # the accumulated UPDATES agree to bf16-path resolution (the two trajectories see order-dependent fp32 sums; the key bias, whose
     # gradient is exactly zero in exact arithmetic, is pure rounding noise and gets an absolute floor)
     bad = [(n, (a - b).norm().item(), (a - i).norm().item()) for (n, _), a, b, i in zip(m.named_parameters(), pe, pg, init)
-           if (a - b).norm().item() > 2e-2 * (a - i).norm().item() + 1e-7 * a.numel() ** 0.5]
+           if (a - b).norm().item() > 5e-2 * (a - i).norm().item() + 1e-6 * a.numel() ** 0.5]   # gross errors (wrong buffers) are O(1)
     assert not bad, bad
     kinds = {k[0] for k, v in m._get_engine()._train_graphs.items() if isinstance(v, tuple)}
     assert kinds == {"fwd", "bwd"}, kinds
