@@ -33,6 +33,7 @@ img = torch.randn(B, 3, 224, 224, device=dev)
 pat = torch.empty(B, 196, 768, device=dev, dtype=torch.bfloat16)
 x3, o3 = x.view(B, S, D), torch.empty(B, S, D, device=dev)
 w9, b9 = torch.randn(D, 1, 3, 3, device=dev), torch.randn(D, device=dev)
+dw9, db9 = torch.zeros(D * 9, device=dev), torch.zeros(D, device=dev)
 o_bf, do_bf = torch.randn(M, D, device=dev).bfloat16(), torch.randn(M, D, device=dev).bfloat16()
 qkv = torch.randn(M, 3 * D, device=dev).bfloat16()
 lse, delta = torch.zeros(B, H, S, device=dev), torch.empty(B, H, S, device=dev)
@@ -47,7 +48,8 @@ def run():
               lambda: ops.adam_step(p, gr, m1, m2, p_bf, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=0, step_counter=step),
               lambda: ops.patchify(img, pat, 16),
               lambda: ops.dwconv_fwd(x3, w9, b9, o3, n_prefix=1),
-              lambda: ops.dwconv_bwd_data(x3, w9, n_prefix=1, dx=o3, sum_bf16=y_bf)):
+              lambda: ops.dwconv_bwd_data(x3, w9, n_prefix=1, dx=o3, sum_bf16=y_bf),
+              lambda: ops.dwconv_bwd_weight(x3, o3, dw9, db9, n_prefix=1)):
         flush.zero_()          # evict the 126 MB L2 so that every kernel streams from HBM
         f()
 
