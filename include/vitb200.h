@@ -177,6 +177,10 @@ VB_API int vb_add_rows_bcast(const float* x, const float* pos, float* out, int64
 VB_API int vb_add3(const float* a, const void* b_bf16, const void* c_bf16, float* out, float* accum, int64_t n, void* stream);
 VB_API int vb_patchify(const float* images, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
                        void* stream);
+/* inverse of vb_patchify: d images [B,C,H,W] fp32 from the bf16 patch-matrix gradient (input gradient of conv_proj, autograd of
+ * vanilla_vit.py:196) */
+VB_API int vb_unpatchify(const void* dpatches_bf16, float* dimages, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
+                         void* stream);
 VB_API int vb_token_rows(float* x, const float* tok0, const float* tok1, const float* pos, int32_t B, int32_t S, int32_t D,
                          int32_t n_prefix, void* stream);
 VB_API int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, float* out_accum, void* stream);

@@ -201,3 +201,26 @@ def test_opt_in_split_k_inference_matches_default(monkeypatch):
     # a different fp32 summation order moves a few LayerNorm outputs across a bf16 rounding boundary: bf16-level, not 1e-6-level, agreement
     assert rel_l2(b, a) < 1e-2 and rel_l2(fb, fa) < 1e-2
     assert rel_l2(b, O.vit_forward(sd, x, **KW)) < 1.5e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frozen", [False, True])
+def test_input_image_gradients(frozen):
+    """d loss / d images (what autograd gives the reference's conv_proj when the batch requires grad: saliency maps, adversarial
+    examples), also with every parameter frozen."""
+    m, sd = _model()
+    if frozen:
+        for p in m.parameters():
+            p.requires_grad_(False)
+    x, y = O.seeded_images(5, 32, 101), O.seeded_labels(5, 10, 102)
+    xc = x.cuda().requires_grad_(True)
+    for _ in range(3):                      # eager, captured, replayed
+        xc.grad = None
+        torch.nn.functional.cross_entropy(m(xc), y.cuda()).backward()
+    xr = x.clone().requires_grad_(True)
+    ref_sd = {k: v.clone().requires_grad_(not frozen) for k, v in sd.items()}
+    torch.nn.functional.cross_entropy(O.vit_forward(ref_sd, xr, **KW), y).backward()
+    assert xc.grad is not None and xc.grad.shape == x.shape
+    assert rel_l2(xc.grad, xr.grad) < 3e-2, rel_l2(xc.grad, xr.grad)
+    if frozen:
+        assert all(p.grad is None for p in m.parameters())

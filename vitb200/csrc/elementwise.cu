@@ -49,6 +49,25 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
     }
 }
 
+// ---- inverse of patchify: d images [B,C,H,W] fp32 <- d patches [B, (H/p)(W/p), C*p*p] bf16 (the input gradient of conv_proj) ----
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ dpat, float* __restrict__ dimg, int B, int C, int H, int W, int p) {
+    const int nw = W / p, np = (H / p) * nw, kdim = C * p * p;
+    const long long total = (long long)B * C * H * W / 4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long o = t * 4;                     // flat patch-matrix index (b * np + patch) * kdim + k
+        const int k = (int)(o % kdim);
+        const long long bp = o / kdim;
+        const int patch = (int)(bp % np);
+        const long long b = bp / np;
+        const int c = k / (p * p), ij = k - c * p * p, i = ij / p, j = ij - i * p;
+        const int ph = patch / nw, pw = patch - ph * nw;
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(dpat + o));
+        float* dst = dimg + ((b * C + c) * H + (ph * p + i)) * (long long)W + pw * p + j;
+        *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u),
+                                                      __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
+    }
+}
+
 // ---- prefix token rows: x[b, t, :] = token_t + pos[t]  (vanilla_vit.py:202-203 + :104) ----------------------
 __global__ void token_rows_kernel(float* __restrict__ x, const float* __restrict__ tok0, const float* __restrict__ tok1,
                                   const float* __restrict__ pos, int B, int S, int D, int n_prefix) {
@@ -206,6 +225,19 @@ extern "C" int vb_patchify(const float* images, void* patches_bf16, int32_t B, i
     const long long items = (long long)B * C * H * W / (patch % 8 == 0 ? 8 : 4);
     VB_REQUIRE(patch % 8 != 0 || ((uintptr_t)patches_bf16 & 15) == 0, "patchify: output must be 16-byte aligned");
     patchify_kernel<<<grid_for(items, 256), 256, 0, as_stream(stream)>>>(images, reinterpret_cast<__nv_bfloat16*>(patches_bf16), B, C, H, W, patch);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_unpatchify(const void* dpatches_bf16, float* dimages, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
+                             void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(dpatches_bf16 && dimages && B > 0 && C > 0 && patch > 0, "unpatchify: bad arguments");
+    VB_REQUIRE(H % patch == 0 && W % patch == 0 && patch % 4 == 0, "unpatchify: H, W must be multiples of patch and patch of 4");
+    VB_REQUIRE(((uintptr_t)dimages & 15) == 0 && ((uintptr_t)dpatches_bf16 & 7) == 0, "unpatchify: misaligned pointers");
+    unpatchify_kernel<<<grid_for((long long)B * C * H * W / 4, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dpatches_bf16), dimages, B, C, H, W, patch);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

@@ -276,16 +276,17 @@ class FlatParams:
         self.bf16_fresh = False          # the replay cast the parameters itself; a pending "fresh" mark must not outlive it
         return outs, ws
 
-    def backward_train(self, ws, grads, *, want):
+    def backward_train(self, ws, grads, *, want, input_grad=False):
         """backward(ws, grads, want=want) for the autograd node (graph replay under the same conditions as forward_train)."""
         if not self._autograd_graph_ok(ws["M"]) or any(g is not None and not g.is_cuda for g in grads):
-            return self.backward(ws, grads, want=want)
+            return self.backward(ws, grads, want=want, input_grad=input_grad)
         graphs = self.__dict__.setdefault("_train_graphs", {})
-        key = ("bwd", id(ws), want, tuple(None if g is None else tuple(g.shape) for g in grads), ws.get("p_drop", 0.0), ws.get("p_attn", 0.0))
+        key = ("bwd", id(ws), want, tuple(None if g is None else tuple(g.shape) for g in grads), ws.get("p_drop", 0.0), ws.get("p_attn", 0.0),
+               input_grad)
         ent = graphs.get(key)
         if ent is None:
             graphs[key] = "warm"
-            return self.backward(ws, grads, want=want)
+            return self.backward(ws, grads, want=want, input_grad=input_grad)
         self.prepare_grads()             # p.grad bookkeeping (and the zeroing it may need) stays outside the graph
         if ent == "warm":
             static_g = [None if g is None else torch.empty(g.shape, device=g.device, dtype=torch.float32) for g in grads]
@@ -295,7 +296,7 @@ class FlatParams:
             torch.cuda.synchronize(self.flat.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                res = self.backward(ws, static_g, want=want)
+                res = self.backward(ws, static_g, want=want, input_grad=input_grad)
             ent = graphs[key] = (graph, static_g, res)
         graph, static_g, res = ent
         for sg, g in zip(static_g, grads):
@@ -607,9 +608,11 @@ class VitEngine(FlatParams):
         return outs, ws
 
     # ------------------------------------------------------------------ backward ----------------------------------
-    def backward(self, ws, grads, *, want, dlogits_ready=False):
+    def backward(self, ws, grads, *, want, dlogits_ready=False, input_grad=False):
         """grads: list matching forward outputs (fp32). Accumulates into the flat gradient buffer.
-        dlogits_ready: ws["dlogits"][t] already holds the bf16 logits gradients (fused cross-entropy path)."""
+        dlogits_ready: ws["dlogits"][t] already holds the bf16 logits gradients (fused cross-entropy path).
+        input_grad: also return d loss / d images ([B,3,H,W] fp32, workspace-owned) — what autograd gives the reference's conv_proj
+        when the batch requires grad (saliency maps, adversarial examples)."""
         self.prepare_grads()
         B, S, D, M, L = ws["B"], self.S, self.D, ws["M"], self.L
         d, d_bf, dh = ws["d"], ws["d_bf16"], ws["dh"]
@@ -747,6 +750,14 @@ class VitEngine(FlatParams):
         pat = ws["patches"].view(B * self.P, self.Kp_ld)[:, :self.Kp]
         self._wgrad(ws["dxp"], pat, ("g", "conv_w"))
         self._seg_done(L + 1)
+        if input_grad:     # d patches = d tokens . conv_w (dgrad GEMM), scattered back to the image layout
+            if "dimg" not in ws:
+                ws["dpat"] = torch.empty(B * self.P, self.Kp_ld, device=d.device, dtype=torch.bfloat16)
+                ws["dimg"] = torch.empty(B, 3, self.image_size, self.image_size, device=d.device, dtype=torch.float32)
+            ops.gemm(ws["dxp"], self.w(("g", "conv_w")), ws["dpat"], b_major=1)
+            ops.unpatchify(ws["dpat"], ws["dimg"], self.p)
+            return ws["dimg"]
+        return None
 
     # The head bias has num_classes entries, but the column-sum kernel works on the 8-padded logits-gradient
     # buffer; sum into a padded scratch and fold the valid part into the gradient.

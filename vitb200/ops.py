@@ -195,6 +195,14 @@ def patchify(images, out, patch):
     _lib.check(lib.vb_patchify(images.data_ptr(), out.data_ptr(), B, C, H, W, patch, _stream()), "vb_patchify")
 
 
+def unpatchify(dpatches, dimages, patch):
+    """dimages [B,3,H,W] fp32 <- dpatches [B, P, 3*p*p] bf16 (contiguous): the inverse of patchify."""
+    lib = _lib.load()
+    B, C, H, W = dimages.shape
+    assert dimages.dtype == torch.float32 and dimages.is_contiguous() and dpatches.dtype == torch.bfloat16 and dpatches.is_contiguous()
+    _lib.check(lib.vb_unpatchify(dpatches.data_ptr(), dimages.data_ptr(), B, C, H, W, patch, _stream()), "vb_unpatchify")
+
+
 def token_rows(x, tok0, tok1, pos, n_prefix):
     lib = _lib.load()
     B, S, D = x.shape

@@ -152,9 +152,10 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        ctx.engine.backward_train(ctx.ws, list(grads), want=ctx.want)
+        dimg = ctx.engine.backward_train(ctx.ws, list(grads), want=ctx.want, input_grad=ctx.needs_input_grad[2])
+        dimg = dimg.clone() if dimg is not None else None
         ctx.lease.release()
-        return (None, None, None) + (None,) * ctx.n_params
+        return (None, None, dimg) + (None,) * ctx.n_params
 
 
 class _TokensFn(torch.autograd.Function):
@@ -175,7 +176,7 @@ class _TokensFn(torch.autograd.Function):
 
 
 def run_engine(engine, images, want, params, module_training, dropout_ps):
-    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or images.requires_grad)
     # dropout is active in train() mode only, as in nn.Dropout / nn.MultiheadAttention (vanilla_vit.py:38,42,67-68,94)
     engine.p_drop, engine.p_attn = (float(dropout_ps[0]), float(dropout_ps[1])) if module_training else (0.0, 0.0)
     if needs_grad:
