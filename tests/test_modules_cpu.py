@@ -66,3 +66,14 @@ def test_dropout_sites_are_distinct():
     assert len(sites) == 24 * 4 + 1
     assert len({DetrDecoderEngine.drop_site(li, s) for li in range(6) for s in range(6)}) == 36
     assert DetrEngine.drop_site(2, 3) == DetrDecoderEngine.drop_site(2, 3)
+
+
+def test_fused_trainer_refuses_frozen_parameters():
+    """The fused flat Adam updates every parameter; frozen ones must fail loudly instead of being trained silently."""
+    import pytest
+    from vitb200.trainer import FusedAdam
+    from vitb200.vit import ViT
+    m = ViT(32, 4, 2, 4, 256, 512, 0.0, 0.0, 10)
+    m.encoder.pos_embedding.requires_grad_(False)
+    with pytest.raises(NotImplementedError):
+        FusedAdam(m)._ensure_state()

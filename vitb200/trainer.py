@@ -24,6 +24,10 @@ class FusedAdam:
 
     def _ensure_state(self):
         eng = self.engine
+        frozen = [k for k, p in eng._order if not p.requires_grad]
+        if frozen:
+            raise NotImplementedError(f"vitb200 FusedAdam updates the whole flat parameter buffer; {len(frozen)} parameters are frozen "
+                                      "(requires_grad=False) — use the autograd path with a torch.optim optimizer for partial fine-tuning")
         eng.ensure_bound()
         if self.exp_avg is None or self.exp_avg.device != eng.flat.device or self.exp_avg.numel() != eng.total:
             self.exp_avg = torch.zeros_like(eng.flat)
