@@ -224,3 +224,23 @@ def test_input_image_gradients(frozen):
     assert rel_l2(xc.grad, xr.grad) < 3e-2, rel_l2(xc.grad, xr.grad)
     if frozen:
         assert all(p.grad is None for p in m.parameters())
+
+
+@pytest.mark.gpu
+def test_out_of_range_label_gives_nan_loss_not_an_illegal_read():
+    from vitb200 import ops
+    z = torch.randn(4, 10, device="cuda")
+    y = torch.tensor([1, 2, 10, 3], device="cuda")            # 10 is out of range for 10 classes
+    loss = torch.zeros(1, device="cuda")
+    dz = torch.empty(4, 10, device="cuda")
+    ops.cross_entropy(z, y, loss, weight=0.25, dlogits_f32=dz)
+    torch.cuda.synchronize()
+    assert torch.isnan(loss).all()
+    loss.zero_()
+    ops.distill_loss(z, z.clone(), z.clone(), y, loss, kind="hard", alpha=0.5, tau=1.0, dlogits_f32=dz, dlogits_kd_f32=dz.clone())
+    torch.cuda.synchronize()
+    assert torch.isnan(loss).all()
+    y[2] = 9
+    loss.zero_()
+    ops.cross_entropy(z, y, loss, weight=0.25, dlogits_f32=dz)
+    assert abs(loss.item() - torch.nn.functional.cross_entropy(z, y).item()) < 1e-5

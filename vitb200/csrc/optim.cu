@@ -30,10 +30,12 @@ __global__ void ce_kernel(const float* __restrict__ logits, long long ld, const 
     for (int c = lane; c < C; c += 32) s += __expf(z[c] - mx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const int y = (int)labels[row];
+    int y = (int)labels[row];
+    const bool bad_label = y < 0 || y >= C;      // PyTorch raises a device assert here; an out-of-range label must not read out of bounds
+    if (bad_label) y = 0;
     const float lse = mx + __logf(s);
     if (lane == 0) {
-        atomicAdd(loss_accum, weight * (lse - z[y]));
+        atomicAdd(loss_accum, bad_label ? __int_as_float(0x7fc00000) : weight * (lse - z[y]));   // NaN loss: loud, not silent
         if (correct_accum && arg == y) atomicAdd(correct_accum, 1);
     }
     const float inv = 1.f / s;
@@ -78,10 +80,12 @@ __global__ void distill_loss_kernel(const float* __restrict__ logits, long long 
     if (row >= B) return;
     const float invB = 1.f / (float)B;
     const float* z = logits + (long long)row * ld;
-    const int y = (int)labels[row];
+    int y = (int)labels[row];
+    const bool bad_label = y < 0 || y >= C;      // as in ce_kernel: no out-of-bounds read, NaN loss
+    if (bad_label) y = 0;
     // base criterion on the class-token logits
     const WarpStat a = warp_softmax_stat(z, C, 1.f, lane);
-    float loss = (1.f - alpha) * invB * (a.mx + __logf(a.sum) - z[y]);
+    float loss = bad_label ? __int_as_float(0x7fc00000) : (1.f - alpha) * invB * (a.mx + __logf(a.sum) - z[y]);
     {
         const float w = grad_scale * (1.f - alpha) * invB, inv = 1.f / a.sum;
         for (int c = lane; c < C; c += 32) {
