@@ -11,7 +11,7 @@ What is rebound:
   models.object_detection.transformer.{TransformerEncoderLayer, TransformerEncoder}      (transformer.py:98-115,192-247)
   models.object_detection.transformer.{TransformerDecoderLayer, TransformerDecoder}      (transformer.py:66-95,118-189)
   timm.models.deit.VisionTransformerDistilled (a shim module, since timm is what deit.py:4 imports)
-  models.image_classification.{cpe_vit.CPEViT, cpvt.CPVT, cpvt_gap.CPVTGAP} (+ their ConditionalPositionalEncoding)
+  models.image_classification.{cpe_vit.CPEViT, cpvt.CPVT, cpvt_gap.CPVTGAP}
 The rebound ``ViT`` subclasses the reference's ``BaseTransformer`` (base.py:12) and borrows the reference's
 ``ViT.train_model`` function object (vanilla_vit.py:217), so the training loop that runs is the reference's own code.
 Nothing is copied from the reference tree.
@@ -118,7 +118,7 @@ def install(reference_root, stub_missing=True):
     except Exception:   # optional: its other imports (token_performer, load_data) may be unavailable
         pass
     # CPE-ViT / CPVT / CPVT-GAP: the model classes are rebound and keep the reference's own train_model functions
-    # (cpe_vit.py:214, cpvt.py:215, cpvt_gap.py:216); their helper classes are parameter containers here.
+    # (cpe_vit.py:214, cpvt.py:215, cpvt_gap.py:216); the reference's helper classes (its own EncoderBlock / PEG) are left untouched.
     from . import cpvt as our_cpvt
     rebound = {}
     for modname, clsname in (("cpe_vit", "CPEViT"), ("cpvt", "CPVT"), ("cpvt_gap", "CPVTGAP")):
@@ -133,7 +133,6 @@ def install(reference_root, stub_missing=True):
             new_cls.train_model = tm
         new_cls.__module__ = ref_mod.__name__
         setattr(ref_mod, clsname, new_cls)
-        ref_mod.ConditionalPositionalEncoding = our_cpvt.ConditionalPositionalEncoding
         rebound[clsname] = new_cls
     return {**rebound, "ViT": ViT, "TransformerEncoder": our_detr.TransformerEncoder, "TransformerEncoderLayer": our_detr.TransformerEncoderLayer,
             "VisionTransformerDistilled": our_deit.VisionTransformerDistilled}
