@@ -1,4 +1,5 @@
 """Shared helpers for the parity tests: relative-L2 comparison and oracle runs (tests may import oracle/)."""
+import contextlib
 import os
 import sys
 
@@ -9,6 +10,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle import vit_oracle as O  # noqa: E402
+
+
+@contextlib.contextmanager
+def strict_fp32():
+    """Runs the oracle's PyTorch operators on the GPU in true fp32 (no TF32 in matmuls or cuDNN convolutions) — used for the parity
+    cases at benchmark size, where the CPU would need minutes."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.get_float32_matmul_precision())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old[0], old[1]
+        torch.set_float32_matmul_precision(old[2])
 
 
 def rel_l2(a, b):

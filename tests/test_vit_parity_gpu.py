@@ -111,6 +111,26 @@ def test_device_prefetcher_delivers_every_batch_in_order():
 
 
 @pytest.mark.gpu
+def test_device_prefetcher_host_running_ahead_of_the_gpu():
+    """with a sync-free consumer the host runs several batches ahead of the GPU; the pinned staging buffer of a
+    slot must not be overwritten before its previous (GPU-delayed) H2D copy has left it.  The consumer queues ~20 ms of GPU work
+    per batch and never synchronises, the loader is instantaneous."""
+    from vitb200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(6)
+    batches = [(torch.full((64, 3, 64, 64), float(i)) + torch.randn(64, 3, 64, 64, generator=g) * 0.01, torch.full((64,), i)) for i in range(12)]
+    heavy = torch.randn(8192, 8192, device="cuda")
+    sums, labs = [], []
+    for img, lab in DevicePrefetcher(batches):
+        for _ in range(6):
+            heavy = torch.tanh(heavy @ heavy * 1e-4)       # keeps the compute stream far behind the host
+        sums.append(img.mean() + 0 * heavy[0, 0])
+        labs.append(lab.float().mean())
+    torch.cuda.synchronize()
+    for i, (s, l) in enumerate(zip(sums, labs)):
+        assert abs(s.item() - i) < 0.01 and l.item() == i, (i, s.item(), l.item())
+
+
+@pytest.mark.gpu
 def test_standalone_encoder_matches_oracle():
     """vitb200.vit.Encoder used on its own (vanilla_vit.py:88-106; T2T_ViT's identical copy t2t_vit.py:89-110): tokens in,
     normalised tokens out, gradients for the tokens and every parameter."""

@@ -161,6 +161,20 @@ def correctness():
         ok &= case("wgrad split 4", 1000, 768, 4000, 1, 1, ops.EPI_ACCUM, ops.F32, split=4, direct=direct)
         ok &= case("many tiles (persistence)", 20000, 768, 768, 0, 0, ops.EPI_STORE, ops.BF16, bias=True, direct=direct)
         ok &= batched_case(direct)
+    # ViT-L/16 (D = 1024, F = 4096: BASELINE.json configs[3]), DeiT-S (D = 384) and DeiT-tiny (D = 192, an odd multiple of 64:
+    # utils/args.py:43-45) shapes through the production (TMA-store) epilogues
+    for D, Fd in ((1024, 4096), (384, 1536), (192, 768)):
+        M = 8 * 197 if D > 192 else 64 * 6
+        ok &= case(f"D={D} qkv", M, 3 * D, D, 0, 0, ops.EPI_STORE, ops.BF16, bias=True)
+        ok &= case(f"D={D} out-proj residual", M, D, D, 0, 0, ops.EPI_RESIDUAL, ops.F32, bias=True)
+        ok &= case(f"D={D} fc1 gelu", M, Fd, D, 0, 0, ops.EPI_GELU, ops.BF16, bias=True)
+        ok &= case(f"D={D} fc2 residual", M, D, Fd, 0, 0, ops.EPI_RESIDUAL, ops.F32, bias=True)
+        ok &= case(f"D={D} fc2 dgrad dgelu", M, Fd, D, 0, 1, ops.EPI_DGELU, ops.BF16)
+        ok &= case(f"D={D} fc1 dgrad", M, D, Fd, 0, 1, ops.EPI_STORE, ops.BF16)
+        ok &= case(f"D={D} qkv dgrad", M, D, 3 * D, 0, 1, ops.EPI_STORE, ops.BF16)
+        ok &= case(f"D={D} fc1 wgrad split 2", Fd, D, M, 1, 1, ops.EPI_ACCUM, ops.F32, split=2)
+        ok &= case(f"D={D} qkv wgrad", 3 * D, D, M, 1, 1, ops.EPI_ACCUM, ops.F32)
+    ok &= case("ViT-L fc1 at batch-64 rows", 64 * 197, 4096, 1024, 0, 0, ops.EPI_GELU, ops.BF16, bias=True)
     return ok
 
 

@@ -203,7 +203,7 @@ def perf():
 
 
 def correctness():
-    for D in (256, 384, 512, 768, 1024):
+    for D in (64, 192, 256, 320, 384, 512, 768, 960, 1024):
         test_ln(1003, D, 1e-6, True)
     test_ln(50, 768, 1e-5, False)
     for (B, H, S) in ((3, 4, 65), (2, 12, 197), (2, 6, 198), (1, 8, 1050), (4, 2, 64), (2, 2, 1)):

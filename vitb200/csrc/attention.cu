@@ -861,11 +861,8 @@ static int launch_short_fwd(const AttnParams& p, cudaStream_t st) {
     const int rows_pad = ((p.S + 15) / 16) * 16;
     const int smem = 3 * rows_pad * 128;
     auto kern = attn_fwd_short_kernel<NW>;
-    static int configured = 0;
-    if (configured < smem) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static DeviceOnce configured;   // opt in once per device for the largest shape this path serves (S <= 256)
+    VB_ONCE_PER_DEVICE(configured, VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 128)));
     kern<<<dim3(p.H, p.B), NW * 32, smem, st>>>(p);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
@@ -875,11 +872,9 @@ static int launch_short_bwd(const AttnParams& p, cudaStream_t st) {
     const int rows_pad = ((p.S + 15) / 16) * 16;
     const int smem = 4 * rows_pad * 128 + 2 * (rows_pad + 32) * (int)sizeof(float);
     auto kern = attn_bwd_short_kernel<NW>;
-    static int configured = 0;
-    if (configured < smem) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static DeviceOnce configured;
+    VB_ONCE_PER_DEVICE(configured, VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                       4 * 256 * 128 + 2 * (256 + 32) * (int)sizeof(float))));
     kern<<<dim3(p.H, p.B), NW * 32, smem, st>>>(p);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
@@ -936,11 +931,11 @@ static AttnParams to_params(const VbAttnDesc* d) {
 static int launch_generic_fwd(const VbAttnDesc* d, const vb::AttnParams& p, cudaStream_t st) {
     using namespace vb;
     const int smem = 5 * TILE_BYTES;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.is_set()) {
         VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.set();
     }
     dim3 grid((d->S + TILE - 1) / TILE, d->H, d->B);
     if (d->dropout_p > 0.f) {
@@ -1018,13 +1013,13 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
         return rc ? rc : bwd_colsums(d, stream);
     }
     const int smem = 6 * TILE_BYTES + 4 * TILE * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.is_set()) {
         VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_BYTES));
         VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_BYTES));
-        configured = true;
+        configured.set();
     }
     const long long nwarps = (long long)d->B * d->S * d->H;
     attn_delta_kernel<<<delta_grid(nwarps), 256, 0, st>>>(p);

@@ -528,10 +528,10 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     }
 #define VB_BWD_LAUNCH(NKS, DR)                                                                                              \
     do {                                                                                                                    \
-        static bool configured = false;                                                                                     \
-        if (!configured) {                                                                                                  \
+        static DeviceOnce configured;                                                                                     \
+        if (!configured.is_set()) {                                                                                                  \
             VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<NKS, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-            configured = true;                                                                                              \
+            configured.set();                                                                                              \
         }                                                                                                                   \
         attn_bwd_tc5_kernel<NKS, DR><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);            \
     } while (0)

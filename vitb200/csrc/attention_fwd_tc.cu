@@ -399,10 +399,10 @@ int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream) {
     }
 #define VB_FWD_LAUNCH(NKS, DR)                                                                                              \
     do {                                                                                                                    \
-        static bool configured = false;                                                                                     \
-        if (!configured) {                                                                                                  \
+        static DeviceOnce configured;                                                                                     \
+        if (!configured.is_set()) {                                                                                                  \
             VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc3_kernel<NKS, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-            configured = true;                                                                                              \
+            configured.set();                                                                                              \
         }                                                                                                                   \
         attn_fwd_tc3_kernel<NKS, DR><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, to, a);                            \
     } while (0)

@@ -289,10 +289,10 @@ int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream) {
     a.scale_log2 = 0.125f * 1.4426950408889634f;
     a.o = (__nv_bfloat16*)d->o; a.ldo = d->ldo; a.tok_stride = d->tok_stride; a.batch_stride = d->batch_stride;
     a.lse = d->lse; a.kpm = d->key_padding_mask;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.is_set()) {
         VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
-        configured = true;
+        configured.set();
     }
     int grid = num_sms();
     if (grid > a.total_heads) grid = a.total_heads;

@@ -721,10 +721,10 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMa
     auto kern = gemm_kernel<AMAJ, BMAJ, EPI, CDT, CG>;
     constexpr uint32_t smem = EpiTraits<EPI, CG>::kSmemBytes;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    static bool configured = false;  // per instantiation; attribute is per-context, benign to repeat on races
-    if (!configured) {
+    static DeviceOnce configured;  // per instantiation; attribute is per-context, benign to repeat on races
+    if (!configured.is_set()) {
         VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.set();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

@@ -39,8 +39,9 @@ __global__ void ce_kernel(const float* __restrict__ logits, long long ld, const 
         if (correct_accum && arg == y) atomicAdd(correct_accum, 1);
     }
     const float inv = 1.f / s;
+    const float poison = bad_label ? __int_as_float(0x7fc00000) : 0.f;   // a bad label must not train the sample towards class 0: NaN gradient too
     for (int c = lane; c < C; c += 32) {
-        const float g = grad_scale * weight * (__expf(z[c] - mx) * inv - (c == y ? 1.f : 0.f));
+        const float g = grad_scale * weight * (__expf(z[c] - mx) * inv - (c == y ? 1.f : 0.f)) + poison;
         if (dz_bf16) dz_bf16[(long long)row * lddz + c] = __float2bfloat16_rn(g);
         if (dz_f32) dz_f32[(long long)row * lddzf + c] = g;
     }
@@ -88,8 +89,9 @@ __global__ void distill_loss_kernel(const float* __restrict__ logits, long long 
     float loss = bad_label ? __int_as_float(0x7fc00000) : (1.f - alpha) * invB * (a.mx + __logf(a.sum) - z[y]);
     {
         const float w = grad_scale * (1.f - alpha) * invB, inv = 1.f / a.sum;
+        const float poison = bad_label ? __int_as_float(0x7fc00000) : 0.f;   // as in ce_kernel: the gradient of a bad-label sample is NaN, not "class 0"
         for (int c = lane; c < C; c += 32) {
-            const float g = w * (__expf(z[c] - a.mx) * inv - (c == y ? 1.f : 0.f));
+            const float g = w * (__expf(z[c] - a.mx) * inv - (c == y ? 1.f : 0.f)) + poison;
             if (dz) dz[(long long)row * lddz + c] = __float2bfloat16_rn(g);
             if (dz_f32) dz_f32[(long long)row * lddzf + c] = g;
         }

@@ -14,7 +14,7 @@ class DevicePrefetcher:
     def __init__(self, loader, device="cuda", depth=2):
         self.loader, self.device, self.depth = loader, torch.device(device), max(2, int(depth))
         self.stream = torch.cuda.Stream(device=self.device)
-        self._slots = None   # per slot: [pinned images, pinned labels, device images, device labels, ready event, consumed event]
+        self._slots = None   # per slot: [pinned images, pinned labels, device images, device labels, ready event, consumed event, used]
 
     def __len__(self):
         return len(self.loader)
@@ -24,16 +24,26 @@ class DevicePrefetcher:
         for _ in range(self.depth):
             self._slots.append([torch.empty(images.shape, dtype=images.dtype).pin_memory(), torch.empty(labels.shape, dtype=labels.dtype).pin_memory(),
                                 torch.empty(images.shape, dtype=images.dtype, device=self.device),
-                                torch.empty(labels.shape, dtype=labels.dtype, device=self.device), torch.cuda.Event(), torch.cuda.Event()])
+                                torch.empty(labels.shape, dtype=labels.dtype, device=self.device), torch.cuda.Event(), torch.cuda.Event(), False])
 
     def _stage(self, slot, images, labels):
-        pin_i, pin_l, dev_i, dev_l, ready, consumed = slot
+        pin_i, pin_l, dev_i, dev_l, ready, consumed, used = slot
         if images.shape != dev_i.shape or labels.shape != dev_l.shape or images.dtype != dev_i.dtype:   # ragged last batch
             with torch.cuda.stream(self.stream):
                 out = (images.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True))
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
+            # allocated on the side stream, consumed on the caller's: the caching allocator must not recycle them underneath it
+            cur = torch.cuda.current_stream(self.device)
+            out[0].record_stream(cur)
+            out[1].record_stream(cur)
             return out[0], out[1], ev
+        # The previous H2D copy out of this slot's pinned buffers is asynchronous and is itself held back on the GPU until the
+        # consumer released the device buffer (wait_event(consumed) below), so with a sync-free trainer the host can be several
+        # batches ahead: wait until that copy has really left the pinned memory before overwriting it.
+        if used:
+            ready.synchronize()
+        slot[6] = True
         src_i = images if images.is_pinned() else pin_i.copy_(images)
         src_l = labels if labels.is_pinned() else pin_l.copy_(labels)
         with torch.cuda.stream(self.stream):

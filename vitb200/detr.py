@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .engine import FlatParams, WorkspaceLease, getstate_without_engine
+from .engine import FlatParams, WorkspaceLease, dropout_start_seed, getstate_without_engine
 from .vit import _EncoderFn  # noqa: F401  (same single-node autograd pattern)
 
 DETR_ROLES = ("norm2_w", "norm2_b", "lin2_w", "lin2_b", "lin1_w", "lin1_b", "norm1_w", "norm1_b", "out_w", "out_b", "in_w", "in_b")
@@ -72,7 +72,8 @@ class TransformerEncoderLayer(nn.Module):
 
 class DetrEngine(FlatParams):
     def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5, pre_norm=False):
-        assert d_model % 128 == 0 and d_model // nhead == 64, "vitb200 kernels need d_model % 128 == 0 and head_dim == 64"
+        if d_model % 64 != 0 or d_model // nhead != 64 or d_model > 1024:
+            raise NotImplementedError(f"vitb200 kernels need head_dim == 64 and d_model <= 1024 (got d_model {d_model}, {nhead} heads)")
         self.D, self.H, self.F, self.L, self.eps = d_model, nhead, dim_feedforward, len(layers), eps
         self.act = activation
         self.pre_norm = bool(pre_norm)   # TransformerEncoderLayer.forward_pre (transformer.py:228-241) instead of forward_post (:213-226)
@@ -100,7 +101,7 @@ class DetrEngine(FlatParams):
         """New masks for this forward: bump the device-side counter and snapshot it into the workspace (graph-capturable)."""
         dev = self.flat.device
         if self._drop_counter is None or self._drop_counter.device != dev:
-            self._drop_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+            self._drop_counter = torch.full((1,), dropout_start_seed(), device=dev, dtype=torch.int32)
         self._drop_counter.add_(1)
         if ws.get("drop_seed") is None:
             ws["drop_seed"] = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -531,7 +532,8 @@ class DetrDecoderEngine(DetrEngine):
     (0 = dropout1, 1 = dropout, 2 = dropout3, 3 = self-attention weights, 4 = cross-attention weights, 5 = dropout2)."""
 
     def __init__(self, layers, norm, d_model, nhead, dim_feedforward, activation, eps=1e-5, return_intermediate=False, pre_norm=False):
-        assert d_model % 128 == 0 and d_model // nhead == 64, "vitb200 kernels need d_model % 128 == 0 and head_dim == 64"
+        if d_model % 64 != 0 or d_model // nhead != 64 or d_model > 1024:
+            raise NotImplementedError(f"vitb200 kernels need head_dim == 64 and d_model <= 1024 (got d_model {d_model}, {nhead} heads)")
         self.D, self.H, self.F, self.L, self.eps = d_model, nhead, dim_feedforward, len(layers), eps
         self.act, self.pre_norm, self.has_norm = activation, bool(pre_norm), norm is not None
         self.return_intermediate = bool(return_intermediate) and self.has_norm

@@ -29,8 +29,26 @@ class GradReducer:
         self.engine = engine
         engine.grad_segment_hook = self._on_segment
         self._last_segment = len(engine.segment_bounds) - 1
+        self._synced = False
+        self.sync_parameters(strict=False)
+
+    def sync_parameters(self, strict=True):
+        """Rank 0's parameters become everybody's (what DistributedDataParallel does at construction): without it ranks built from
+        different seeds / checkpoints would silently train different replicas.  Deferred to the first step when the model is not on
+        its device yet."""
+        eng = self.engine
+        if hasattr(eng, "ensure_bound"):
+            if not eng._order[0][1].is_cuda and not strict:
+                return
+            eng.ensure_bound()
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+        dist.broadcast(eng.flat, src=src, group=self.pg)
+        eng.bf16_fresh = False      # the bf16 shadow must be re-cast from the broadcast values
+        self._synced = True
 
     def begin_step(self):
+        if not self._synced:
+            self.sync_parameters()
         self._works = []
         self._bucket_start = None
         if self.comm_stream is None and self.engine.flat.is_cuda:

@@ -37,6 +37,13 @@ def pick_split_k(tiles, k_blocks, sms):
     return best
 
 
+def dropout_start_seed():
+    """First value of an engine's dropout-mask counter: a function of torch.manual_seed() and the data-parallel rank, so that
+    neither every run nor every rank draws the same masks (the counter is bumped once per training forward)."""
+    rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+    return ((torch.initial_seed() * 0x9E3779B97F4A7C15 + (rank + 1) * 0x632BE59BD9B4E019) >> 33) & 0x3FFFFFFF
+
+
 class WorkspaceLease:
     """Marks a workspace as holding the saved activations of a forward whose backward is still pending.  While the lease is alive
     ``workspace()`` hands out another buffer set for the same shape, so a second forward (evaluation inside a training loop, two
@@ -365,8 +372,10 @@ class VitEngine(FlatParams):
                  globals_, layers, seq_length=None):
         """globals_: role -> Parameter for cls, [dist], pos, conv_w, conv_b, lnf_w, lnf_b, head_w, head_b, [headd_w, headd_b];
         layers: list of dicts role -> Parameter (LAYER_ROLES)."""
-        assert hidden_dim % 128 == 0 and hidden_dim // num_heads == 64, \
-            "vitb200 kernels need hidden_dim % 128 == 0 and head_dim == 64 (true for every reference config)"
+        if hidden_dim % 64 != 0 or hidden_dim // num_heads != 64 or hidden_dim > 1024:
+            # every config of the reference has head_dim 64: ViT 256/4, DeiT 192/3, 384/6, 768/12 (utils/args.py:6-15,43-61)
+            raise NotImplementedError(f"vitb200 kernels need head_dim == 64 and hidden_dim <= 1024 (got hidden_dim {hidden_dim}, "
+                                      f"{num_heads} heads)")
         # tokens mode (seq_length given): the stack is fed [B, S, D] tokens instead of images — a stand-alone Encoder
         # (vanilla_vit.py:88-106): input + pos_embedding, dropout, L blocks, final LayerNorm; no patch embedding, no heads.
         self.tokens_mode = seq_length is not None
@@ -422,7 +431,7 @@ class VitEngine(FlatParams):
     def _begin_dropout(self, ws):
         """New masks for this forward: bump the device-side counter and snapshot it into the workspace (graph-capturable)."""
         if self._drop_counter is None or self._drop_counter.device != self.flat.device:
-            self._drop_counter = torch.zeros(1, device=self.flat.device, dtype=torch.int32)
+            self._drop_counter = torch.full((1,), dropout_start_seed(), device=self.flat.device, dtype=torch.int32)
         self._drop_counter.add_(1)
         if "drop_seed" not in ws:
             ws["drop_seed"] = torch.zeros(1, device=self.flat.device, dtype=torch.int32)
