@@ -32,5 +32,7 @@ prev_end = 0
 for i in range(42):
     r = [(x.item() - t0) for x in t[i, :8]]
     gap = r[0] - prev_end; prev_end = r[7]
+    if i % 2 == 0 and t[i, 13].item() > 0:
+        print(f"    stats warp for head {i // 2}: stage free {t[i,13].item()-t0:7d} | dO landed {t[i,14].item()-t0:7d} | delta done {t[i,15].item()-t0:7d}   (head's first tile: s_full seen at {r[4]:7d})")
     if i < 6: print("    group ends rel. to s_full seen:", [(x.item() - t0) - r[4] for x in t[i, 8:13]])
     print(f"{i:2d}: gap {gap:6d} mma {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} | ew {r[4]:7d} {r[5]:7d} {r[6]:7d} {r[7]:7d}   item total {r[7]-r[0]:6d}  scoreMMA+wake {r[4]-r[1]:5d} elem {r[5]-r[4]:5d} p_full->mma {r[2]-r[5]:5d} outMMA+wake {r[6]-r[3]:5d} readout {r[7]-r[6]:5d}")

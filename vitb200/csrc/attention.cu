@@ -996,9 +996,7 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     const char* tc_env = getenv("VITB200_ATTN_TC_BWD");
     const bool cross = p.Sk != p.S;
     if (!cross && d->S <= 208 && d->tok_stride == 1 && d->key_padding_mask == nullptr && !(tc_env && tc_env[0] == '0')) {
-        attn_delta_kernel<<<delta_grid((long long)d->B * d->S * d->H), 256, 0, st>>>(p);
-        VB_CUDA_CHECK(cudaGetLastError());
-        const int tc = attention_bwd_tc5(d, st);
+        const int tc = attention_bwd_tc5(d, st);   // computes delta = rowsum(dO o O) itself
         if (tc <= 0) return tc;
     }
     const bool drop = d->dropout_p > 0.f;

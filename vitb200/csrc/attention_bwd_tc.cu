@@ -56,7 +56,8 @@ struct Args {
     int B, H, S, npad, nks, n_t, total_heads;
     float scale, scale_log2;
     const float* lse;
-    const float* delta;
+    const __nv_bfloat16* o;     // forward output [token, H*64] bf16: delta = rowsum(dO o O) is computed in-kernel by the stats warp
+    long long ldo;
     long long batch_stride;
     uint32_t drop_thresh, drop_stream;   // attention dropout (DROP instantiations)
     float drop_inv_keep;
@@ -113,7 +114,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* stats = reinterpret_cast<float*>(smem + kStatsOff);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
-    uint64_t* qdo_full = bars;        // [2] count 2: TMA expect_tx + stats warp
+    uint64_t* qdo_full = bars;        // [2] TMA expect_tx (Q and dO of the head have landed)
     uint64_t* qdo_empty = bars + 2;   // [2] store warp: the head's dQ tiles (parked in the Q / dO stage) have left
     uint64_t* kv_full = bars + 4;     // [2]
     uint64_t* kv_empty = bars + 6;    // [2] store warp: the tile's dV / dK tiles (parked in the K_t / V_t stage) have left
@@ -122,7 +123,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* o_full = bars + 12;
     uint64_t* tile_free = bars + 13;  // count kEwWarps: accumulators read out, TMEM free for the next tile's scores
     uint64_t* out_ready = bars + 14;  // count kEwWarps: output tiles staged in shared memory
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* stats_full = bars + 15; // [2] stats warp: -lse and delta of the head are in shared memory
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
 
     const uint32_t warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = args.S, n_t = args.n_t;
@@ -137,7 +139,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     if (warp_idx == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&qdo_full[i], 2); mbar_init(&qdo_empty[i], 1);
+            mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&stats_full[i], 1);
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], kEwWarps);
         }
@@ -171,30 +173,103 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else if (warp_idx == 3) {
-        // ---------------- -lse / delta loader (whole warp) ----------------
+        // ---------------- statistics warp: -lse from global, delta[q] = sum_d dO[q,d] O[q,d] computed here ----------------
+        // (replaces the separate attn_delta pre-kernel: 32 us per layer at batch 256).  dO of the head is already in shared memory
+        // (TMA, 128-byte swizzle); O rows are read from global, 4 lanes x 32 bytes (LDG.256) per row, 8 rows per pass, fp32 accumulation.
+        // The stage is filled one head ahead of its use, so this work is off the critical path.
         int hc = 0;
+        const int rsub = lane >> 2, csub = lane & 3;   // 4 lanes x 32 bytes per row, 8 rows per pass, 26 passes
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
-            const int qs = hc & 1;
+            const int qs = hc & 1, b = head / args.H, h = head - b * args.H;
             mbar_wait(&qdo_empty[qs], ((hc >> 1) & 1) ^ 1);
+            const bool sdbg = args.dbg && blockIdx.x == 0 && hc < 32 && lane == 0;   // stamps in the row of the head's first tile
+            if (sdbg) args.dbg[hc * 2 * 16 + 13] = clock64();
             float* nl = stats + qs * 2 * kMaxQ;
             float* dl = nl + kMaxQ;
             const float* gl = args.lse + (long long)head * S;
-            const float* gd = args.delta + (long long)head * S;
-            // all loads first (independent, one round trip), then the shared-memory writes
-            float lv[7], dv[7];
+            const __nv_bfloat16* go = args.o + ((long long)b * args.batch_stride) * args.ldo + h * 64 + csub * 16;
+            constexpr int kBatch = 9;                           // 3 batches x 9 passes (the last pass of the third batch is empty)
+            uint32_t ov[kBatch][8];
+            auto load_batch = [&](int p0) {                     // independent 256-bit loads: one round trip per batch
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int row = (p0 + j) * 8 + rsub;
+                    if (row < S) {
+                        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(ov[j][0]), "=r"(ov[j][1]), "=r"(ov[j][2]), "=r"(ov[j][3]), "=r"(ov[j][4]), "=r"(ov[j][5]),
+                                       "=r"(ov[j][6]), "=r"(ov[j][7])
+                                     : "l"(go + (long long)row * args.ldo));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ov[j][i] = 0u;
+                    }
+                }
+            };
+            load_batch(0);                                      // O does not depend on the TMA: its latency hides behind the wait below
+            {   // pull the NEXT head's O rows (and lse) into L2 now, so that its three load batches are L2 hits instead of HBM round trips
+                const int nhead = head + (int)gridDim.x;
+                if (nhead < args.total_heads) {
+                    const int nb = nhead / args.H, nh = nhead - nb * args.H;
+                    const __nv_bfloat16* no = args.o + ((long long)nb * args.batch_stride) * args.ldo + nh * 64;
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        const int row = lane + 32 * r;
+                        if (row < S) asm volatile("prefetch.global.L2 [%0];" ::"l"(no + (long long)row * args.ldo));
+                    }
+                    if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(args.lse + (long long)nhead * S + lane * 32));
+                }
+            }
+            float lv[7];
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
                 const int i = lane + 32 * r;
                 lv[r] = i < S ? -__ldg(gl + i) : -INFINITY;   // -inf => P = 0 for padded queries
-                dv[r] = i < S ? __ldg(gd + i) : 0.f;
             }
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
                 const int i = lane + 32 * r;
-                if (i < (int)kMaxQ) { nl[i] = lv[r]; dl[i] = dv[r]; }
+                if (i < (int)kMaxQ) nl[i] = lv[r];
+            }
+            mbar_wait(&qdo_full[qs], (hc >> 1) & 1);          // dO has landed
+            if (sdbg) args.dbg[hc * 2 * 16 + 14] = clock64();
+            const uint8_t* sdo_p = smem + kQdoOff + qs * 2 * kQBytes + kQBytes;
+            // acc += a.lo * b.lo + a.hi * b.hi with bf16 operands and fp32 accumulation: the mixed-precision FMA of sm_100
+            // (FHFMA.BF16 with half-register selectors) needs no unpacking — one instruction per multiply-add
+            auto dot2 = [](float acc, uint32_t a, uint32_t bb) {
+                asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+                    "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %0, ah, bh, %0;\n\t}"
+                    : "+f"(acc) : "r"(a), "r"(bb));
+                return acc;
+            };
+            for (int p0 = 0; p0 < 27; p0 += kBatch) {
+                if (p0 > 0) load_batch(p0);
+                // the nine passes of a batch are independent: plain (schedulable) shared loads, nine accumulators, shuffles at the end
+                float accs[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int row = min((p0 + j) * 8 + rsub, (int)kMaxQ - 1);
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {               // this lane's two 16-byte chunks of the swizzled dO row
+                        const uint4 dd = *reinterpret_cast<const uint4*>(sdo_p + row * 128 + (((csub * 2 + c) ^ (row & 7)) << 4));
+                        a0 = dot2(dot2(a0, dd.x, ov[j][4 * c]), dd.y, ov[j][4 * c + 1]);
+                        a1 = dot2(dot2(a1, dd.z, ov[j][4 * c + 2]), dd.w, ov[j][4 * c + 3]);
+                    }
+                    accs[j] = a0 + a1;
+                }
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) accs[j] += __shfl_xor_sync(0xffffffffu, accs[j], 1);
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) accs[j] += __shfl_xor_sync(0xffffffffu, accs[j], 2);
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int row = (p0 + j) * 8 + rsub;
+                    if (csub == 0 && row < (int)kMaxQ) dl[row] = row < S ? accs[j] : 0.f;
+                }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&qdo_full[qs]);
+            if (lane == 0) mbar_arrive(&stats_full[qs]);
+            if (sdbg) args.dbg[hc * 2 * 16 + 15] = clock64();
         }
     } else if (warp_idx == 2) {
         // ---------------- store warp: output tiles (shared memory) -> global by TMA, then recycle the buffers ----------------
@@ -342,6 +417,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t kv_row = smem_u32(smem + kKvOff + ks * 2 * kBlk) + row_in_tile * 128;   // K_t row; V_t row = + kBlk
                 const uint32_t drop_base = (uint32_t)head * (uint32_t)S * (uint32_t)S + (uint32_t)(t * 128 + row_in_tile);   // element (q, key) -> base + q * S
                 const bool dbg_on = args.dbg && blockIdx.x == 0 && ic < 64 && warp_idx == 4 && lane == 0;
+                if (t == 0) mbar_wait(&stats_full[qs], (hc >> 1) & 1);   // -lse / delta of this head (written a head ahead)
                 mbar_wait(&s_full[0], ic & 1);
                 tcgen05_fence_after();
                 if (dbg_on) args.dbg[ic * 16 + 4] = clock64();
@@ -484,7 +560,7 @@ static long long* g_dbg = nullptr;
 
 }  // namespace bwd5
 
-// Returns VB_OK if launched, 1 if this shape is not handled here.  `delta` must already hold rowsum(dO o O).
+// Returns VB_OK if launched, 1 if this shape is not handled here.  delta = rowsum(dO o O) is computed inside (from d->o and d->dout).
 int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     using namespace bwd5;
     static int enabled = -1;
@@ -493,13 +569,16 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
         enabled = (e && e[0] == '0') ? 0 : 1;
     }
     if (!enabled || d->S > (int)kMaxQ || d->head_dim != 64 || d->tok_stride != 1 || d->key_padding_mask != nullptr) return 1;
+    VB_REQUIRE(d->o != nullptr && d->ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(d->o) & 31) == 0,
+               "attention_bwd: the forward output o (32-byte aligned, pitch % 16 == 0) is needed for delta = rowsum(dO o O)");
     const int S = d->S, npad = (S + 15) / 16 * 16;
     Args a{};
     a.B = d->B; a.H = d->H; a.S = S; a.npad = npad; a.nks = npad / 16;
     a.n_t = (S + 127) / 128;
     a.total_heads = d->B * d->H;
     a.scale = 0.125f; a.scale_log2 = 0.125f * 1.4426950408889634f;
-    a.lse = d->lse; a.delta = d->delta;
+    a.lse = d->lse;
+    a.o = reinterpret_cast<const __nv_bfloat16*>(d->o); a.ldo = d->ldo;
     a.batch_stride = d->batch_stride;
     a.colsum = d->dqkv_colsum;
     { const char* e = getenv("VITB200_ATTN_BWD_LATE_RELEASE"); a.late_release = (e && e[0] == '1') ? 1 : 0; }

@@ -475,8 +475,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 const bool write_c = (EPI != VB_EPI_GELU) || args.C != nullptr;
-                // (Tried and rejected: 16-byte global stores straight from registers instead of staging + TMA store — the LSU handles 32
-                // rows per instruction and becomes the bottleneck at K = 768: 10.4 k vs 7.5 k cycles per tile.)
+                // (Tried and rejected: global stores straight from registers instead of staging + TMA store — a lane owns a ROW, so one
+                // store instruction touches 32 different cache lines and the LSU becomes the bottleneck at K = 768: 16-byte stores
+                // 10.4 k vs 7.5 k cycles per tile (round 1); 256-bit STG.256 / LDG.256 for the aux operand (round 2): fc1 + GELU
+                // 235 -> 265 us, fc2 dgrad x gelu' 205 -> 250 us, out-proj + residual 82 -> 103 us.  Also rejected in round 2: a
+                // MUFU-free-reciprocal erf (degree-8 polynomial for erfcx, one MUFU per element instead of two): 235 us unchanged —
+                // the two-output epilogue is bound by shared-memory staging traffic next to the operand reads, not by the math.)
                 uint8_t* obuf = buf_o0;
 #pragma unroll
                 for (int g = 0; g < int(CPC / 32); ++g) {
