@@ -5,6 +5,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 
 from vitb200 import ops
@@ -14,7 +15,10 @@ from vitb200.vit import ViT
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 which = sys.argv[2] if len(sys.argv) > 2 else "vit_b16"
 torch.manual_seed(0)
-if which == "deit_s":     # BASELINE.json configs[2]: DeiT-S/16 with distillation token (student step, plain CE on the class head here)
+if which == "detr":      # BASELINE.json configs[4]: DETR encoder, S = 1050, autograd path + torch.optim.Adam
+    import configs_bench
+    step_fn, model = configs_bench.detr_encoder_step("cuda", B if B <= 16 else 4)
+elif which == "deit_s":     # BASELINE.json configs[2]: DeiT-S/16 with distillation token (student step, plain CE on the class head here)
     from vitb200.deit import VisionTransformerDistilled
     model = VisionTransformerDistilled(img_size=224, patch_size=16, depth=12, num_heads=6, embed_dim=384, mlp_ratio=4, num_classes=1000)
 elif which == "vit_l16":
@@ -25,17 +29,22 @@ else:
     model = ViT(224, 16, 12, 12, 768, 3072, 0.0, 0.0, 1000)
     with torch.no_grad():
         model.heads.head.weight.normal_(std=0.02)
-model = model.cuda().train()
-tr = Trainer(model, use_cuda_graph=False)
-images = torch.randn(B, 3, 224, 224, device="cuda")
-labels = torch.randint(0, 1000, (B,), device="cuda")
+if which == "detr":
+    os.environ["VITB200_AUTOGRAD_GRAPH"] = "0"
+    step = step_fn
+else:
+    model = model.cuda().train()
+    tr = Trainer(model, use_cuda_graph=False)
+    images = torch.randn(B, 3, 224, 224, device="cuda")
+    labels = torch.randint(0, 1000, (B,), device="cuda")
+    step = lambda: tr.step(images, labels)
 for _ in range(5):
-    tr.step(images, labels)
+    step()
 torch.cuda.synchronize()
 
 rec = []
 names = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "cast_bf16", "patchify", "token_rows", "colsum_bf16",
-         "embed_bwd", "cross_entropy", "adam_step"]
+         "embed_bwd", "cross_entropy", "adam_step", "add_cast_bf16", "add3", "dropout_f32"]
 orig = {n: getattr(ops, n) for n in names}
 
 
@@ -61,7 +70,7 @@ s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 for rep in range(3):
     rec.clear()
     s0.record()
-    tr.step(images, labels)
+    step()
     s1.record()
     torch.cuda.synchronize()
 tot = collections.Counter()

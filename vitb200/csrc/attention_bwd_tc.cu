@@ -44,12 +44,12 @@ constexpr uint32_t kQBytes = kMaxQ * 128;              // Q or dO of one head
 constexpr uint32_t kStagingOff = 0;                    // 3 blocks (queries 0..191); block 3 aliases V_t
 constexpr uint32_t kQdoOff = 3 * kBlk;                 // 2 stages x {Q, dO}
 constexpr uint32_t kKvOff = kQdoOff + 4 * kQBytes;     // 2 stages x {K_t, V_t}
-constexpr uint32_t kStatsOff = kKvOff + 4 * kBlk;      // 2 stages x {-lse[208], delta[208]} fp32
+constexpr uint32_t kStatsOff = kKvOff + 4 * kBlk;      // 2 stages x {-lse[208], -delta[208]} fp32
 constexpr uint32_t kBarOff = kStatsOff + 2 * 2 * kMaxQ * 4;
 constexpr uint32_t kSmemBytes = kBarOff + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 
-constexpr uint32_t kColST = 0, kColDPT = 208, kColDV = 208, kColDK = 272, kColDQ1 = 336, kColDQ0 = 448;
+constexpr uint32_t kColST = 0, kColDPT = 208, kColDV = 208, kColDK = 272, kColDQ1 = 336, kColCarry = 416, kColDQ0 = 448;
 
 struct Args {
     long long* dbg;
@@ -68,37 +68,46 @@ struct Args {
 
 using namespace atc;
 
-// 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key).
+// 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key).  nls / dls point at
+// -lse[q] and -delta[q] of the 16 queries; the arithmetic is fp32x2-packed (FFMA2 / FADD2 / FMUL2: half the issue slots).
 // DROP (attention dropout): element (query q, key) of head-local index didx0 + j * S was kept iff its hash clears the threshold;
 // dV sees keep * P / (1 - p), and dP = keep * (dO V^T) / (1 - p) enters dS = P o (dP - delta) (delta = rowsum(dO o O) still holds).
 template <bool DROP>
-__device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_t (&dv)[16], uint32_t nls, uint32_t dls, float c,
+__device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_t (&dv)[16], uint32_t nls, uint32_t dls, f2 c2,
                                          uint32_t (&pp)[8], uint32_t (&pd)[8], uint32_t dkey, uint32_t didx0, uint32_t S, uint32_t thresh,
                                          float inv_keep) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float4 l4 = lds128(nls + 16 * i);
-        const float4 d4 = lds128(dls + 16 * i);
-        const float p0 = ex2f(fmaf(__uint_as_float(sv[4 * i + 0]), c, l4.x));
-        const float p1 = ex2f(fmaf(__uint_as_float(sv[4 * i + 1]), c, l4.y));
-        const float p2 = ex2f(fmaf(__uint_as_float(sv[4 * i + 2]), c, l4.z));
-        const float p3 = ex2f(fmaf(__uint_as_float(sv[4 * i + 3]), c, l4.w));
-        float g0 = __uint_as_float(dv[4 * i + 0]), g1 = __uint_as_float(dv[4 * i + 1]), g2 = __uint_as_float(dv[4 * i + 2]),
-              g3 = __uint_as_float(dv[4 * i + 3]);
+        f2 l01, l23, d01, d23;
+        lds_2xf2(nls + 16 * i, l01, l23);
+        lds_2xf2(dls + 16 * i, d01, d23);
+        float x0, x1, x2, x3;
+        f2_unpack(f2_fma(f2_pack_u(sv[4 * i + 0], sv[4 * i + 1]), c2, l01), x0, x1);
+        f2_unpack(f2_fma(f2_pack_u(sv[4 * i + 2], sv[4 * i + 3]), c2, l23), x2, x3);
+        const float p0 = ex2f(x0), p1 = ex2f(x1), p2 = ex2f(x2), p3 = ex2f(x3);
+        f2 g01 = f2_pack_u(dv[4 * i + 0], dv[4 * i + 1]), g23 = f2_pack_u(dv[4 * i + 2], dv[4 * i + 3]);
+        f2 p01 = f2_pack(p0, p1), p23 = f2_pack(p2, p3);
         if (DROP) {
-            const float k0 = dropout_keep(dkey, didx0 + (4 * i + 0) * S, thresh) ? inv_keep : 0.f;
-            const float k1 = dropout_keep(dkey, didx0 + (4 * i + 1) * S, thresh) ? inv_keep : 0.f;
-            const float k2 = dropout_keep(dkey, didx0 + (4 * i + 2) * S, thresh) ? inv_keep : 0.f;
-            const float k3 = dropout_keep(dkey, didx0 + (4 * i + 3) * S, thresh) ? inv_keep : 0.f;
-            pp[2 * i] = pack2(p0 * k0, p1 * k1);
-            pp[2 * i + 1] = pack2(p2 * k2, p3 * k3);
-            g0 *= k0; g1 *= k1; g2 *= k2; g3 *= k3;
+            const f2 k01 = f2_pack(dropout_keep(dkey, didx0 + (4 * i + 0) * S, thresh) ? inv_keep : 0.f,
+                                   dropout_keep(dkey, didx0 + (4 * i + 1) * S, thresh) ? inv_keep : 0.f);
+            const f2 k23 = f2_pack(dropout_keep(dkey, didx0 + (4 * i + 2) * S, thresh) ? inv_keep : 0.f,
+                                   dropout_keep(dkey, didx0 + (4 * i + 3) * S, thresh) ? inv_keep : 0.f);
+            float a, b;
+            f2_unpack(f2_mul(p01, k01), a, b);
+            pp[2 * i] = pack2(a, b);
+            f2_unpack(f2_mul(p23, k23), a, b);
+            pp[2 * i + 1] = pack2(a, b);
+            g01 = f2_mul(g01, k01);
+            g23 = f2_mul(g23, k23);
         } else {
             pp[2 * i] = pack2(p0, p1);
             pp[2 * i + 1] = pack2(p2, p3);
         }
-        pd[2 * i] = pack2(p0 * (g0 - d4.x), p1 * (g1 - d4.y));
-        pd[2 * i + 1] = pack2(p2 * (g2 - d4.z), p3 * (g3 - d4.w));
+        float s0, s1, s2, s3;
+        f2_unpack(f2_mul(p01, f2_add(g01, d01)), s0, s1);
+        f2_unpack(f2_mul(p23, f2_add(g23, d23)), s2, s3);
+        pd[2 * i] = pack2(s0, s1);
+        pd[2 * i + 1] = pack2(s2, s3);
     }
 }
 
@@ -264,7 +273,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < kBatch; ++j) {
                     const int row = (p0 + j) * 8 + rsub;
-                    if (csub == 0 && row < (int)kMaxQ) dl[row] = row < S ? accs[j] : 0.f;
+                    if (csub == 0 && row < (int)kMaxQ) dl[row] = row < S ? -accs[j] : 0.f;   // stored negated: dS = P o (dP + (-delta))
                 }
             }
             __syncwarp();
@@ -403,9 +412,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t stg_row = smem_u32(smem + kStagingOff) + row_in_tile * 128;
         const uint32_t stats_u32 = smem_u32(stats);
         const uint32_t drop_key = DROP ? dropout_key(*args.drop_seed, args.drop_stream) : 0u;
-        float dq1c[32];   // dQ contribution of key tile 0 to query tile 1 (parts 1 and 2: columns 0..31 / 32..63)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) dq1c[i] = 0.f;
+        const f2 c2 = f2_pack(c, c);
         int hc = 0, ic = 0;
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
             const int qs = hc & 1;
@@ -421,7 +428,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(&s_full[0], ic & 1);
                 tcgen05_fence_after();
                 if (dbg_on) args.dbg[ic * 16 + 4] = clock64();
-                bool arrivedA = false;
+                bool arrivedA = false, waitedB = false;
                 auto arriveA = [&]() {
                     tmem_st_wait();
                     fence_proxy_async_smem();   // staging writes must be visible to the tensor core's (async proxy) reads
@@ -430,20 +437,21 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (lane == 0) mbar_arrive(&p_full[0]);
                     arrivedA = true;
                 };
-                for (int g = part; g < nks; g += 3) {
-                    if (g >= 8 && !arrivedA) {
-                        arriveA();
+                // Software-pipelined over this warp's 16-query groups (g, g + 3, g + 6, ...): the TMEM loads of the next group are in
+                // flight while the current one is exponentiated, packed and stored — with three warps per scheduler the ld -> ex2 ->
+                // pack -> st chain of a single group was the critical path (700 cycles per group against 128 cycles of MUFU work).
+                auto issue = [&](uint32_t (&sv)[16], uint32_t (&dv)[16], int g) {
+                    if (g >= 8 && !waitedB) {      // queries >= 128: their scores are committed separately
                         mbar_wait(&s_full[1], ic & 1);
                         tcgen05_fence_after();
-                    } else if (g >= 8 && g < 11) {
-                        mbar_wait(&s_full[1], ic & 1);
-                        tcgen05_fence_after();
+                        waitedB = true;
                     }
-                    uint32_t sv[16], dv[16], pp[8], pd[8];
                     tmem_ld_32x32b_x16(t_lane + kColST + g * 16, sv);
                     tmem_ld_32x32b_x16(t_lane + kColDPT + g * 16, dv);
-                    tmem_ld_wait();
-                    ew_group<DROP>(sv, dv, nls + g * 64, dls + g * 64, c, pp, pd, drop_key, drop_base + (uint32_t)(g * 16) * (uint32_t)S, (uint32_t)S,
+                };
+                auto process = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int g) {
+                    uint32_t pp[8], pd[8];
+                    ew_group<DROP>(sv, dv, nls + g * 64, dls + g * 64, c2, pp, pd, drop_key, drop_base + (uint32_t)(g * 16) * (uint32_t)S, (uint32_t)S,
                                    args.drop_thresh, args.drop_inv_keep);
                     tmem_st_32x32b_x8(t_lane + kColST + g * 16, pp);
                     const uint32_t dst = (g < 12) ? stg_row + (g >> 2) * kBlk : kv_row + kBlk;   // block 3 aliases V_t
@@ -451,6 +459,22 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     sts128(dst + ((ch ^ swz) << 4), pd[0], pd[1], pd[2], pd[3]);
                     sts128(dst + (((ch + 1) ^ swz) << 4), pd[4], pd[5], pd[6], pd[7]);
                     if (dbg_on) args.dbg[ic * 16 + 8 + g / 3] = clock64();
+                    if (g < 8 && g + 3 >= 8 && !arrivedA) arriveA();   // that was this warp's last group of the first part
+                };
+                {
+                    uint32_t svA[16], dvA[16], svB[16], dvB[16];
+                    int g = part;
+                    if (g < nks) issue(svA, dvA, g);
+                    for (; g < nks; g += 6) {
+                        tmem_ld_wait();
+                        if (g + 3 < nks) issue(svB, dvB, g + 3);
+                        process(svA, dvA, g);
+                        if (g + 3 < nks) {
+                            tmem_ld_wait();
+                            if (g + 6 < nks) issue(svA, dvA, g + 6);
+                            process(svB, dvB, g + 3);
+                        }
+                    }
                 }
                 if (!arrivedA) arriveA();
                 tmem_st_wait();
@@ -523,14 +547,29 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (part == 0) {
                     stage32(rb, kv_row + kBlk, 1u, args.scale);
                 } else if (has_q1) {
+                    // The dQ contribution of key tile 0 to the queries >= 128 has to survive the next tile's score products, which
+                    // overwrite its accumulator: it is parked as packed bf16 in the 32 TMEM columns nothing else uses (16 per part) —
+                    // 32 registers less than carrying it in fp32, which is what pays for the double-buffered loads above.
+                    const uint32_t t_carry = t_lane + kColCarry + (part - 1) * 16;
                     if (last) {
+                        if (n_t > 1) {
+                            uint32_t cr[16];
+                            tmem_ld_32x32b_x16(t_carry, cr);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) rb[i] = __float_as_uint(__uint_as_float(rb[i]) + dq1c[i]);
+                            for (int i = 0; i < 16; ++i) {
+                                rb[2 * i] = __float_as_uint(__uint_as_float(rb[2 * i]) + __uint_as_float(cr[i] << 16));
+                                rb[2 * i + 1] = __float_as_uint(__uint_as_float(rb[2 * i + 1]) + __uint_as_float(cr[i] & 0xFFFF0000u));
+                            }
+                        }
                         stage32(rb, q_row + kBlk, part - 1, args.scale);
                         if (do_cs) colsum32(rb, args.scale, 128 + row_in_tile < S, args.colsum + hcol + (part - 1) * 32);
                     } else {
+                        uint32_t cr[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) dq1c[i] = __uint_as_float(rb[i]);
+                        for (int i = 0; i < 16; ++i) cr[i] = pack2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+                        tmem_st_32x32b_x16(t_carry, cr);
+                        tmem_st_wait();
                     }
                 }
                 if (third) {
