@@ -148,9 +148,16 @@ typedef struct VbAttnDesc {
      * delta stay [B,H,S].  Served by the 64x64-tile mma.sync kernels. */
     int32_t S_kv;
     int32_t reserved0;
+    /* scratch for the shapes the one-block kernels do not cover (S > 208, key-padding masks, sequence-first strides, cross-
+     * attention): forward = per-key-block partial outputs + log-sum-exps, backward = fp32 dK / dV accumulators.  Caller-allocated
+     * device memory, 256-byte aligned, at least vb_attention_workspace_bytes() bytes; may be NULL when that returns 0. */
+    void* workspace;
+    int64_t workspace_bytes;
 } VbAttnDesc;
 VB_API int vb_attention_fwd(const VbAttnDesc* desc, void* stream);
 VB_API int vb_attention_bwd(const VbAttnDesc* desc, void* stream);
+/* bytes of VbAttnDesc.workspace the forward (backward = 0) or backward (backward = 1) call of this descriptor needs; 0 = none */
+VB_API int64_t vb_attention_workspace_bytes(const VbAttnDesc* desc, int32_t backward);
 /* profiling aid: device buffer (>= 1024 int64) receiving in-kernel cycle stamps of the tcgen05 backward; NULL disables */
 VB_API int vb_debug_set_attn_timeline(void* device_buffer);
 /* same for the GEMM: >= 8 int64 of cluster 0's MMA issuer (total cycles, waiting for operand stages, for a free accumulator, for

@@ -46,6 +46,7 @@ class VbAttnDesc(Structure):
         ("dropout_p", c_float), ("dropout_stream", c_uint32), ("dropout_seed", c_void_p),
         ("dqkv_colsum", c_void_p),
         ("S_kv", c_int32), ("reserved0", c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
     ]
 
 
@@ -79,6 +80,7 @@ SIGNATURES = {
     "vb_debug_set_attn_timeline": (c_int, [c_void_p]),
     "vb_attention_fwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),
     "vb_attention_bwd": (c_int, [POINTER(VbAttnDesc), c_void_p]),
+    "vb_attention_workspace_bytes": (c_int64, [POINTER(VbAttnDesc), c_int32]),
     "vb_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                  c_void_p, c_int32, c_int32, c_float, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "vb_layernorm_bwd": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -890,6 +890,26 @@ static unsigned delta_grid(long long units) {
 int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream);   // attention_tc.cu (older tcgen05 path: S <= 256, key-padding masks)
 int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream);  // attention_fwd_tc.cu (S <= 208, no mask: three threads per row)
 int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream);   // attention_bwd_tc.cu (five-product tcgen05 path, S <= 208)
+int attention_fwd_gen(const VbAttnDesc* d, cudaStream_t stream);   // attention_fwd_tc.cu: any S / S_kv, masks, strides (tcgen05)
+int attention_bwd_gen(const VbAttnDesc* d, cudaStream_t stream);   // attention_bwd_tc.cu
+size_t attention_fwd_gen_workspace(const VbAttnDesc* d);
+size_t attention_bwd_gen_workspace(const VbAttnDesc* d);
+
+// The one-block tcgen05 kernels serve batch-first self-attention over <= 208 tokens without a mask (every ViT / DeiT config); everything
+// else (DETR: S = 1050 / 4200, key-padding masks, sequence-first strides, 100 queries against the S-token memory) goes to the general
+// tcgen05 kernels.  VITB200_ATTN_GEN=0 selects the mma.sync kernels of this file instead (A/B comparisons).
+static bool one_block_shape(const VbAttnDesc* d) {
+    const bool cross = d->S_kv > 0 && d->S_kv != d->S;
+    return !cross && d->S <= 208 && d->tok_stride == 1 && d->key_padding_mask == nullptr;
+}
+static bool gen_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VITB200_ATTN_GEN");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
 
 static int check_common(const VbAttnDesc* d) {
     VB_REQUIRE(d != nullptr, "attention: null descriptor");
@@ -953,6 +973,7 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (int rc = check_arch()) return rc;
     if (int rc = check_common(d)) return rc;
     const AttnParams p = to_params(d);
+    if (!one_block_shape(d) && gen_enabled()) return attention_fwd_gen(d, as_stream(stream));
     if (p.Sk != p.S) return launch_generic_fwd(d, p, as_stream(stream));   // cross-attention: query and key counts differ
     if (d->S <= 256) {
         int tc = attention_fwd_tc3(d, as_stream(stream));
@@ -983,6 +1004,12 @@ static int bwd_colsums(const VbAttnDesc* d, void* stream) {
     return vb_colsum_bf16(d->dv, d->lddv, (int)rows_kv, cols, d->dqkv_colsum + 2 * cols, stream);
 }
 
+extern "C" int64_t vb_attention_workspace_bytes(const VbAttnDesc* d, int32_t backward) {
+    using namespace vb;
+    if (d == nullptr || one_block_shape(d) || !gen_enabled()) return 0;
+    return (int64_t)(backward ? attention_bwd_gen_workspace(d) : attention_fwd_gen_workspace(d));
+}
+
 extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     using namespace vb;
     if (int rc = check_arch()) return rc;
@@ -995,6 +1022,10 @@ extern "C" int vb_attention_bwd(const VbAttnDesc* d, void* stream) {
     // VITB200_ATTN_TC_BWD=0 selects the mma.sync kernels below (A/B comparisons).
     const char* tc_env = getenv("VITB200_ATTN_TC_BWD");
     const bool cross = p.Sk != p.S;
+    if (!one_block_shape(d) && gen_enabled()) {
+        if (int rc = attention_bwd_gen(d, st)) return rc;
+        return bwd_colsums(d, stream);
+    }
     if (!cross && d->S <= 208 && d->tok_stride == 1 && d->key_padding_mask == nullptr && !(tc_env && tc_env[0] == '0')) {
         const int tc = attention_bwd_tc5(d, st);   // computes delta = rowsum(dO o O) itself
         if (tc <= 0) return tc;

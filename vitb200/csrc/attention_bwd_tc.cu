@@ -20,6 +20,10 @@
 // so the second-stage products of the first part overlap the element-wise work on the second.  Accumulators are read out
 // into the dead K_t / V_t / Q buffers and leave by TMA store issued from a dedicated warp.
 //
+// GEN instantiations (any number of queries / keys, key-padding masks, sequence-first strides, cross-attention: the DETR encoder and
+// decoder): a work item is (batch, head, 128-query block) looping over ALL key tiles; dQ of the block accumulates in TMEM across
+// the key tiles as above, while dK_t / dV_t — partial sums over this query block only — are reduce-added (red.global.add.v4.f32)
+// from registers into fp32 accumulators that attn_acc_to_bf16_kernel converts afterwards.  Masked keys get P = dS = 0.
 // Replaces the autograd of F.scaled_dot_product_attention reached from nn.MultiheadAttention (vanilla_vit.py:77,
 // torch/nn/functional.py:6676-6688).  delta = rowsum(dO o O) comes from attn_delta_kernel (attention.cu).
 #include <cuda.h>
@@ -41,13 +45,20 @@ constexpr int kThreads = 128 + kEwWarps * 32;          // warps 0-3: TMA, MMA, T
 constexpr uint32_t kMaxQ = 208;                        // padded queries / keys per head
 constexpr uint32_t kBlk = 128 * 128;                   // one 64-wide staging block / K_t / V_t tile: 128 rows x 128 B
 constexpr uint32_t kQBytes = kMaxQ * 128;              // Q or dO of one head
-constexpr uint32_t kStagingOff = 0;                    // 3 blocks (queries 0..191); block 3 aliases V_t
-constexpr uint32_t kQdoOff = 3 * kBlk;                 // 2 stages x {Q, dO}
-constexpr uint32_t kKvOff = kQdoOff + 4 * kQBytes;     // 2 stages x {K_t, V_t}
-constexpr uint32_t kStatsOff = kKvOff + 4 * kBlk;      // 2 stages x {-lse[208], -delta[208]} fp32
-constexpr uint32_t kBarOff = kStatsOff + 2 * 2 * kMaxQ * 4;
-constexpr uint32_t kSmemBytes = kBarOff + 256 + 1024;
-static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+// Shared-memory layout.  GEN items have at most 128 queries: two staging blocks, 16 KB Q / dO slots, and two extra 16 KB buffers in
+// which the fp32 dK_t halves wait for their TMA reduce-add (the fp32 dV_t halves park in the dead K_t / V_t buffers).
+template <bool GEN>
+struct Lay {
+    static constexpr uint32_t kStaging = 0;                                   // dS^T blocks of 64 queries (block 3 aliases V_t)
+    static constexpr uint32_t kQSlot = GEN ? kBlk : kQBytes;                  // Q or dO of one item
+    static constexpr uint32_t kQdo = (GEN ? 2 : 3) * kBlk;                    // 2 stages x {Q, dO}
+    static constexpr uint32_t kKv = kQdo + 4 * kQSlot;                        // 2 stages x {K_t, V_t}
+    static constexpr uint32_t kDk = kKv + 4 * kBlk;                           // GEN: fp32 dK_t columns 0..31 / 32..63
+    static constexpr uint32_t kStats = kDk + (GEN ? 2 * kBlk : 0);            // 2 stages x {-lse[208], -delta[208]} fp32
+    static constexpr uint32_t kBar = kStats + 2 * 2 * kMaxQ * 4;
+    static constexpr uint32_t kSmem = kBar + 256 + 1024;
+    static_assert(kSmem <= 232448, "shared memory budget exceeded");
+};
 
 constexpr uint32_t kColST = 0, kColDPT = 208, kColDV = 208, kColDK = 272, kColDQ1 = 336, kColCarry = 416, kColDQ0 = 448;
 
@@ -62,11 +73,35 @@ struct Args {
     uint32_t drop_thresh, drop_stream;   // attention dropout (DROP instantiations)
     float drop_inv_keep;
     const uint32_t* drop_seed;
+    // GEN: S = number of queries, Sk = number of keys (n_t = key tiles), n_qb = 128-query blocks per head, total_heads = work items;
+    // tok_stride / batch_stride address the rows of o; dk_acc / dv_acc are fp32 [B * Sk, H * 64] accumulators (zeroed by the host)
+    int Sk, n_qb;
+    long long tok_stride;
+    const uint8_t* kpm;
+    float* dk_acc;
+    float* dv_acc;
     int late_release;   // A/B switch (VITB200_ATTN_BWD_LATE_RELEASE=1): hand TMEM back only after the whole read-out
     float* colsum;   // optional fp32 [3][H*64]: += column sums of dq and dv (in-projection bias gradient; the dk part is exactly 0)
 };
 
 using namespace atc;
+
+struct Item {
+    int b, h, bh, qb;
+};
+template <bool GEN>
+__device__ __forceinline__ Item decode_item(const Args& a, int item) {
+    Item it;
+    if (GEN) {
+        it.bh = item / a.n_qb;
+        it.qb = item - it.bh * a.n_qb;
+    } else {
+        it.bh = item; it.qb = 0;
+    }
+    it.b = it.bh / a.H;
+    it.h = it.bh - it.b * a.H;
+    return it;
+}
 
 // 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key).  nls / dls point at
 // -lse[q] and -delta[q] of the 16 queries; the arithmetic is fp32x2-packed (FFMA2 / FADD2 / FMUL2: half the issue slots).
@@ -112,7 +147,7 @@ __device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_
 }
 
 // NKS_T > 0: number of 16-query steps known at compile time (fully unrolled MMA issue); NKS_T == 0: generic.
-template <int NKS_T, bool DROP>
+template <int NKS_T, bool DROP, bool GEN>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -121,8 +156,10 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* stats = reinterpret_cast<float*>(smem + kStatsOff);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+    using L = Lay<GEN>;
+    constexpr uint32_t kQdoOff = L::kQdo, kKvOff = L::kKv, kStagingOff = L::kStaging, kQSlot = L::kQSlot;
+    float* stats = reinterpret_cast<float*>(smem + L::kStats);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
     uint64_t* qdo_full = bars;        // [2] TMA expect_tx (Q and dO of the head have landed)
     uint64_t* qdo_empty = bars + 2;   // [2] store warp: the head's dQ tiles (parked in the Q / dO stage) have left
     uint64_t* kv_full = bars + 4;     // [2]
@@ -133,12 +170,14 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* tile_free = bars + 13;  // count kEwWarps: accumulators read out, TMEM free for the next tile's scores
     uint64_t* out_ready = bars + 14;  // count kEwWarps: output tiles staged in shared memory
     uint64_t* stats_full = bars + 15; // [2] stats warp: -lse and delta of the head are in shared memory
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* dk_free = bars + 17;    // GEN: the TMA reduce-adds have finished reading the fp32 dK_t buffers
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
     const uint32_t warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = args.S, n_t = args.n_t;
     const int nks = NKS_T ? NKS_T : args.nks;
-    const int npad = nks * 16;
+    const int npad = nks * 16;                                        // padded queries of an item
+    const int npad_k = GEN ? (args.Sk + 15) / 16 * 16 : npad;       // padded keys of the head
     const int jA = nks < 8 ? nks : 8;          // 16-query groups of the first part (queries < 128)
     const bool has_q1 = npad > 128;
 
@@ -152,7 +191,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], kEwWarps);
         }
-        mbar_init(o_full, 1); mbar_init(tile_free, kEwWarps); mbar_init(out_ready, kEwWarps);
+        mbar_init(o_full, 1); mbar_init(tile_free, kEwWarps); mbar_init(out_ready, kEwWarps); mbar_init(dk_free, 1);
         fence_barrier_init();
     }
     if (warp_idx == 2) tmem_alloc<512>(tmem_ptr_smem);
@@ -165,12 +204,13 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) {   // ---------------- TMA loader ----------------
             int hc = 0, ic = 0;
             for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
-                const int qs = hc & 1, b = head / args.H, h = head - b * args.H;
+                const Item it = decode_item<GEN>(args, head);
+                const int qs = hc & 1, b = it.b, h = it.h;
                 mbar_wait(&qdo_empty[qs], ((hc >> 1) & 1) ^ 1);
-                uint8_t* qb = smem + kQdoOff + qs * 2 * kQBytes;
+                uint8_t* qb = smem + kQdoOff + qs * 2 * kQSlot;
                 mbar_arrive_expect_tx(&qdo_full[qs], 2 * npad * 128);
-                tma_load_3d(qb, &tmQ, &qdo_full[qs], h * 64, 0, b);
-                tma_load_3d(qb + kQBytes, &tmdO, &qdo_full[qs], h * 64, 0, b);
+                tma_load_3d(qb, &tmQ, &qdo_full[qs], h * 64, it.qb * 128, b);
+                tma_load_3d(qb + kQSlot, &tmdO, &qdo_full[qs], h * 64, it.qb * 128, b);
                 for (int t = 0; t < n_t; ++t, ++ic) {
                     const int ks = ic & 1;
                     mbar_wait(&kv_empty[ks], ((ic >> 1) & 1) ^ 1);
@@ -189,25 +229,28 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         int hc = 0;
         const int rsub = lane >> 2, csub = lane & 3;   // 4 lanes x 32 bytes per row, 8 rows per pass, 26 passes
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
-            const int qs = hc & 1, b = head / args.H, h = head - b * args.H;
+            const Item it = decode_item<GEN>(args, head);
+            const int qs = hc & 1, b = it.b, h = it.h, q0 = it.qb * 128;
+            const int nq = GEN ? min(128, S - q0) : S;                 // valid queries of this item
             mbar_wait(&qdo_empty[qs], ((hc >> 1) & 1) ^ 1);
             const bool sdbg = args.dbg && blockIdx.x == 0 && hc < 32 && lane == 0;   // stamps in the row of the head's first tile
             if (sdbg) args.dbg[hc * 2 * 16 + 13] = clock64();
             float* nl = stats + qs * 2 * kMaxQ;
             float* dl = nl + kMaxQ;
-            const float* gl = args.lse + (long long)head * S;
-            const __nv_bfloat16* go = args.o + ((long long)b * args.batch_stride) * args.ldo + h * 64 + csub * 16;
+            const float* gl = args.lse + (long long)it.bh * S + q0;
+            const long long orow = GEN ? args.tok_stride * args.ldo : args.ldo;   // pitch between consecutive tokens of o
+            const __nv_bfloat16* go = args.o + ((long long)b * args.batch_stride) * args.ldo + (long long)q0 * orow + h * 64 + csub * 16;
             constexpr int kBatch = 9;                           // 3 batches x 9 passes (the last pass of the third batch is empty)
             uint32_t ov[kBatch][8];
             auto load_batch = [&](int p0) {                     // independent 256-bit loads: one round trip per batch
 #pragma unroll
                 for (int j = 0; j < kBatch; ++j) {
                     const int row = (p0 + j) * 8 + rsub;
-                    if (row < S) {
+                    if (row < nq) {
                         asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                                      : "=r"(ov[j][0]), "=r"(ov[j][1]), "=r"(ov[j][2]), "=r"(ov[j][3]), "=r"(ov[j][4]), "=r"(ov[j][5]),
                                        "=r"(ov[j][6]), "=r"(ov[j][7])
-                                     : "l"(go + (long long)row * args.ldo));
+                                     : "l"(go + (long long)row * orow));
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) ov[j][i] = 0u;
@@ -218,21 +261,22 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             {   // pull the NEXT head's O rows (and lse) into L2 now, so that its three load batches are L2 hits instead of HBM round trips
                 const int nhead = head + (int)gridDim.x;
                 if (nhead < args.total_heads) {
-                    const int nb = nhead / args.H, nh = nhead - nb * args.H;
-                    const __nv_bfloat16* no = args.o + ((long long)nb * args.batch_stride) * args.ldo + nh * 64;
+                    const Item nx = decode_item<GEN>(args, nhead);
+                    const int nq0 = nx.qb * 128, nnq = GEN ? min(128, S - nq0) : S;
+                    const __nv_bfloat16* no = args.o + ((long long)nx.b * args.batch_stride) * args.ldo + (long long)nq0 * orow + nx.h * 64;
 #pragma unroll
                     for (int r = 0; r < 7; ++r) {
                         const int row = lane + 32 * r;
-                        if (row < S) asm volatile("prefetch.global.L2 [%0];" ::"l"(no + (long long)row * args.ldo));
+                        if (row < nnq) asm volatile("prefetch.global.L2 [%0];" ::"l"(no + (long long)row * orow));
                     }
-                    if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(args.lse + (long long)nhead * S + lane * 32));
+                    if (lane * 32 < nnq) asm volatile("prefetch.global.L2 [%0];" ::"l"(args.lse + (long long)nx.bh * S + nq0 + lane * 32));
                 }
             }
             float lv[7];
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
                 const int i = lane + 32 * r;
-                lv[r] = i < S ? -__ldg(gl + i) : -INFINITY;   // -inf => P = 0 for padded queries
+                lv[r] = i < nq ? -__ldg(gl + i) : -INFINITY;   // -inf => P = 0 for padded queries
             }
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
@@ -241,7 +285,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             mbar_wait(&qdo_full[qs], (hc >> 1) & 1);          // dO has landed
             if (sdbg) args.dbg[hc * 2 * 16 + 14] = clock64();
-            const uint8_t* sdo_p = smem + kQdoOff + qs * 2 * kQBytes + kQBytes;
+            const uint8_t* sdo_p = smem + kQdoOff + qs * 2 * kQSlot + kQSlot;
             // acc += a.lo * b.lo + a.hi * b.hi with bf16 operands and fp32 accumulation: the mixed-precision FMA of sm_100
             // (FHFMA.BF16 with half-register selectors) needs no unpacking — one instruction per multiply-add
             auto dot2 = [](float acc, uint32_t a, uint32_t bb) {
@@ -273,7 +317,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < kBatch; ++j) {
                     const int row = (p0 + j) * 8 + rsub;
-                    if (csub == 0 && row < (int)kMaxQ) dl[row] = row < S ? -accs[j] : 0.f;   // stored negated: dS = P o (dP + (-delta))
+                    if (csub == 0 && row < (int)kMaxQ) dl[row] = row < nq ? -accs[j] : 0.f;   // stored negated: dS = P o (dP + (-delta))
                 }
             }
             __syncwarp();
@@ -284,18 +328,26 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---------------- store warp: output tiles (shared memory) -> global by TMA, then recycle the buffers ----------------
         int hc = 0, ic = 0;
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
-            const int qs = hc & 1, b = head / args.H, h = head - b * args.H;
+            const Item it = decode_item<GEN>(args, head);
+            const int qs = hc & 1, b = it.b, h = it.h;
             for (int t = 0; t < n_t; ++t, ++ic) {
                 const int ks = ic & 1;
                 mbar_wait(out_ready, ic & 1);
                 const bool last = (t == n_t - 1);
                 uint8_t* kb = smem + kKvOff + ks * 2 * kBlk;
-                uint8_t* qb = smem + kQdoOff + qs * 2 * kQBytes;
+                uint8_t* qb = smem + kQdoOff + qs * 2 * kQSlot;
                 if (lane == 0) {
-                    tma_store_3d(&tmDV, kb, h * 64, t * 128, b);
-                    tma_store_3d(&tmDK, kb + kBlk, h * 64, t * 128, b);
+                    if (GEN) {   // partial sums over this item's query block: fp32 reduce-add into the accumulators (tmDV / tmDK are fp32 maps)
+                        tma_reduce_add_3d(&tmDV, kb, h * 64, t * 128, b);
+                        tma_reduce_add_3d(&tmDV, kb + kBlk, h * 64 + 32, t * 128, b);
+                        tma_reduce_add_3d(&tmDK, smem + L::kDk, h * 64, t * 128, b);
+                        tma_reduce_add_3d(&tmDK, smem + L::kDk + kBlk, h * 64 + 32, t * 128, b);
+                    } else {
+                        tma_store_3d(&tmDV, kb, h * 64, t * 128, b);
+                        tma_store_3d(&tmDK, kb + kBlk, h * 64, t * 128, b);
+                    }
                     if (last) {
-                        tma_store_3d(&tmDQ, qb, h * 64, 0, b);
+                        tma_store_3d(&tmDQ, qb, h * 64, it.qb * 128, b);
                         if (has_q1) tma_store_3d(&tmDQ, qb + kBlk, h * 64, 128, b);
                     }
                     tma_store_commit();
@@ -304,6 +356,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (lane == 0) {
                     tma_store_wait_read<0>();
                     mbar_arrive(&kv_empty[ks]);
+                    if (GEN) mbar_arrive(dk_free);
                     if (last) mbar_arrive(&qdo_empty[qs]);
                 }
                 __syncwarp();
@@ -326,7 +379,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
             const int qs = hc & 1;
             mbar_wait(&qdo_full[qs], (hc >> 1) & 1);
-            const uint32_t sQ = smem_u32(smem + kQdoOff + qs * 2 * kQBytes), sdO = sQ + kQBytes;
+            const uint32_t sQ = smem_u32(smem + kQdoOff + qs * 2 * kQSlot), sdO = sQ + kQSlot;
             for (int t = 0; t < n_t; ++t, ++ic) {
                 const int ks = ic & 1;
                 const uint32_t sK = smem_u32(smem + kKvOff + ks * 2 * kBlk), sV = sK + kBlk;
@@ -359,7 +412,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint64_t ad_q0 = umma_smem_desc(mdesc, stg);
                 const uint64_t ad_q1 = umma_smem_desc(umma_smem_desc_base(sV - (stg + 2 * kBlk), 1024), stg + 2 * kBlk);
                 const uint64_t ad_k = umma_smem_desc(kdesc, stg), ad_kv = umma_smem_desc(kdesc, sV);
-                const int ksteps = (min(npad - t * 128, 128)) >> 4;
+                const int ksteps = (min(npad_k - t * 128, 128)) >> 4;
                 // ---- first part: queries < 128 ----
                 mbar_wait(&p_full[0], ic & 1);
                 tcgen05_fence_after();
@@ -415,14 +468,22 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const f2 c2 = f2_pack(c, c);
         int hc = 0, ic = 0;
         for (int head = blockIdx.x; head < args.total_heads; head += gridDim.x, ++hc) {
+            const Item it = decode_item<GEN>(args, head);
             const int qs = hc & 1;
             const uint32_t nls = stats_u32 + qs * 2 * kMaxQ * 4;
             const uint32_t dls = nls + kMaxQ * 4;
-            const uint32_t q_row = smem_u32(smem + kQdoOff + qs * 2 * kQBytes) + row_in_tile * 128;   // dQ tiles park in the Q / dO stage
+            const uint32_t q_row = smem_u32(smem + kQdoOff + qs * 2 * kQSlot) + row_in_tile * 128;   // dQ tiles park in the Q / dO stage
             for (int t = 0; t < n_t; ++t, ++ic) {
                 const int ks = ic & 1;
                 const uint32_t kv_row = smem_u32(smem + kKvOff + ks * 2 * kBlk) + row_in_tile * 128;   // K_t row; V_t row = + kBlk
-                const uint32_t drop_base = (uint32_t)head * (uint32_t)S * (uint32_t)S + (uint32_t)(t * 128 + row_in_tile);   // element (q, key) -> base + q * S
+                // element (q, key) of the head -> base + q * (number of keys)
+                const uint32_t kstride = GEN ? (uint32_t)args.Sk : (uint32_t)S;
+                const uint32_t drop_base = ((uint32_t)it.bh * (uint32_t)S + (uint32_t)(it.qb * 128)) * kstride + (uint32_t)(t * 128 + row_in_tile);
+                bool key_off = false;      // GEN: this row's key is padded or masked: P = dS = 0
+                if (GEN) {
+                    const int key = t * 128 + row_in_tile;
+                    key_off = key >= args.Sk || (args.kpm != nullptr && args.kpm[(long long)it.b * args.Sk + key] != 0);
+                }
                 const bool dbg_on = args.dbg && blockIdx.x == 0 && ic < 64 && warp_idx == 4 && lane == 0;
                 if (t == 0) mbar_wait(&stats_full[qs], (hc >> 1) & 1);   // -lse / delta of this head (written a head ahead)
                 mbar_wait(&s_full[0], ic & 1);
@@ -451,8 +512,12 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 };
                 auto process = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int g) {
                     uint32_t pp[8], pd[8];
-                    ew_group<DROP>(sv, dv, nls + g * 64, dls + g * 64, c2, pp, pd, drop_key, drop_base + (uint32_t)(g * 16) * (uint32_t)S, (uint32_t)S,
+                    ew_group<DROP>(sv, dv, nls + g * 64, dls + g * 64, c2, pp, pd, drop_key, drop_base + (uint32_t)(g * 16) * kstride, kstride,
                                    args.drop_thresh, args.drop_inv_keep);
+                    if (GEN && key_off) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pp[i] = pd[i] = 0u;
+                    }
                     tmem_st_32x32b_x8(t_lane + kColST + g * 16, pp);
                     const uint32_t dst = (g < 12) ? stg_row + (g >> 2) * kBlk : kv_row + kBlk;   // block 3 aliases V_t
                     const uint32_t ch = (uint32_t)(g & 3) * 2;
@@ -508,7 +573,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     atomicAdd(dst + lane, v[0]);
                 };
                 const bool do_cs = args.colsum != nullptr;
-                const int hd = args.H * 64, hcol = (head - (head / args.H) * args.H) * 64;
+                const int hd = args.H * 64, hcol = it.h * 64;
                 auto stage32 = [&](const uint32_t (&r)[32], uint32_t row_addr, uint32_t hi, float mul) {
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4) {
@@ -519,6 +584,16 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         sts128(row_addr + (((hi * 4 + v4) ^ swz) << 4), w0, w1, w2, w3);
                     }
                 };
+                // GEN: a 32-column fp32 slice of dV_t / dK_t (partial over the item's query block) -> swizzled 128-byte rows for the TMA
+                // reduce-add into the global accumulators
+                auto stage32f = [&](const uint32_t (&r)[32], uint32_t row_addr, float mul) {
+#pragma unroll
+                    for (int v4 = 0; v4 < 8; ++v4)
+                        sts128(row_addr + (((uint32_t)v4 ^ swz) << 4), __float_as_uint(__uint_as_float(r[4 * v4]) * mul),
+                               __float_as_uint(__uint_as_float(r[4 * v4 + 1]) * mul), __float_as_uint(__uint_as_float(r[4 * v4 + 2]) * mul),
+                               __float_as_uint(__uint_as_float(r[4 * v4 + 3]) * mul));
+                };
+                const uint32_t dk_row = smem_u32(smem + L::kDk) + row_in_tile * 128;   // GEN: dK_t columns 0..31; 32..63 at + kBlk
                 // slices: part 0: dV lo, dK hi, [dQ0 lo]; part 1: dV hi, dQ1 lo, [dQ0 hi]; part 2: dK lo, dQ1 hi.
                 // The TMEM loads come first and TMEM is handed back (tile_free) as soon as the last of them has landed, so the next tile's
                 // score products run while the packing, the shared-memory stores and the column-sum butterflies are still in progress.
@@ -535,7 +610,14 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (second) tmem_ld_32x32b_x32(t_lane + (part == 0 ? kColDK + 32 : kColDQ1 + (part - 1) * 32), rb);
                 tmem_ld_wait();
                 if (!third) release_tmem();
-                stage32(ra, part == 2 ? kv_row + kBlk : kv_row, part == 1 ? 1u : 0u, part == 2 ? args.scale : 1.0f);
+                if (GEN) {
+                    if (part != 1) mbar_wait(dk_free, (ic & 1) ^ 1);   // the previous tile's dK_t has left its buffers
+                    if (part == 0) stage32f(ra, kv_row, 1.0f);              // dV_t columns 0..31  -> dead K_t buffer
+                    else if (part == 1) stage32f(ra, kv_row + kBlk, 1.0f);  // dV_t columns 32..63 -> dead V_t buffer
+                    else stage32f(ra, dk_row, args.scale);                  // dK_t columns 0..31
+                } else {
+                    stage32(ra, part == 2 ? kv_row + kBlk : kv_row, part == 1 ? 1u : 0u, part == 2 ? args.scale : 1.0f);
+                }
                 // part 0: dV columns 0..31, part 1: dV 32..63.  dK is skipped: sum_k dS[q,k] = sum_k P (dP - delta) = 0 for every query, so
                 // the column sum of dK = dS^T Q (the key-bias gradient) is exactly zero — softmax ignores a constant key offset.
                 if (do_cs && part < 2) colsum32(ra, 1.0f, t * 128 + row_in_tile < S, args.colsum + 2 * hd + hcol + part * 32);
@@ -545,7 +627,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     release_tmem();
                 }
                 if (part == 0) {
-                    stage32(rb, kv_row + kBlk, 1u, args.scale);
+                    if (GEN) stage32f(rb, dk_row + kBlk, args.scale);          // dK_t columns 32..63
+                    else stage32(rb, kv_row + kBlk, 1u, args.scale);
                 } else if (has_q1) {
                     // The dQ contribution of key tile 0 to the queries >= 128 has to survive the next tile's score products, which
                     // overwrite its accumulator: it is parked as packed bf16 in the 32 TMEM columns nothing else uses (16 per part) —
@@ -619,6 +702,7 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     a.lse = d->lse;
     a.o = reinterpret_cast<const __nv_bfloat16*>(d->o); a.ldo = d->ldo;
     a.batch_stride = d->batch_stride;
+    a.tok_stride = 1;
     a.colsum = d->dqkv_colsum;
     { const char* e = getenv("VITB200_ATTN_BWD_LATE_RELEASE"); a.late_release = (e && e[0] == '1') ? 1 : 0; }
     a.dbg = g_dbg;
@@ -648,10 +732,10 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     do {                                                                                                                    \
         static DeviceOnce configured;                                                                                     \
         if (!configured.is_set()) {                                                                                                  \
-            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<NKS, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<NKS, DR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::kSmem)); \
             configured.set();                                                                                              \
         }                                                                                                                   \
-        attn_bwd_tc5_kernel<NKS, DR><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);            \
+        attn_bwd_tc5_kernel<NKS, DR, false><<<grid, kThreads, Lay<false>::kSmem, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a); \
     } while (0)
     if (a.nks == 13) {
         if (drop) VB_BWD_LAUNCH(13, true); else VB_BWD_LAUNCH(13, false);
@@ -659,6 +743,103 @@ int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
         if (drop) VB_BWD_LAUNCH(0, true); else VB_BWD_LAUNCH(0, false);
     }
 #undef VB_BWD_LAUNCH
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// General path (GEN instantiations): any S / S_kv, key-padding masks, sequence-first strides, cross-attention
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace bwd5 {
+// out[b, s, :] (bf16, caller's strides) = acc[(b * S + s), :] (fp32, contiguous): dK / dV after the reduce-adds of every query block
+__global__ void attn_acc_to_bf16_kernel(const float4* __restrict__ acc, __nv_bfloat16* __restrict__ out, long long ldo, long long tok_stride,
+                                        long long batch_stride, int B, int S, int d4) {
+    const long long total = (long long)B * S * d4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long tok = i / d4;
+        const int c = (int)(i - tok * d4);
+        const int s = (int)(tok % S), b = (int)(tok / S);
+        const float4 v = __ldg(acc + i);
+        uint2 w;
+        w.x = pack2(v.x, v.y);
+        w.y = pack2(v.z, v.w);
+        *reinterpret_cast<uint2*>(out + ((long long)b * batch_stride + (long long)s * tok_stride) * ldo + c * 4) = w;
+    }
+}
+}  // namespace bwd5
+
+size_t attention_bwd_gen_workspace(const VbAttnDesc* d) {
+    const int Sk = d->S_kv > 0 ? d->S_kv : d->S;
+    return 2 * (size_t)d->B * Sk * d->H * 64 * sizeof(float);
+}
+
+int attention_bwd_gen(const VbAttnDesc* d, cudaStream_t stream) {
+    using namespace bwd5;
+    const int S = d->S, Sk = d->S_kv > 0 ? d->S_kv : d->S;
+    const size_t need = attention_bwd_gen_workspace(d);
+    VB_REQUIRE(d->workspace != nullptr && (size_t)d->workspace_bytes >= need && (reinterpret_cast<uintptr_t>(d->workspace) & 255) == 0,
+               "attention_bwd: this shape needs a 256-byte aligned workspace of %zu bytes (vb_attention_workspace_bytes)", need);
+    VB_REQUIRE(d->o != nullptr && (d->ldo * d->tok_stride) % 16 == 0 && d->ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(d->o) & 31) == 0,
+               "attention_bwd: the forward output o (32-byte aligned rows) is needed for delta = rowsum(dO o O)");
+    Args a{};
+    a.B = d->B; a.H = d->H; a.S = S; a.Sk = Sk; a.npad = 128; a.nks = 8;
+    a.n_t = (Sk + 127) / 128;
+    a.n_qb = (S + 127) / 128;
+    const long long items = (long long)d->B * d->H * a.n_qb;
+    VB_REQUIRE(items < (1ll << 31), "attention_bwd: too many work items");
+    a.total_heads = (int)items;
+    a.scale = 0.125f; a.scale_log2 = 0.125f * 1.4426950408889634f;
+    a.lse = d->lse;
+    a.o = reinterpret_cast<const __nv_bfloat16*>(d->o); a.ldo = d->ldo;
+    a.batch_stride = d->batch_stride; a.tok_stride = d->tok_stride;
+    a.kpm = d->key_padding_mask;
+    a.colsum = nullptr;
+    a.late_release = 0;
+    a.dbg = nullptr;
+    const size_t half = (size_t)d->B * Sk * d->H * 64;
+    a.dk_acc = reinterpret_cast<float*>(d->workspace);
+    a.dv_acc = a.dk_acc + half;
+    VB_CUDA_CHECK(cudaMemsetAsync(d->workspace, 0, need, stream));
+    CUtensorMap tq, tk, tv, tdo, tdq;
+    const uint64_t cols = (uint64_t)d->H * 64;
+    int rc;
+    if ((rc = make_tmap_3d(&tq, VB_BF16, d->q, cols, S, d->B, d->tok_stride * d->ldq, d->batch_stride * d->ldq, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tk, VB_BF16, d->k, cols, Sk, d->B, d->tok_stride * d->ldk, d->batch_stride * d->ldk, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tv, VB_BF16, d->v, cols, Sk, d->B, d->tok_stride * d->ldv, d->batch_stride * d->ldv, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tdo, VB_BF16, d->dout, cols, S, d->B, d->tok_stride * d->lddo, d->batch_stride * d->lddo, 64, 128))) return rc;
+    if ((rc = make_tmap_3d(&tdq, VB_BF16, d->dq, cols, S, d->B, d->tok_stride * d->lddq, d->batch_stride * d->lddq, 64, 128))) return rc;
+    int grid = num_sms();
+    if (grid > a.total_heads) grid = a.total_heads;
+    const bool drop = d->dropout_p > 0.f;
+    if (drop) {
+        VB_REQUIRE(d->dropout_p < 1.f && d->dropout_seed != nullptr, "attention dropout: p must be < 1 and dropout_seed non-null");
+        VB_REQUIRE((long long)d->B * d->H * S * Sk < (1ll << 32), "attention dropout: more than 2^32 score elements");
+        a.drop_thresh = dropout_threshold(d->dropout_p);
+        a.drop_inv_keep = 1.0f / (1.0f - d->dropout_p);
+        a.drop_seed = d->dropout_seed;
+        a.drop_stream = d->dropout_stream;
+    }
+    static DeviceOnce configured;
+    if (!configured.is_set()) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::kSmem));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc5_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::kSmem));
+        configured.set();
+    }
+    // here the dK / dV maps address the fp32 accumulators ([B, Sk, H * 64] contiguous; 32-column boxes for the TMA reduce-adds)
+    CUtensorMap tdk, tdv;
+    if ((rc = make_tmap_3d(&tdk, VB_F32, a.dk_acc, cols, Sk, d->B, cols, (uint64_t)Sk * cols, 32, 128))) return rc;
+    if ((rc = make_tmap_3d(&tdv, VB_F32, a.dv_acc, cols, Sk, d->B, cols, (uint64_t)Sk * cols, 32, 128))) return rc;
+    if (drop) attn_bwd_tc5_kernel<8, true, true><<<grid, kThreads, Lay<true>::kSmem, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);
+    else attn_bwd_tc5_kernel<8, false, true><<<grid, kThreads, Lay<true>::kSmem, stream>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a);
+    VB_CUDA_CHECK(cudaGetLastError());
+    const int d4 = (int)(cols / 4);
+    const long long n4 = (long long)d->B * Sk * d4;
+    int cgrid = (int)((n4 + 255) / 256);
+    if (cgrid > num_sms() * 8) cgrid = num_sms() * 8;
+    attn_acc_to_bf16_kernel<<<cgrid, 256, 0, stream>>>(reinterpret_cast<const float4*>(a.dk_acc), reinterpret_cast<__nv_bfloat16*>(d->dk), d->lddk,
+                                                       d->tok_stride, d->batch_stride, d->B, Sk, d4);
+    attn_acc_to_bf16_kernel<<<cgrid, 256, 0, stream>>>(reinterpret_cast<const float4*>(a.dv_acc), reinterpret_cast<__nv_bfloat16*>(d->dv), d->lddv,
+                                                       d->tok_stride, d->batch_stride, d->B, Sk, d4);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

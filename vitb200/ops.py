@@ -11,7 +11,7 @@ from ._lib import VbGemmDesc
 
 # kernels launched by libvitb200.so since import (bench.py reports the per-step delta as `gpu_launches`)
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 2,
+_KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 1,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
                      "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1, "vb_add_rows_bcast": 1, "vb_dropout_f32": 1, "vb_dropout_bf16_pair": 1,
                      "vb_dropout_mask_u8": 1}
@@ -126,6 +126,20 @@ def _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, kpm, S_kv=0):
     return d
 
 
+_ATTN_WS = {}   # (device, backward) -> scratch tensor, grown on demand (VbAttnDesc.workspace: caller-allocated, never retained by the library)
+
+
+def _attn_workspace(lib, d, device, backward):
+    need = lib.vb_attention_workspace_bytes(ctypes.byref(d), 1 if backward else 0)
+    if need <= 0:
+        return
+    key = (device, backward)
+    ws = _ATTN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _ATTN_WS[key] = torch.empty(int(need * 1.25) + 256, device=device, dtype=torch.uint8)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+
+
 def _attn_dropout(d, dropout):
     """dropout: None or (p, seed_dev int32/uint32 tensor, stream_id)."""
     if dropout is not None and dropout[0] > 0:
@@ -137,6 +151,7 @@ def attention_fwd(q, k, v, o, lse, *, B, H, S, tok_stride, batch_stride, key_pad
     lib = _lib.load()
     d = _attn_desc(q, k, v, o, lse, B, H, S, tok_stride, batch_stride, key_padding_mask, S_kv)
     _attn_dropout(d, dropout)
+    _attn_workspace(lib, d, q.device, False)
     _lib.check(lib.vb_attention_fwd(ctypes.byref(d), _stream()), "vb_attention_fwd")
 
 
@@ -153,6 +168,7 @@ def attention_bwd(q, k, v, o, lse, dout, dq, dk, dv, delta, *, B, H, S, tok_stri
     d.delta = delta.data_ptr()
     d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     d.lddq, d.lddk, d.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    _attn_workspace(lib, d, q.device, True)
     _lib.check(lib.vb_attention_bwd(ctypes.byref(d), _stream()), "vb_attention_bwd")
 
 
