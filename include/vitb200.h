@@ -182,6 +182,15 @@ VB_API int vb_add_cast_bf16(const float* a, const float* b, void* out_bf16, int6
 VB_API int vb_add_rows_bcast(const float* x, const float* pos, float* out, int64_t rows, int32_t period, int32_t D, void* stream);
 /* out = a + b_bf16 (+ c_bf16); accum += b_bf16 if accum != NULL (DETR backward: d_src and d_pos assembly) */
 VB_API int vb_add3(const float* a, const void* b_bf16, const void* c_bf16, float* out, float* accum, int64_t n, void* stream);
+/* dst_bf16[r, c] = bf16(src[r, c]), row-pitched (pitches in elements, lddst even): the NCHW backbone feature map as the bf16 operand of
+ * input_proj, the 1x1 convolution in front of the DETR transformer (detr.py:125), run as a GEMM with a_major = 1 */
+VB_API int vb_cast_rows_bf16(const float* src, int64_t ldsrc, void* dst_bf16, int64_t lddst, int64_t rows, int32_t cols, void* stream);
+/* AbsolutePositionalEncoding (detr.py:33-63) in the encoder's sequence-first layout: pos[(y*w + x), n, :] = [col_embed[x] | row_embed[y]]
+ * (fp32, [h*w, N, 2*pf]); bwd ACCUMULATES the embedding-table gradients from dpos of the same layout */
+VB_API int vb_pos_embed_2d_fwd(const float* row_embed, const float* col_embed, float* pos, int32_t h, int32_t w, int32_t N, int32_t pf,
+                               void* stream);
+VB_API int vb_pos_embed_2d_bwd(const float* dpos, float* drow_accum, float* dcol_accum, int32_t h, int32_t w, int32_t N, int32_t pf,
+                               void* stream);
 VB_API int vb_patchify(const float* images, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W, int32_t patch,
                        void* stream);
 /* inverse of vb_patchify: d images [B,C,H,W] fp32 from the bf16 patch-matrix gradient (input gradient of conv_proj, autograd of

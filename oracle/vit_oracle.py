@@ -326,6 +326,41 @@ def detr_encoder_forward(sd, src, *, nhead, num_layers, normalize_before=False, 
 
 
 # ------------------------------------------------------------------------------------------------------------
+# DETR: what sits between the backbone and the encoder — detr.py:33-63 (AbsolutePositionalEncoding), :125 (input_proj),
+# transformer.py:47-53 (flatten to sequence-first), utils/coco/util/misc.py:307-332 (nested_tensor_from_tensor_list)
+# ------------------------------------------------------------------------------------------------------------
+def detr_abs_pos_encoding(row_w, col_w, n, h, w):
+    """AbsolutePositionalEncoding.forward — detr.py:49-63: [n, 2*pf, h, w] with channels [col_embed[x] | row_embed[y]]."""
+    i = torch.arange(w, device=row_w.device)
+    j = torch.arange(h, device=row_w.device)
+    x_emb = F.embedding(i, col_w)
+    y_emb = F.embedding(j, row_w)
+    return torch.cat([x_emb.unsqueeze(0).repeat(h, 1, 1), y_emb.unsqueeze(1).repeat(1, w, 1)], dim=-1).permute(2, 0, 1).unsqueeze(0).repeat(
+        n, 1, 1, 1)
+
+
+def detr_input_proj(features, w, b):
+    """Detr.input_proj — detr.py:125: nn.Conv2d(C_in, hidden, kernel_size=1) on the [N, C_in, h, w] backbone feature map."""
+    return F.conv2d(features, w, b)
+
+
+def detr_flatten(src, pos_embed, mask):
+    """Transformer.forward's first lines — transformer.py:49-53: NxCxHxW -> HWxNxC, mask [N, h, w] -> [N, h*w]."""
+    return src.flatten(2).permute(2, 0, 1), pos_embed.flatten(2).permute(2, 0, 1), mask.flatten(1)
+
+
+def nested_tensor_from_tensor_list(tensor_list):
+    """utils/coco/util/misc.py:307-332: (zero-padded batch [b, c, H, W], mask [b, H, W] with True on padding)."""
+    max_size = [max(img.shape[d] for img in tensor_list) for d in range(3)]
+    tensor = torch.zeros([len(tensor_list)] + max_size, dtype=tensor_list[0].dtype)
+    mask = torch.ones((len(tensor_list), max_size[1], max_size[2]), dtype=torch.bool)
+    for img, pad_img, m in zip(tensor_list, tensor, mask):
+        pad_img[: img.shape[0], : img.shape[1], : img.shape[2]].copy_(img)
+        m[: img.shape[1], : img.shape[2]] = False
+    return tensor, mask
+
+
+# ------------------------------------------------------------------------------------------------------------
 # DETR transformer decoder — transformer.py:66-95 (TransformerDecoder), :118-189 (TransformerDecoderLayer).
 # The reference layer registers its cross-attention as ``multi_head_attn`` (:122) but calls ``self.multihead_attn`` (:148,:172), so it
 # raises AttributeError as written; the restatement below is the forward the code spells out with that name resolved, and it is

@@ -50,3 +50,23 @@ def test_install_rebinds_reference_modules():
     r = subprocess.run([sys.executable, "-c", CODE % (ROOT, REF)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "DROPIN_OK 92" in r.stdout
+
+
+def test_transformer_wrapper_keys_match_reference_constructor():
+    """vitb200.detr_front.Transformer vs the reference's own Transformer.__init__ (transformer.py:25-46): same parameter names and shapes
+    (the forward differs only by the reference's typos), and AbsolutePositionalEncoding / InputProjection carry the keys of detr.py:41-42,125."""
+    if not os.path.isdir(REF):
+        import pytest
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, REF)
+    src = open(os.path.join(REF, "models", "object_detection", "transformer.py")).read()
+    ns = {}
+    exec(compile(src, "ref_transformer", "exec"), ns)          # a private copy of the unmodified module (dropin may have rebound the live one)
+    ref = ns["Transformer"](d_model=256, nhead=4, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=512)
+    from vitb200.detr_front import AbsolutePositionalEncoding, InputProjection, Transformer
+    ours = Transformer(d_model=256, nhead=4, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=512)
+    a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert a == b
+    assert set(AbsolutePositionalEncoding(128).state_dict()) == {"row_embed.weight", "col_embed.weight"}
+    assert {k: tuple(v.shape) for k, v in InputProjection(2048, 256, kernel_size=1).state_dict().items()} == {"weight": (256, 2048, 1, 1), "bias": (256,)}

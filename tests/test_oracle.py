@@ -315,3 +315,48 @@ def test_oracle_against_live_reference():
     assert rel_l2(out, ref) < 1e-5
     for n, p in m.named_parameters():
         assert rel_l2(osd[n].grad, p.grad) < 1e-4, n
+
+
+def _detr_front_oracle(gd):
+    """The oracle's restatement of the DETR front end on the fixture's seeded inputs; returns everything the fixture records."""
+    import torch.nn.functional as F
+    seed, c_in, D = gd["seed"], gd["c_in"], gd["d_model"]
+    g = torch.Generator().manual_seed(seed)
+    imgs = [torch.randn(3, 96, 128, generator=g), torch.randn(3, 112, 104, generator=g)]
+    padded, mask_full = O.nested_tensor_from_tensor_list(imgs)
+    stem = torch.randn(c_in, 3, 8, 8, generator=g) * 0.05
+    feats = F.conv2d(padded, stem, stride=8).detach().requires_grad_(True)
+    mask = F.interpolate(mask_full[None].float(), size=feats.shape[-2:]).to(torch.bool)[0]
+    row_w = torch.rand(50, D // 2, generator=g).requires_grad_(True)
+    col_w = torch.rand(50, D // 2, generator=g).requires_grad_(True)
+    pw = (torch.randn(D, c_in, 1, 1, generator=g) * (1.0 / math.sqrt(c_in))).requires_grad_(True)
+    pb = (torch.randn(D, generator=g) * 0.1).requires_grad_(True)
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.seeded_state_dict(O.detr_param_shapes(D, gd["ffn"], gd["layers"], False), seed + 1).items()}
+    return dict(imgs=imgs, padded=padded, mask_full=mask_full, feats=feats, mask=mask, row_w=row_w, col_w=col_w, pw=pw, pb=pb, sd=sd, g=g)
+
+
+def test_oracle_detr_front_end_matches_reference_golden():
+    """nested_tensor_from_tensor_list (misc.py:307-332), AbsolutePositionalEncoding (detr.py:33-63), input_proj (detr.py:125), the
+    flatten / permute of Transformer.forward (transformer.py:49-53) and the encoder behind them, against the fixture generated from
+    the reference's own code (tools/make_golden.py::detr_front_case)."""
+    gd = load("detr_front_d256.pt")
+    t = _detr_front_oracle(gd)
+    assert tuple(t["padded"].shape) == tuple(gd["padded_shape"]) and abs(t["padded"].sum().item() - gd["padded_sum"]) < 1e-2
+    assert torch.equal(t["padded"][1, 0, 100], gd["padded_1_0_100"]) and torch.equal(t["mask_full"], gd["mask_full"])
+    assert torch.equal(t["mask"], gd["mask_feat"])
+    n, _, h, w = t["feats"].shape
+    import torch.nn.functional as F  # noqa: F401
+    pos = O.detr_abs_pos_encoding(t["row_w"], t["col_w"], n, h, w)
+    assert abs(pos.sum().item() - gd["pos_sum"]) < 1e-2 and torch.allclose(pos[0, :, 0, 0], gd["pos_00"]) and torch.allclose(pos[1, :, -1, -1], gd["pos_last"])
+    src = O.detr_input_proj(t["feats"], t["pw"], t["pb"])
+    assert abs(src.norm().item() - gd["src_norm"]) < 1e-3 * gd["src_norm"] and torch.allclose(src[0, 0], gd["src_n0_c0"], atol=1e-5)
+    s2, p2, m2 = O.detr_flatten(src, pos, t["mask"])
+    out = O.detr_encoder_forward(t["sd"], s2, nhead=gd["nhead"], num_layers=gd["layers"], src_key_padding_mask=m2, pos=p2)
+    gout = torch.randn(out.shape, generator=t["g"])
+    out.backward(gout)
+    assert abs(out.norm().item() - gd["out_norm"]) < 1e-4 * gd["out_norm"] and torch.allclose(out[0], gd["out_row0"], atol=1e-4)
+    assert abs(t["feats"].grad.norm().item() - gd["dfeat_norm"]) < 1e-4 * gd["dfeat_norm"]
+    assert torch.allclose(t["feats"].grad[1, 3], gd["dfeat_n1_c3"], atol=1e-5)
+    assert abs(t["pw"].grad.norm().item() - gd["dW_norm"]) < 1e-4 * gd["dW_norm"] and torch.allclose(t["pw"].grad[0, :, 0, 0], gd["dW_row0"], atol=1e-4)
+    assert torch.allclose(t["pb"].grad, gd["db"], atol=1e-4)
+    assert torch.allclose(t["row_w"].grad, gd["drow"], atol=1e-4) and torch.allclose(t["col_w"].grad, gd["dcol"], atol=1e-4)

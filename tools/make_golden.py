@@ -59,6 +59,64 @@ def vit_case(name, cfg, batch, seed):
     print(name, "loss", loss.item())
 
 
+def _ref_abs_pos_encoding_class():
+    """models/object_detection/detr.py does not parse (its last line is an unfinished assignment), so the class cannot be imported:
+    its source lines (the class statement up to the next top-level statement) are executed as they are."""
+    lines = open(os.path.join(REF, "models", "object_detection", "detr.py")).read().split("\n")
+    i0 = next(i for i, l in enumerate(lines) if l.startswith("class AbsolutePositionalEncoding"))
+    i1 = next(i for i in range(i0 + 1, len(lines)) if lines[i].startswith("def ") or lines[i].startswith("class "))
+    ns = {"torch": torch, "nn": torch.nn, "NestedTensor": object}
+    exec("\n".join(lines[i0:i1]), ns)
+    return ns["AbsolutePositionalEncoding"]
+
+
+def detr_front_case(name, seed, c_in=64, d_model=256, nhead=4, ffn=512, layers=2):
+    """Two images of different sizes -> the reference's nested_tensor_from_tensor_list -> a fixed strided-conv stand-in for the backbone
+    (not on the path) -> the reference's AbsolutePositionalEncoding + nn.Conv2d(C_in, hidden, 1) (detr.py:125) + the flatten / permute
+    lines of Transformer.forward (transformer.py:49-53) -> the reference encoder."""
+    from utils.coco.util.misc import nested_tensor_from_tensor_list as ref_nested
+    RefPos = _ref_abs_pos_encoding_class()
+    g = torch.Generator().manual_seed(seed)
+    imgs = [torch.randn(3, 96, 128, generator=g), torch.randn(3, 112, 104, generator=g)]
+    nt = ref_nested(imgs)
+    stem = torch.randn(c_in, 3, 8, 8, generator=g) * 0.05
+    feats = torch.nn.functional.conv2d(nt.tensors, stem, stride=8).detach().requires_grad_(True)          # [2, c_in, 14, 16]
+    mask = torch.nn.functional.interpolate(nt.mask[None].float(), size=feats.shape[-2:]).to(torch.bool)[0]
+    posm = RefPos(d_model // 2)
+    with torch.no_grad():
+        posm.row_embed.weight.copy_(torch.rand(posm.row_embed.weight.shape, generator=g))
+        posm.col_embed.weight.copy_(torch.rand(posm.col_embed.weight.shape, generator=g))
+
+    class _NT:
+        tensors = feats
+    pos = posm(_NT())
+    proj = torch.nn.Conv2d(c_in, d_model, kernel_size=1)
+    with torch.no_grad():
+        proj.weight.copy_(torch.randn(proj.weight.shape, generator=g) * (1.0 / math.sqrt(c_in)))
+        proj.bias.copy_(torch.randn(proj.bias.shape, generator=g) * 0.1)
+    src = proj(feats)
+    bs, c, h, w = src.shape
+    s2 = src.flatten(2).permute(2, 0, 1)                      # transformer.py:49-53
+    p2 = pos.flatten(2).permute(2, 0, 1)
+    m2 = mask.flatten(1)
+    enc = RefEnc(RefLayer(d_model, nhead, ffn, 0.0, "relu", False), layers, None)
+    sd = O.seeded_state_dict(O.detr_param_shapes(d_model, ffn, layers, False), seed + 1)
+    enc.load_state_dict(sd)
+    enc.train()
+    out = enc(s2, src_key_padding_mask=m2, pos=p2)
+    gout = torch.randn(out.shape, generator=g)
+    out.backward(gout)
+    torch.save({"seed": seed, "c_in": c_in, "d_model": d_model, "nhead": nhead, "ffn": ffn, "layers": layers,
+                "padded_shape": tuple(nt.tensors.shape), "padded_sum": nt.tensors.sum().item(), "padded_1_0_100": nt.tensors[1, 0, 100].clone(),
+                "mask_full": nt.mask.clone(), "mask_feat": mask.clone(), "pos_sum": pos.sum().item(),
+                "pos_00": pos[0, :, 0, 0].clone(), "pos_last": pos[1, :, -1, -1].clone(), "src_norm": src.norm().item(),
+                "src_n0_c0": src[0, 0].detach().clone(), "out_norm": out.norm().item(), "out_row0": out[0].detach().clone(),
+                "dfeat_norm": feats.grad.norm().item(), "dfeat_n1_c3": feats.grad[1, 3].clone(),
+                "dW_norm": proj.weight.grad.norm().item(), "dW_row0": proj.weight.grad[0, :, 0, 0].clone(), "db": proj.bias.grad.clone(),
+                "drow": posm.row_embed.weight.grad.clone(), "dcol": posm.col_embed.weight.grad.clone()}, os.path.join(OUT, name))
+    print(name, "out norm", out.norm().item())
+
+
 def detr_case(name, d_model, nhead, ffn, layers, S, N, seed, pre_norm=False):
     # transformer.py:32-33: the encoder gets a final LayerNorm iff normalize_before
     enc = RefEnc(RefLayer(d_model, nhead, ffn, 0.0, "relu", pre_norm), layers, torch.nn.LayerNorm(d_model) if pre_norm else None)
@@ -256,3 +314,4 @@ if __name__ == "__main__":
     cpe_case("cpe_vit_tiny_b4.pt", "CPEViT", dict(TINY, num_layers=3), 4, 171)
     cpe_case("cpvt_tiny_b4.pt", "CPVT", dict(TINY, num_layers=3), 4, 181)
     cpe_case("cpvt_gap_tiny_b4.pt", "CPVTGAP", dict(TINY, num_layers=2), 4, 191)
+    detr_front_case("detr_front_d256.pt", 301)

@@ -194,6 +194,61 @@ __global__ void add3_kernel(const float4* __restrict__ a, const uint2* __restric
     }
 }
 
+// ---- dst_bf16[r, c] = bf16(src_f32[r, c]) for row-pitched matrices: the NCHW backbone feature map as the (K x M, M contiguous) bf16
+// operand of the input_proj 1x1 convolution-as-GEMM (detr.py:125); the destination pitch is padded to a TMA-legal multiple of 8 ----
+__global__ void cast_rows_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd, long long rows,
+                                 int cols) {
+    const int cp = (cols + 1) >> 1;   // pairs per row
+    const long long total = rows * cp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cp;
+        const int c = (int)(i - r * cp) * 2;
+        const float a = src[r * lds + c];
+        const float b = c + 1 < cols ? src[r * lds + c + 1] : 0.f;
+        if (c + 1 < ldd) *reinterpret_cast<__nv_bfloat162*>(dst + r * ldd + c) = __floats2bfloat162_rn(a, b);
+        else dst[r * ldd + c] = __float2bfloat16_rn(a);
+    }
+}
+
+// ---- learned 2-D position embedding of DETR (AbsolutePositionalEncoding.forward, detr.py:49-63) written straight in the encoder's
+// sequence-first layout: pos[(y * w + x), n, c] = c < pf ? col_embed[x, c] : row_embed[y, c - pf]  (the reference builds [N, 2 pf, h, w]
+// with cat / permute / repeat and Transformer.forward flattens it back: transformer.py:49-52) ----
+__global__ void pos_embed_2d_fwd_kernel(const float* __restrict__ row_embed, const float* __restrict__ col_embed, float* __restrict__ pos,
+                                        int h, int w, int N, int pf) {
+    const int C4 = pf / 2;   // float4 per embedding half... (2 * pf) / 4 vectors per token, pf / 4 per half
+    const long long total = (long long)h * w * N * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % C4);
+        const long long tok = i / C4;             // (y * w + x) * N + n
+        const long long yx = tok / N;
+        const int y = (int)(yx / w), x = (int)(yx - (long long)y * w);
+        const int c = v * 4;
+        const float4 e = c < pf ? __ldg(reinterpret_cast<const float4*>(col_embed + (long long)x * pf + c))
+                                : __ldg(reinterpret_cast<const float4*>(row_embed + (long long)y * pf + (c - pf)));
+        *reinterpret_cast<float4*>(pos + tok * (2 * pf) + c) = e;
+    }
+}
+// d col_embed[x] += sum_{y, n} dpos[(y, x), n, :pf];  d row_embed[y] += sum_{x, n} dpos[(y, x), n, pf:]   (fp32 atomics: a few MB per step)
+__global__ void pos_embed_2d_bwd_kernel(const float* __restrict__ dpos, float* __restrict__ drow, float* __restrict__ dcol, int h, int w, int N,
+                                        int pf) {
+    // one thread per (y or x, channel): the serial walk over the other grid axis and the batch keeps the sums deterministic
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int line = blockIdx.y;                 // 0 .. w - 1: column x;  w .. w + h - 1: row y
+    if (c >= pf) return;
+    float acc = 0.f;
+    if (line < w) {
+        const int x = line;
+        for (int y = 0; y < h; ++y)
+            for (int n = 0; n < N; ++n) acc += dpos[(((long long)y * w + x) * N + n) * (2 * pf) + c];
+        dcol[(long long)x * pf + c] += acc;
+    } else {
+        const int y = line - w;
+        for (int x = 0; x < w; ++x)
+            for (int n = 0; n < N; ++n) acc += dpos[(((long long)y * w + x) * N + n) * (2 * pf) + pf + c];
+        drow[(long long)y * pf + c] += acc;
+    }
+}
+
 static int grid_for(long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = (long long)num_sms() * 8;
@@ -323,6 +378,39 @@ extern "C" int vb_add3(const float* a, const void* b_bf16, const void* c_bf16, f
     add3_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const uint2*>(b_bf16),
                                                                      reinterpret_cast<const uint2*>(c_bf16), reinterpret_cast<float4*>(out),
                                                                      reinterpret_cast<float4*>(accum), n / 4);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_cast_rows_bf16(const float* src, int64_t ldsrc, void* dst_bf16, int64_t lddst, int64_t rows, int32_t cols, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(src && dst_bf16 && rows >= 0 && cols > 0 && ldsrc >= cols && lddst >= cols, "cast_rows: bad arguments");
+    VB_REQUIRE(lddst % 2 == 0 && ((uintptr_t)dst_bf16 & 3) == 0, "cast_rows: destination pitch must be even and the base 4-byte aligned");
+    if (rows == 0) return VB_OK;
+    cast_rows_kernel<<<grid_for(rows * ((cols + 1) / 2), 256), 256, 0, as_stream(stream)>>>(src, ldsrc, reinterpret_cast<__nv_bfloat16*>(dst_bf16),
+                                                                                           lddst, rows, cols);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_pos_embed_2d_fwd(const float* row_embed, const float* col_embed, float* pos, int32_t h, int32_t w, int32_t N, int32_t pf,
+                                   void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(row_embed && col_embed && pos && h > 0 && w > 0 && N > 0 && pf > 0 && pf % 4 == 0, "pos_embed_2d_fwd: bad arguments");
+    VB_REQUIRE(((uintptr_t)row_embed & 15) == 0 && ((uintptr_t)col_embed & 15) == 0 && ((uintptr_t)pos & 15) == 0, "pos_embed_2d_fwd: misaligned");
+    pos_embed_2d_fwd_kernel<<<grid_for((long long)h * w * N * (pf / 2), 256), 256, 0, as_stream(stream)>>>(row_embed, col_embed, pos, h, w, N, pf);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_pos_embed_2d_bwd(const float* dpos, float* drow_accum, float* dcol_accum, int32_t h, int32_t w, int32_t N, int32_t pf,
+                                   void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(dpos && drow_accum && dcol_accum && h > 0 && w > 0 && N > 0 && pf > 0, "pos_embed_2d_bwd: bad arguments");
+    pos_embed_2d_bwd_kernel<<<dim3((pf + 127) / 128, h + w), 128, 0, as_stream(stream)>>>(dpos, drow_accum, dcol_accum, h, w, N, pf);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

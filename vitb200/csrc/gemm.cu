@@ -885,6 +885,11 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
         if (ep == VB_EPI_STORE && cd == VB_F32) VB_LAUNCH(0, 1, VB_EPI_STORE, VB_F32);
         if (ep == VB_EPI_DGELU && cd == VB_BF16) VB_LAUNCH(0, 1, VB_EPI_DGELU, VB_BF16);
         if (ep == VB_EPI_DRELU && cd == VB_BF16) VB_LAUNCH(0, 1, VB_EPI_DRELU, VB_BF16);
+    } else if (am == 1 && bm == 0) {
+        // A stored [K, M] (M contiguous), B stored [N, K]: the 1x1 input_proj convolution on an NCHW feature map (detr.py:125) —
+        // forward (A = features [C_in, HW], B = weight), weight gradient (A = dY [tokens, hidden], B = features) and input gradient
+        if (ep == VB_EPI_STORE && cd == VB_F32) VB_LAUNCH(1, 0, VB_EPI_STORE, VB_F32);
+        if (ep == VB_EPI_ACCUM && cd == VB_F32) VB_LAUNCH(1, 0, VB_EPI_ACCUM, VB_F32);
     } else if (am == 1 && bm == 1) {
         if (ep == VB_EPI_ACCUM && cd == VB_F32) VB_LAUNCH(1, 1, VB_EPI_ACCUM, VB_F32);
         if (ep == VB_EPI_STORE && cd == VB_F32) VB_LAUNCH(1, 1, VB_EPI_STORE, VB_F32);

@@ -70,6 +70,11 @@ def install(reference_root, stub_missing=True):
     # the decoder: the reference layer cannot run as written (transformer.py:122 vs :148); ours resolves the name
     ref_tr.TransformerDecoderLayer = our_detr.TransformerDecoderLayer
     ref_tr.TransformerDecoder = our_detr.TransformerDecoder
+    # Transformer (transformer.py:25-63): the reference's constructor; its forward ends in two typos (memory.permte, hs.transpose(1, 1)),
+    # ours is the forward the code spells out.  AbsolutePositionalEncoding / input_proj / NestedTensor live in detr.py, which does not
+    # parse (:155) and therefore cannot be rebound: import them from vitb200.detr_front.
+    from . import detr_front as our_front
+    ref_tr.Transformer = our_front.Transformer
 
     # timm shim for models/image_classification/deit.py:4-5
     have_timm = True

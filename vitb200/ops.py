@@ -14,7 +14,7 @@ LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 1,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
                      "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1, "vb_add_rows_bcast": 1, "vb_dropout_f32": 1, "vb_dropout_bf16_pair": 1,
-                     "vb_dropout_mask_u8": 1}
+                     "vb_dropout_mask_u8": 1, "vb_cast_rows_bf16": 1, "vb_pos_embed_2d_fwd": 1, "vb_pos_embed_2d_bwd": 1}
 
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_ACCUM = range(7)
 BF16, F32 = 0, 1
@@ -202,6 +202,26 @@ def cast_bf16(src, dst):
     lib = _lib.load()
     assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
     _lib.check(lib.vb_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "vb_cast_f32_to_bf16")
+
+
+def cast_rows_bf16(src, dst):
+    """dst (bf16 [rows, cols] view, any even pitch) = bf16(src) (fp32 [rows, cols] view)."""
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.shape == dst.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    _lib.check(_lib.load().vb_cast_rows_bf16(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0], src.shape[1], _stream()),
+               "vb_cast_rows_bf16")
+
+
+def pos_embed_2d_fwd(row_embed, col_embed, pos, h, w, N):
+    """pos: fp32 [h*w, N, 2*pf] contiguous."""
+    pf = row_embed.shape[1]
+    assert pos.is_contiguous() and pos.shape == (h * w, N, 2 * pf) and row_embed.is_contiguous() and col_embed.is_contiguous()
+    _lib.check(_lib.load().vb_pos_embed_2d_fwd(row_embed.data_ptr(), col_embed.data_ptr(), pos.data_ptr(), h, w, N, pf, _stream()), "vb_pos_embed_2d_fwd")
+
+
+def pos_embed_2d_bwd(dpos, drow, dcol, h, w, N):
+    pf = drow.shape[1]
+    assert dpos.is_contiguous() and dpos.dtype == torch.float32 and dpos.shape == (h * w, N, 2 * pf)
+    _lib.check(_lib.load().vb_pos_embed_2d_bwd(dpos.data_ptr(), drow.data_ptr(), dcol.data_ptr(), h, w, N, pf, _stream()), "vb_pos_embed_2d_bwd")
 
 
 def patchify(images, out, patch):
