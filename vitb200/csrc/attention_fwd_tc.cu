@@ -26,6 +26,7 @@
 #include "ptx.cuh"
 #include "attn_tc_common.cuh"
 #include "dropout.cuh"
+#include "pdl.cuh"
 
 namespace vb {
 
@@ -122,6 +123,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int nks = NKS_T ? NKS_T : args.nks;
     const int npad = nks * 16;
     const int jA = nks < 8 ? nks : 8;
+    pdl_launch_dependents();
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
@@ -144,6 +146,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();
 
     if (warp_idx == 0) {
         if (lane == 0) {   // ---------------- TMA loader ----------------
@@ -508,7 +511,7 @@ int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream) {
             VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc3_kernel<NKS, DR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::kSmem)); \
             configured.set();                                                                                              \
         }                                                                                                                   \
-        attn_fwd_tc3_kernel<NKS, DR, false><<<grid, kThreads, Lay<false>::kSmem, stream>>>(tq, tk, tv, to, a);              \
+        VB_CUDA_CHECK(launch_pdl(attn_fwd_tc3_kernel<NKS, DR, false>, dim3(grid), dim3(kThreads), Lay<false>::kSmem, stream, tq, tk, tv, to, a)); \
     } while (0)
     if (a.nks == 13) {
         if (drop) VB_FWD_LAUNCH(13, true); else VB_FWD_LAUNCH(13, false);
@@ -645,10 +648,9 @@ int attention_fwd_gen(const VbAttnDesc* d, cudaStream_t stream) {
         configured.set();
     }
     // 176-key blocks (every long sequence: S_kv > 176 splits into blocks of ~176) get the fully unrolled instantiation
-    if (drop) attn_fwd_tc3_kernel<0, true, true><<<grid, kThreads, Lay<true>::kSmem, stream>>>(tq, tk, tv, to, a);
-    else if (a.nks == 11) attn_fwd_tc3_kernel<11, false, true><<<grid, kThreads, Lay<true>::kSmem, stream>>>(tq, tk, tv, to, a);
-    else attn_fwd_tc3_kernel<0, false, true><<<grid, kThreads, Lay<true>::kSmem, stream>>>(tq, tk, tv, to, a);
-    VB_CUDA_CHECK(cudaGetLastError());
+    if (drop) VB_CUDA_CHECK(launch_pdl(attn_fwd_tc3_kernel<0, true, true>, dim3(grid), dim3(kThreads), Lay<true>::kSmem, stream, tq, tk, tv, to, a));
+    else if (a.nks == 11) VB_CUDA_CHECK(launch_pdl(attn_fwd_tc3_kernel<11, false, true>, dim3(grid), dim3(kThreads), Lay<true>::kSmem, stream, tq, tk, tv, to, a));
+    else VB_CUDA_CHECK(launch_pdl(attn_fwd_tc3_kernel<0, false, true>, dim3(grid), dim3(kThreads), Lay<true>::kSmem, stream, tq, tk, tv, to, a));
     if (a.n_kb > 1) {
         const long long units = (long long)d->B * S * d->H;
         attn_merge_kernel<<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(opart, a.lse_part, reinterpret_cast<__nv_bfloat16*>(d->o), d->ldo,

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
+#include "pdl.cuh"
 
 namespace vb {
 
@@ -212,6 +213,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const uint32_t warp_idx = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
+    pdl_launch_dependents();   // the next kernel's CTAs may take this SM's place as soon as this CTA exits (pdl.cuh)
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -245,6 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();                // everything above is independent of the kernels in front; from here on their results are needed
 
     // ---- tile scheduling ----------------------------------------------------------------------------------------------
     // Static: cluster c owns units c, c + #clusters, ...  Dynamic (args.sched_counter): the first unit is still the cluster index,
@@ -735,13 +738,15 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMa
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled_gemm() ? 2 : 1;
     VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tA, tB, tC, tC2, tX, args));
     return VB_OK;
 }

@@ -6,6 +6,7 @@
 // residual-gradient add (x = x + f(LN(x)) => dx = dres + LN'(dy)) and the per-column sum of its output, which
 // is the bias gradient of the linear layer that produced this LayerNorm's input stream.
 #include "common.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 
 namespace vb {
@@ -38,6 +39,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();
     if (row >= rows) return;
     auto ok = [&](int i) { return !kTail || i < NV - 1 || lane < 16; };
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
@@ -108,6 +111,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const void* __restrict__
         *reinterpret_cast<float4*>(mine + 2 * D + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    pdl_launch_dependents();
+    pdl_wait();
 
     for (int row = blockIdx.x * wpb + warp; row < rows; row += gridDim.x * wpb) {
         const float mu = mean[row], rs = rstd[row];
@@ -190,10 +195,9 @@ static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, cons
                          float* y_f32, long long ldyf, float* mean, float* rstd, int rows, float eps, const float* add,
                          long long ldadd, void* y2, long long ldy2, cudaStream_t st) {
     const int wpb = 8;
-    ln_fwd_kernel<D><<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, ldx, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), ldyb,
-                                                                  y_f32, ldyf, mean, rstd, rows, eps, add, ldadd,
-                                                                  reinterpret_cast<__nv_bfloat16*>(y2), ldy2);
-    VB_CUDA_CHECK(cudaGetLastError());
+    VB_CUDA_CHECK(launch_pdl(ln_fwd_kernel<D>, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, st, x, ldx, gamma, beta,
+                             reinterpret_cast<__nv_bfloat16*>(y_bf16), ldyb, y_f32, ldyf, mean, rstd, rows, eps, add, ldadd,
+                             reinterpret_cast<__nv_bfloat16*>(y2), ldy2));
     return VB_OK;
 }
 
@@ -211,10 +215,9 @@ static int ln_bwd_launch(const void* dy, long long lddy, const float* x, long lo
     const int need = (rows + wpb - 1) / wpb;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<grid, wpb * 32, smem, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx,
-                                       reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta, colsum, rows,
-                                       reinterpret_cast<const __nv_bfloat16*>(dy_add), lddya);
-    VB_CUDA_CHECK(cudaGetLastError());
+    VB_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(wpb * 32), smem, st, dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx,
+                             reinterpret_cast<__nv_bfloat16*>(dxb), lddxb, dgamma, dbeta, colsum, rows,
+                             reinterpret_cast<const __nv_bfloat16*>(dy_add), lddya));
     return VB_OK;
 }
 

@@ -1,5 +1,7 @@
 // Library-level entry points of libvitb200.so: version, error text, device checks.
 #include "common.h"
+#include "pdl.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -40,6 +42,17 @@ static int query_device(int dev) {
     }
     return 0;
 }
+
+int pdl_level() {   // VITB200_PDL: 0 = off (default), 1 = every PDL-aware kernel, 2 = GEMM only, 3 = everything but the GEMM
+    static int lvl = -1;
+    if (lvl < 0) {
+        const char* e = getenv("VITB200_PDL");
+        lvl = e ? atoi(e) : 0;
+    }
+    return lvl;
+}
+bool pdl_enabled() { return pdl_level() == 1 || pdl_level() == 3; }
+bool pdl_enabled_gemm() { return pdl_level() == 1 || pdl_level() == 2; }
 
 int num_sms() {
     int dev = 0;
