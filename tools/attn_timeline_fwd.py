@@ -19,7 +19,7 @@ for rep in range(2):
 lib.vb_debug_set_attn_timeline(None)
 t = dbg.view(64, 16).cpu()
 t0 = t[0, 0].item()
-print("tile (softmax group = tile & 1): start | wait S | pass 1 (row max) | exchange | pass 2 (exp, pack)   (cycles; stamps of warp 4 / 12 lane 0)")
+print("tile: start | wait S | load + row max | exchange | exp, pack, store   (cycles; stamps of warp 4 lane 0)")
 for i in range(24):
     r = [x.item() - t0 for x in t[i, :5]]
     print(f"{i:2d}: start {r[0]:7d} | waitS {r[1]-r[0]:5d} | pass1 {r[2]-r[1]:5d} | exch {r[3]-r[2]:5d} | pass2 {r[4]-r[3]:5d} | total {r[4]-r[0]:6d}")

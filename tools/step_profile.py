@@ -81,5 +81,8 @@ for tag, a, b in rec:
 total = s0.elapsed_time(s1)
 ksum = sum(tot.values())
 print(f"{which}: step {total:.2f} ms, sum of bracketed ops {ksum:.2f} ms, batch {B}")
+if os.environ.get("STEP_PROFILE_LIST"):
+    want = os.environ["STEP_PROFILE_LIST"]
+    print(want, "per call (us):", " ".join(f"{a.elapsed_time(b) * 1e3:.0f}" for tag, a, b in rec if tag.startswith(want)))
 for k, v in tot.most_common():
     print(f"  {k:34s} n={cnt[k]:3d} {v:8.3f} ms {100 * v / total:5.1f}%")

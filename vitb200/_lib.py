@@ -9,6 +9,8 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+if os.environ.get("VITB200_LIB"):      # experiments: an alternative build of the library (tools only; the product path is the in-tree .so)
+    LIB_PATH = os.environ["VITB200_LIB"]
 
 
 class VbError(RuntimeError):

@@ -11,7 +11,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libvitb200.so")
+LIB = os.environ.get("VITB200_BUILD_LIB") or os.path.join(HERE, "libvitb200.so")
+if os.environ.get("VITB200_BUILD_LIB"):
+    OBJ = OBJ + "_" + os.path.basename(LIB)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -19,7 +21,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("VITB200_NVCC_DEFS", "").split()      # experiments: extra -D flags (e.g. -DVB_FWD4_POLY_EVERY=5)
 
 
 def _sources():

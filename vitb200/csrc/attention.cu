@@ -888,7 +888,8 @@ static unsigned delta_grid(long long units) {
 }
 
 int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream);   // attention_tc.cu (older tcgen05 path: S <= 256, key-padding masks)
-int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream);  // attention_fwd_tc.cu (S <= 208, no mask: three threads per row)
+int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream);  // attention_fwd_tc.cu (S <= 208, no mask: two-pass softmax, two threads per row)
+int attention_fwd_tc4(const VbAttnDesc* d, cudaStream_t stream);  // attention_fwd_tc4.cu (193 <= S <= 208: score row in registers, four threads per row)
 int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream);   // attention_bwd_tc.cu (five-product tcgen05 path, S <= 208)
 int attention_fwd_gen(const VbAttnDesc* d, cudaStream_t stream);   // attention_fwd_tc.cu: any S / S_kv, masks, strides (tcgen05)
 int attention_bwd_gen(const VbAttnDesc* d, cudaStream_t stream);   // attention_bwd_tc.cu
@@ -976,7 +977,9 @@ extern "C" int vb_attention_fwd(const VbAttnDesc* d, void* stream) {
     if (!one_block_shape(d) && gen_enabled()) return attention_fwd_gen(d, as_stream(stream));
     if (p.Sk != p.S) return launch_generic_fwd(d, p, as_stream(stream));   // cross-attention: query and key counts differ
     if (d->S <= 256) {
-        int tc = attention_fwd_tc3(d, as_stream(stream));
+        int tc = attention_fwd_tc4(d, as_stream(stream));
+        if (tc <= 0) return tc;
+        tc = attention_fwd_tc3(d, as_stream(stream));
         if (tc <= 0) return tc;
         if (d->dropout_p > 0.f) return launch_generic_fwd(d, p, as_stream(stream));   // masks / sequence-first layouts with dropout
         tc = attention_fwd_tc(d, as_stream(stream));

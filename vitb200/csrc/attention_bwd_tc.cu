@@ -33,6 +33,14 @@
 #include "attn_tc_common.cuh"
 #include "dropout.cuh"
 
+// In-kernel cycle stamps (tools/attn_timeline*.py) are compiled in only with -DVB_ATTN_DBG (VITB200_NVCC_DEFS=-DVB_ATTN_DBG python -m
+// vitb200.build): even predicated off they cost issue slots in the element-wise loops.
+#ifdef VB_ATTN_DBG
+#define VB_DBG(cond, slot) do { if (cond) slot = clock64(); } while (0)
+#else
+#define VB_DBG(cond, slot) do { (void)(cond); } while (0)
+#endif
+
 namespace vb {
 
 int make_tmap_3d(CUtensorMap* m, int dtype, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
@@ -103,44 +111,53 @@ __device__ __forceinline__ Item decode_item(const Args& a, int item) {
     return it;
 }
 
-// 16 columns of one tile row: P^T / dS^T from the raw scores sv and their gradient dv (one TMEM lane = one key).  nls / dls point at
-// -lse[q] and -delta[q] of the 16 queries; the arithmetic is fp32x2-packed (FFMA2 / FADD2 / FMUL2: half the issue slots).
+// 16 columns of one tile row, phase 1: P^T = exp2(S^T c - lse[q]) from the raw scores sv (one TMEM lane = one key), packed to bf16 (pp,
+// the A operand of dV) and kept in fp32 (pf) for phase 2.  nls points at -lse[q] of the 16 queries; fp32x2-packed arithmetic.
 // DROP (attention dropout): element (query q, key) of head-local index didx0 + j * S was kept iff its hash clears the threshold;
-// dV sees keep * P / (1 - p), and dP = keep * (dO V^T) / (1 - p) enters dS = P o (dP - delta) (delta = rowsum(dO o O) still holds).
+// dV sees keep * P / (1 - p); `keep` returns the 16 keep bits for phase 2.
 template <bool DROP>
-__device__ __forceinline__ void ew_group(const uint32_t (&sv)[16], const uint32_t (&dv)[16], uint32_t nls, uint32_t dls, f2 c2,
-                                         uint32_t (&pp)[8], uint32_t (&pd)[8], uint32_t dkey, uint32_t didx0, uint32_t S, uint32_t thresh,
-                                         float inv_keep) {
+__device__ __forceinline__ void ew_phase1(const uint32_t (&sv)[16], uint32_t nls, f2 c2, f2 (&pf)[8], uint32_t (&pp)[8], uint32_t& keep,
+                                          uint32_t dkey, uint32_t didx0, uint32_t S, uint32_t thresh, float inv_keep) {
+    keep = 0u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        f2 l01, l23, d01, d23;
+        f2 l01, l23;
         lds_2xf2(nls + 16 * i, l01, l23);
-        lds_2xf2(dls + 16 * i, d01, d23);
         float x0, x1, x2, x3;
         f2_unpack(f2_fma(f2_pack_u(sv[4 * i + 0], sv[4 * i + 1]), c2, l01), x0, x1);
         f2_unpack(f2_fma(f2_pack_u(sv[4 * i + 2], sv[4 * i + 3]), c2, l23), x2, x3);
         const float p0 = ex2f(x0), p1 = ex2f(x1), p2 = ex2f(x2), p3 = ex2f(x3);
-        f2 g01 = f2_pack_u(dv[4 * i + 0], dv[4 * i + 1]), g23 = f2_pack_u(dv[4 * i + 2], dv[4 * i + 3]);
-        f2 p01 = f2_pack(p0, p1), p23 = f2_pack(p2, p3);
+        pf[2 * i] = f2_pack(p0, p1);
+        pf[2 * i + 1] = f2_pack(p2, p3);
         if (DROP) {
-            const f2 k01 = f2_pack(dropout_keep(dkey, didx0 + (4 * i + 0) * S, thresh) ? inv_keep : 0.f,
-                                   dropout_keep(dkey, didx0 + (4 * i + 1) * S, thresh) ? inv_keep : 0.f);
-            const f2 k23 = f2_pack(dropout_keep(dkey, didx0 + (4 * i + 2) * S, thresh) ? inv_keep : 0.f,
-                                   dropout_keep(dkey, didx0 + (4 * i + 3) * S, thresh) ? inv_keep : 0.f);
-            float a, b;
-            f2_unpack(f2_mul(p01, k01), a, b);
-            pp[2 * i] = pack2(a, b);
-            f2_unpack(f2_mul(p23, k23), a, b);
-            pp[2 * i + 1] = pack2(a, b);
-            g01 = f2_mul(g01, k01);
-            g23 = f2_mul(g23, k23);
+            const bool k0 = dropout_keep(dkey, didx0 + (4 * i + 0) * S, thresh), k1 = dropout_keep(dkey, didx0 + (4 * i + 1) * S, thresh);
+            const bool k2 = dropout_keep(dkey, didx0 + (4 * i + 2) * S, thresh), k3 = dropout_keep(dkey, didx0 + (4 * i + 3) * S, thresh);
+            keep |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u) | (k2 ? 4u : 0u) | (k3 ? 8u : 0u)) << (4 * i);
+            pp[2 * i] = pack2(k0 ? p0 * inv_keep : 0.f, k1 ? p1 * inv_keep : 0.f);
+            pp[2 * i + 1] = pack2(k2 ? p2 * inv_keep : 0.f, k3 ? p3 * inv_keep : 0.f);
         } else {
             pp[2 * i] = pack2(p0, p1);
             pp[2 * i + 1] = pack2(p2, p3);
         }
+    }
+}
+// phase 2: dS^T = P^T o (dP^T - delta[q]) from the score gradients dv; dls points at -delta[q]; with dropout dP = keep * (dO V^T) / (1 - p)
+// (delta = rowsum(dO o O) still holds).
+template <bool DROP>
+__device__ __forceinline__ void ew_phase2(const f2 (&pf)[8], const uint32_t (&dv)[16], uint32_t dls, uint32_t (&pd)[8], uint32_t keep, float inv_keep) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f2 d01, d23;
+        lds_2xf2(dls + 16 * i, d01, d23);
+        f2 g01 = f2_pack_u(dv[4 * i + 0], dv[4 * i + 1]), g23 = f2_pack_u(dv[4 * i + 2], dv[4 * i + 3]);
+        if (DROP) {
+            const uint32_t kb = keep >> (4 * i);
+            g01 = f2_mul(g01, f2_pack((kb & 1u) ? inv_keep : 0.f, (kb & 2u) ? inv_keep : 0.f));
+            g23 = f2_mul(g23, f2_pack((kb & 4u) ? inv_keep : 0.f, (kb & 8u) ? inv_keep : 0.f));
+        }
         float s0, s1, s2, s3;
-        f2_unpack(f2_mul(p01, f2_add(g01, d01)), s0, s1);
-        f2_unpack(f2_mul(p23, f2_add(g23, d23)), s2, s3);
+        f2_unpack(f2_mul(pf[2 * i], f2_add(g01, d01)), s0, s1);
+        f2_unpack(f2_mul(pf[2 * i + 1], f2_add(g23, d23)), s2, s3);
         pd[2 * i] = pack2(s0, s1);
         pd[2 * i + 1] = pack2(s2, s3);
     }
@@ -234,7 +251,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int nq = GEN ? min(128, S - q0) : S;                 // valid queries of this item
             mbar_wait(&qdo_empty[qs], ((hc >> 1) & 1) ^ 1);
             const bool sdbg = args.dbg && blockIdx.x == 0 && hc < 32 && lane == 0;   // stamps in the row of the head's first tile
-            if (sdbg) args.dbg[hc * 2 * 16 + 13] = clock64();
+            VB_DBG(sdbg, args.dbg[hc * 2 * 16 + 13]);
             float* nl = stats + qs * 2 * kMaxQ;
             float* dl = nl + kMaxQ;
             const float* gl = args.lse + (long long)it.bh * S + q0;
@@ -284,7 +301,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (i < (int)kMaxQ) nl[i] = lv[r];
             }
             mbar_wait(&qdo_full[qs], (hc >> 1) & 1);          // dO has landed
-            if (sdbg) args.dbg[hc * 2 * 16 + 14] = clock64();
+            VB_DBG(sdbg, args.dbg[hc * 2 * 16 + 14]);
             const uint8_t* sdo_p = smem + kQdoOff + qs * 2 * kQSlot + kQSlot;
             // acc += a.lo * b.lo + a.hi * b.hi with bf16 operands and fp32 accumulation: the mixed-precision FMA of sm_100
             // (FHFMA.BF16 with half-register selectors) needs no unpacking — one instruction per multiply-add
@@ -322,7 +339,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&stats_full[qs]);
-            if (sdbg) args.dbg[hc * 2 * 16 + 15] = clock64();
+            VB_DBG(sdbg, args.dbg[hc * 2 * 16 + 15]);
         }
     } else if (warp_idx == 2) {
         // ---------------- store warp: output tiles (shared memory) -> global by TMA, then recycle the buffers ----------------
@@ -353,6 +370,47 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tma_store_commit();
                 }
                 __syncwarp();
+                if (!GEN && args.colsum != nullptr) {
+                    // In-projection bias gradient (torch/nn/functional.py:5835-5847): column sums of the staged bf16 dV / dQ tiles, taken
+                    // HERE — by the otherwise idle store warp, while the TMA engine reads the same tiles — instead of by butterfly
+                    // shuffles in the read-out of the element-wise warps (that was 60 us of a 240 us launch, on the critical path).
+                    // The dK part is skipped: sum_k dS[q,k] = sum_k P (dP - delta) = 0 for every query, so the column sum of
+                    // dK = dS^T Q (the key-bias gradient) is exactly zero — softmax ignores a constant key offset.
+                    auto colsum_tile = [&](const uint8_t* tile, int valid_rows, float* dst) {
+                        const uint32_t base = smem_u32(tile);
+                        const int c = lane & 7, rg = lane >> 3;
+                        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                        for (int i = 0; i < 32; ++i) {
+                            const int r = 4 * i + rg;
+                            if (r < valid_rows) {
+                                uint32_t w[4];
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                                             : "r"(base + r * 128 + ((c ^ (r & 7)) << 4)));
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)   // fp32 += bf16 (FHADD.BF16 with half-register selectors: no unpacking)
+                                    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+                                        : "+f"(acc[2 * q]), "+f"(acc[2 * q + 1]) : "r"(w[q]));
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 8);
+                            acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+                        }
+                        if (rg == 0) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) atomicAdd(dst + c * 8 + q, acc[q]);
+                        }
+                    };
+                    const int hd = args.H * 64;
+                    colsum_tile(kb, min(128, S - t * 128), args.colsum + 2 * hd + h * 64);
+                    if (last) {
+                        colsum_tile(qb, min(128, S), args.colsum + h * 64);
+                        if (has_q1) colsum_tile(qb + kBlk, S - 128, args.colsum + h * 64);
+                    }
+                    __syncwarp();
+                }
                 if (lane == 0) {
                     tma_store_wait_read<0>();
                     mbar_arrive(&kv_empty[ks]);
@@ -384,22 +442,31 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const int ks = ic & 1;
                 const uint32_t sK = smem_u32(smem + kKvOff + ks * 2 * kBlk), sV = sK + kBlk;
                 mbar_wait(&kv_full[ks], (ic >> 1) & 1);
-                mbar_wait(tile_free, (ic & 1) ^ 1);
                 tcgen05_fence_after();
                 const bool dbg_on = args.dbg && blockIdx.x == 0 && ic < 64 && lane == 0;
-                if (dbg_on) args.dbg[ic * 16 + 0] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 0]);
+                // S^T = K_t Q^T goes first and does not wait for the previous tile's read-out: its columns only hold the packed P^T that the
+                // dV products in front of it in the (in-order) tensor pipe consume, so it runs while the accumulators are still being read.
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16_ss(tb + kColST, umma_smem_desc(kdesc, sK + k * 32), umma_smem_desc(kdesc, sQ + k * 32), idesc_sA, k > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tb + kColDPT, umma_smem_desc(kdesc, sV + k * 32), umma_smem_desc(kdesc, sdO + k * 32), idesc_sA, k > 0 ? 1u : 0u);
-                    umma_commit(&s_full[0]);
                     if (nB > 0) {   // queries >= 128: rows 128.. of Q / dO, columns 128.. of the score regions
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16_ss(tb + kColST + 128, umma_smem_desc(kdesc, sK + k * 32), umma_smem_desc(kdesc, sQ + kBlk + k * 32), idesc_sB, k > 0 ? 1u : 0u);
+                    }
+                }
+                __syncwarp();
+                // dP^T = V_t dO^T lands on the columns that hold the previous tile's dV / dK / dQ accumulators: after the read-out
+                mbar_wait(tile_free, (ic & 1) ^ 1);
+                tcgen05_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tb + kColDPT, umma_smem_desc(kdesc, sV + k * 32), umma_smem_desc(kdesc, sdO + k * 32), idesc_sA, k > 0 ? 1u : 0u);
+                    umma_commit(&s_full[0]);
+                    if (nB > 0) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16_ss(tb + kColDPT + 128, umma_smem_desc(kdesc, sV + k * 32), umma_smem_desc(kdesc, sdO + kBlk + k * 32), idesc_sB, k > 0 ? 1u : 0u);
@@ -407,7 +474,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                 }
                 __syncwarp();
-                if (dbg_on) args.dbg[ic * 16 + 1] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 1]);
                 const uint64_t bd_do = umma_smem_desc(mdesc, sdO), bd_q = umma_smem_desc(mdesc, sQ), bd_k = umma_smem_desc(mdesc, sK);
                 const uint64_t ad_q0 = umma_smem_desc(mdesc, stg);
                 const uint64_t ad_q1 = umma_smem_desc(umma_smem_desc_base(sV - (stg + 2 * kBlk), 1024), stg + 2 * kBlk);
@@ -416,7 +483,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 // ---- first part: queries < 128 ----
                 mbar_wait(&p_full[0], ic & 1);
                 tcgen05_fence_after();
-                if (dbg_on) args.dbg[ic * 16 + 2] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 2]);
                 if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)   // dV_t = P^T dO: A = packed P^T of group j at TMEM column 16 j
@@ -452,7 +519,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     umma_commit(o_full);
                 }
                 __syncwarp();
-                if (dbg_on) args.dbg[ic * 16 + 3] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 3]);
             }
         }
     } else if (warp_idx >= 4) {
@@ -488,7 +555,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (t == 0) mbar_wait(&stats_full[qs], (hc >> 1) & 1);   // -lse / delta of this head (written a head ahead)
                 mbar_wait(&s_full[0], ic & 1);
                 tcgen05_fence_after();
-                if (dbg_on) args.dbg[ic * 16 + 4] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 4]);
                 bool arrivedA = false, waitedB = false;
                 auto arriveA = [&]() {
                     tmem_st_wait();
@@ -498,22 +565,31 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (lane == 0) mbar_arrive(&p_full[0]);
                     arrivedA = true;
                 };
-                // Software-pipelined over this warp's 16-query groups (g, g + 3, g + 6, ...): the TMEM loads of the next group are in
-                // flight while the current one is exponentiated, packed and stored — with three warps per scheduler the ld -> ex2 ->
-                // pack -> st chain of a single group was the critical path (700 cycles per group against 128 cycles of MUFU work).
-                auto issue = [&](uint32_t (&sv)[16], uint32_t (&dv)[16], int g) {
+                // Software-pipelined over this warp's 16-query groups (g, g + 3, g + 6, ...): the scores of the NEXT group are prefetched
+                // from TMEM while the current group is exponentiated; the current group's score gradients are loaded at the top of its
+                // own step, under the MUFU latency of the exponentials (a second prefetch buffer for them costs 16 registers this kernel
+                // does not have: 512 threads x 128).
+                auto wait_b = [&](int g) {
                     if (g >= 8 && !waitedB) {      // queries >= 128: their scores are committed separately
                         mbar_wait(&s_full[1], ic & 1);
                         tcgen05_fence_after();
                         waitedB = true;
                     }
-                    tmem_ld_32x32b_x16(t_lane + kColST + g * 16, sv);
-                    tmem_ld_32x32b_x16(t_lane + kColDPT + g * 16, dv);
                 };
-                auto process = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int g) {
-                    uint32_t pp[8], pd[8];
-                    ew_group<DROP>(sv, dv, nls + g * 64, dls + g * 64, c2, pp, pd, drop_key, drop_base + (uint32_t)(g * 16) * kstride, kstride,
-                                   args.drop_thresh, args.drop_inv_keep);
+                // svc: scores of group g (already requested); svn: buffer for the scores of group g + 3
+                auto step = [&](const uint32_t (&svc)[16], uint32_t (&svn)[16], int g) {
+                    uint32_t dv[16], pp[8], pd[8], keep;
+                    f2 pf[8];
+                    tmem_ld_wait();                                            // svc has landed
+                    tmem_ld_32x32b_x16(t_lane + kColDPT + g * 16, dv);
+                    if (g + 3 < nks) {
+                        wait_b(g + 3);
+                        tmem_ld_32x32b_x16(t_lane + kColST + (g + 3) * 16, svn);
+                    }
+                    ew_phase1<DROP>(svc, nls + g * 64, c2, pf, pp, keep, drop_key, drop_base + (uint32_t)(g * 16) * kstride, kstride,
+                                    args.drop_thresh, args.drop_inv_keep);
+                    tmem_ld_wait();                                            // dv (and the prefetched scores) have landed
+                    ew_phase2<DROP>(pf, dv, dls + g * 64, pd, keep, args.drop_inv_keep);
                     if (GEN && key_off) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pp[i] = pd[i] = 0u;
@@ -523,22 +599,19 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t ch = (uint32_t)(g & 3) * 2;
                     sts128(dst + ((ch ^ swz) << 4), pd[0], pd[1], pd[2], pd[3]);
                     sts128(dst + (((ch + 1) ^ swz) << 4), pd[4], pd[5], pd[6], pd[7]);
-                    if (dbg_on) args.dbg[ic * 16 + 8 + g / 3] = clock64();
+                    VB_DBG(dbg_on, args.dbg[ic * 16 + 8 + g / 3]);
                     if (g < 8 && g + 3 >= 8 && !arrivedA) arriveA();   // that was this warp's last group of the first part
                 };
                 {
-                    uint32_t svA[16], dvA[16], svB[16], dvB[16];
+                    uint32_t svA[16], svB[16];
                     int g = part;
-                    if (g < nks) issue(svA, dvA, g);
+                    if (g < nks) {
+                        wait_b(g);
+                        tmem_ld_32x32b_x16(t_lane + kColST + g * 16, svA);
+                    }
                     for (; g < nks; g += 6) {
-                        tmem_ld_wait();
-                        if (g + 3 < nks) issue(svB, dvB, g + 3);
-                        process(svA, dvA, g);
-                        if (g + 3 < nks) {
-                            tmem_ld_wait();
-                            if (g + 6 < nks) issue(svA, dvA, g + 6);
-                            process(svB, dvB, g + 3);
-                        }
+                        step(svA, svB, g);
+                        if (g + 3 < nks) step(svB, svA, g + 3);
                     }
                 }
                 if (!arrivedA) arriveA();
@@ -546,34 +619,13 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 fence_proxy_async_smem();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (dbg_on) args.dbg[ic * 16 + 5] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 5]);
                 if (lane == 0) mbar_arrive(&p_full[1]);
                 // ---- read-out: accumulator slices -> bf16 tiles in the dead K_t / V_t (dV, dK) and Q / dO (dQ) buffers ----
                 mbar_wait(o_full, ic & 1);
                 tcgen05_fence_after();
-                if (dbg_on) args.dbg[ic * 16 + 6] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 6]);
                 const bool last = (t == n_t - 1);
-                // In-projection bias gradient: column sums of this warp's 32 x 32 accumulator slice by a transposing butterfly (31
-                // shuffles: after the step with offset o a lane keeps the half of its columns whose bit o matches its lane bit), one
-                // atomicAdd per lane.  Rows beyond the sequence are excluded.
-                auto colsum32 = [&](const uint32_t (&r)[32], float mul, bool row_valid, float* dst) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = row_valid ? __uint_as_float(r[i]) * mul : 0.f;
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float send = up ? v[i] : v[i + off];
-                            const float keep = up ? v[i + off] : v[i];
-                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
-                    }
-                    atomicAdd(dst + lane, v[0]);
-                };
-                const bool do_cs = args.colsum != nullptr;
-                const int hd = args.H * 64, hcol = it.h * 64;
                 auto stage32 = [&](const uint32_t (&r)[32], uint32_t row_addr, uint32_t hi, float mul) {
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4) {
@@ -618,9 +670,6 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 } else {
                     stage32(ra, part == 2 ? kv_row + kBlk : kv_row, part == 1 ? 1u : 0u, part == 2 ? args.scale : 1.0f);
                 }
-                // part 0: dV columns 0..31, part 1: dV 32..63.  dK is skipped: sum_k dS[q,k] = sum_k P (dP - delta) = 0 for every query, so
-                // the column sum of dK = dS^T Q (the key-bias gradient) is exactly zero — softmax ignores a constant key offset.
-                if (do_cs && part < 2) colsum32(ra, 1.0f, t * 128 + row_in_tile < S, args.colsum + 2 * hd + hcol + part * 32);
                 if (third) {   // re-use ra for the dQ(0..127) slice; TMEM is free once it has landed
                     tmem_ld_32x32b_x32(t_lane + kColDQ0 + part * 32, ra);
                     tmem_ld_wait();
@@ -646,7 +695,6 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             }
                         }
                         stage32(rb, q_row + kBlk, part - 1, args.scale);
-                        if (do_cs) colsum32(rb, args.scale, 128 + row_in_tile < S, args.colsum + hcol + (part - 1) * 32);
                     } else {
                         uint32_t cr[16];
 #pragma unroll
@@ -657,7 +705,6 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 if (third) {
                     stage32(ra, q_row, part, args.scale);
-                    if (do_cs) colsum32(ra, args.scale, row_in_tile < S, args.colsum + hcol + part * 32);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -665,7 +712,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (args.late_release) mbar_arrive(tile_free);
                     mbar_arrive(out_ready);   // output tiles staged: the store warp takes over
                 }
-                if (dbg_on) args.dbg[ic * 16 + 7] = clock64();
+                VB_DBG(dbg_on, args.dbg[ic * 16 + 7]);
             }
         }
     }

@@ -28,6 +28,14 @@
 #include "dropout.cuh"
 #include "pdl.cuh"
 
+// In-kernel cycle stamps (tools/attn_timeline*.py) are compiled in only with -DVB_ATTN_DBG (VITB200_NVCC_DEFS=-DVB_ATTN_DBG python -m
+// vitb200.build): even predicated off they cost issue slots in the element-wise loops.
+#ifdef VB_ATTN_DBG
+#define VB_DBG(cond, slot) do { if (cond) slot = clock64(); } while (0)
+#else
+#define VB_DBG(cond, slot) do { (void)(cond); } while (0)
+#endif
+
 namespace vb {
 
 int make_tmap_3d(CUtensorMap* m, int dtype, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld_elems,
@@ -278,10 +286,10 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t t_s = t_lane + (j & 1) * kMaxQ;
                 const uint32_t xoff = ((j & 3) * 2 * 128 + row_in_tile) * 4;
                 const bool dbg_on = args.dbg && blockIdx.x == 0 && j < 64 && (warp_idx == 4 || warp_idx == 12) && lane == 0;
-                if (dbg_on) args.dbg[j * 16 + 0] = clock64();
+                VB_DBG(dbg_on, args.dbg[j * 16 + 0]);
                 mbar_wait(&s_full[j & 1], (j >> 1) & 1);
                 tcgen05_fence_after();
-                if (dbg_on) args.dbg[j * 16 + 1] = clock64();
+                VB_DBG(dbg_on, args.dbg[j * 16 + 1]);
                 // ---- pass 1: partial row maximum over my groups (raw scores; keys >= S are dead) ----
                 float mx = -INFINITY;
                 {
@@ -322,12 +330,12 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         }
                     }
                 }
-                if (dbg_on) args.dbg[j * 16 + 2] = clock64();
+                VB_DBG(dbg_on, args.dbg[j * 16 + 2]);
                 sts32(xm_u32 + xoff + part * 512, mx);
                 named_bar_sync(1 + grp * 4 + quad, 64);
                 mx = fmaxf(lds32(xm_u32 + xoff), lds32(xm_u32 + xoff + 512));
                 const float nm = (GEN && mx == -INFINITY) ? 0.f : -mx * c;   // every key of this block masked: P = 0, l = 0 (no NaN)
-                if (dbg_on) args.dbg[j * 16 + 3] = clock64();
+                VB_DBG(dbg_on, args.dbg[j * 16 + 3]);
                 // ---- pass 2: P = exp2(s c - m c) packed over the group's own columns; partial row sum ----
                 float l = 0.f;
                 bool arrivedA = false;
@@ -398,7 +406,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[2 * grp + 1]);
-                if (dbg_on) args.dbg[j * 16 + 4] = clock64();
+                VB_DBG(dbg_on, args.dbg[j * 16 + 4]);
             }
         }
     } else if (warp_idx >= 4 + kEwWarps) {

@@ -305,9 +305,10 @@ int attention_fwd_tc(const VbAttnDesc* d, cudaStream_t stream) {
 
 // Debug hook (not part of the documented ABI surface used by the engine): device buffer of >= 64*16 int64 that receives
 // cycle stamps from CTA 0 of the tcgen05 attention kernels (attention_fwd_tc.cu, attention_bwd_tc.cu); NULL disables.
-namespace vb { void attention_bwd_tc5_set_debug(long long* p); void attention_fwd_tc3_set_debug(long long* p); }
+namespace vb { void attention_bwd_tc5_set_debug(long long* p); void attention_fwd_tc3_set_debug(long long* p); void attention_fwd_tc4_set_debug(long long* p); }
 extern "C" VB_API int vb_debug_set_attn_timeline(void* device_buffer) {
     vb::attention_bwd_tc5_set_debug(reinterpret_cast<long long*>(device_buffer));
     vb::attention_fwd_tc3_set_debug(reinterpret_cast<long long*>(device_buffer));
+    vb::attention_fwd_tc4_set_debug(reinterpret_cast<long long*>(device_buffer));
     return VB_OK;
 }

@@ -93,13 +93,23 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     const int r_end = min(rows, r_begin + rows_per_block);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c0 < cols) {
-        for (int r = r_begin + warp; r < r_end; r += 8) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + (long long)r * ld + c0));
-            acc[0] += __uint_as_float(w.x << 16); acc[1] += __uint_as_float(w.x & 0xFFFF0000u);
-            acc[2] += __uint_as_float(w.y << 16); acc[3] += __uint_as_float(w.y & 0xFFFF0000u);
-            acc[4] += __uint_as_float(w.z << 16); acc[5] += __uint_as_float(w.z & 0xFFFF0000u);
-            acc[6] += __uint_as_float(w.w << 16); acc[7] += __uint_as_float(w.w & 0xFFFF0000u);
+        // fp32 += bf16 with the mixed-precision add of sm_100 (FHADD.BF16 on half-register selectors: no unpacking)
+        auto add8 = [&](const uint4& w) {
+            const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+                    : "+f"(acc[2 * q]), "+f"(acc[2 * q + 1]) : "r"(v[q]));
+        };
+        int r = r_begin + warp;
+        for (; r + 24 < r_end; r += 32) {   // four independent 16-byte loads in flight per lane
+            const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(x + (long long)r * ld + c0));
+            const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(x + (long long)(r + 8) * ld + c0));
+            const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(x + (long long)(r + 16) * ld + c0));
+            const uint4 w3 = __ldg(reinterpret_cast<const uint4*>(x + (long long)(r + 24) * ld + c0));
+            add8(w0); add8(w1); add8(w2); add8(w3);
         }
+        for (; r < r_end; r += 8) add8(__ldg(reinterpret_cast<const uint4*>(x + (long long)r * ld + c0)));
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];

@@ -15,7 +15,11 @@ from . import ops
 
 import os
 _INFER_SPLIT_K = os.environ.get("VITB200_INFER_SPLIT_K", "0") == "1"
-_FUSED_QKV_COLSUM = os.environ.get("VITB200_FUSED_QKV_COLSUM", "1") != "0"   # A/B switch: in-kernel column sums of dq|dk|dv
+# In-projection bias gradient (column sums of dq | dk | dv).  "id" (default): the key part is exactly zero (softmax ignores a constant
+# key offset) and, without attention dropout, the value part equals the column sum of dO (dV = P^T dO and every row of P sums to
+# one), so two bandwidth-bound passes over L2-hot [M, D] matrices (dq, dO) replace work on the attention kernel's critical path
+# (the in-kernel sums cost 60 us of a 240 us launch).  "1": in-kernel sums; "0": three column-sum passes over dq, dk, dv.
+_QKV_COLSUM_MODE = os.environ.get("VITB200_FUSED_QKV_COLSUM", "id")
 LAYER_ROLES = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
 _ALIGN = 64  # elements; keeps every parameter 256-byte (fp32) / 128-byte (bf16) aligned for TMA and float4 access
 
@@ -722,13 +726,19 @@ class VitEngine(FlatParams):
                 self._wgrad(d_bf, buf["o"], (li, "proj_w"))
                 ops.gemm(d_bf, self.w((li, "proj_w")), dh, b_major=1)
             qkv, dqkv = buf["qkv"], ws["dqkv"]
+            cs_mode = _QKV_COLSUM_MODE if (pa == 0 or _QKV_COLSUM_MODE != "id") else "1"   # the identity needs un-dropped P rows
+            qkv_bg = self.gview((li, "qkv_b"))
+            if cs_mode == "id":
+                ops.colsum_bf16(dh, qkv_bg[2 * D:])          # d v-bias = colsum(dV) = colsum(dO): dO was just written by the out-proj dgrad
             ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"], dh, dqkv[:, :D], dqkv[:, D:2 * D],
                               dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S,
                               dropout=(pa, seed, self.drop_site(li, 3)) if pa > 0 else None,
-                              dqkv_colsum=self.gview((li, "qkv_b")) if _FUSED_QKV_COLSUM else None)
+                              dqkv_colsum=qkv_bg if cs_mode == "1" else None)
+            if cs_mode == "id":
+                ops.colsum_bf16(dqkv[:, :D], qkv_bg[:D])     # d q-bias (the k-bias gradient is exactly zero)
             self._wgrad(dqkv, buf["h1"], (li, "qkv_w"))
-            if not _FUSED_QKV_COLSUM:
-                ops.colsum_bf16(dqkv, self.gview((li, "qkv_b")))
+            if cs_mode == "0":
+                ops.colsum_bf16(dqkv, qkv_bg)
             ops.gemm(dqkv, self.w((li, "qkv_w")), dh, b_major=1)
             prev_b2 = self.gview((li - 1, "fc2_b")) if li > 0 else None
             ops.layernorm_bwd(dh, x_in, buf["mean1"], buf["rstd1"], self.f((li, "ln1_w")), dres=d2, dx=d2,
