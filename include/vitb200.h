@@ -200,6 +200,9 @@ VB_API int vb_unpatchify(const void* dpatches_bf16, float* dimages, int32_t B, i
 VB_API int vb_token_rows(float* x, const float* tok0, const float* tok1, const float* pos, int32_t B, int32_t S, int32_t D,
                          int32_t n_prefix, void* stream);
 VB_API int vb_colsum_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, float* out_accum, void* stream);
+/* y_accum[n] += sum_k x[k] * W[k, n] (fp32, W row-major [K, N] with pitch ldw); x_accum[k] += x[k] if x_accum != NULL.  Used for the value-
+ * bias gradient of the packed in-projection: colsum(dV) = colsum(dO) = colsum(d) W_out_proj (torch/nn/functional.py:5835-5847, 6690). */
+VB_API int vb_vecmat_accum(const float* x, const float* W, int64_t ldw, float* y_accum, float* x_accum, int32_t K, int32_t N, void* stream);
 VB_API int vb_embed_bwd(const float* dx, float* possum_scratch, void* dx_patches_bf16, float* dpos, float* dtok0, float* dtok1,
                         float* dbias, int32_t B, int32_t S, int32_t D, int32_t n_prefix, void* stream);
 

@@ -67,6 +67,7 @@ SIGNATURES = {
     "vb_unpatchify": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "vb_token_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "vb_colsum_bf16": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "vb_vecmat_accum": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "vb_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                              c_int32, c_int32, c_void_p]),
     "vb_cross_entropy": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_float, c_void_p, c_int64, c_void_p,

@@ -259,6 +259,22 @@ __global__ void pos_embed_2d_bwd_kernel(const float* __restrict__ dpos, float* _
     }
 }
 
+// ---- y[n] += sum_k x[k] * W[k, n]  (fp32, W row-major [K, N]);  x_accum[k] += x[k] (optional) -------------------------------------
+// The value-bias gradient of the packed in-projection without touching dV: colsum(dV) = colsum(dO) (rows of P sum to one) and
+// dO = d W_proj, so colsum(dO) = colsum(d) W_proj — colsum(d) is the out-proj bias gradient the LayerNorm backward has just summed.
+__global__ void __launch_bounds__(128) vecmat_accum_kernel(const float* __restrict__ x, const float* __restrict__ W, long long ldw,
+                                                           float* __restrict__ y, float* __restrict__ x_accum, int K, int N, int k_per_block) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block);
+    if (x_accum != nullptr && blockIdx.x == 0)
+        for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) x_accum[k] += x[k];
+    if (n >= N) return;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(x + k), __ldg(W + (long long)k * ldw + n), acc);
+    atomicAdd(y + n, acc);
+}
+
 static int grid_for(long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = (long long)num_sms() * 8;
@@ -421,6 +437,16 @@ extern "C" int vb_pos_embed_2d_bwd(const float* dpos, float* drow_accum, float* 
     if (int rc = check_arch()) return rc;
     VB_REQUIRE(dpos && drow_accum && dcol_accum && h > 0 && w > 0 && N > 0 && pf > 0, "pos_embed_2d_bwd: bad arguments");
     pos_embed_2d_bwd_kernel<<<dim3((pf + 127) / 128, h + w), 128, 0, as_stream(stream)>>>(dpos, drow_accum, dcol_accum, h, w, N, pf);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return VB_OK;
+}
+
+extern "C" int vb_vecmat_accum(const float* x, const float* W, int64_t ldw, float* y_accum, float* x_accum, int32_t K, int32_t N, void* stream) {
+    using namespace vb;
+    if (int rc = check_arch()) return rc;
+    VB_REQUIRE(x && W && y_accum && K > 0 && N > 0 && ldw >= N, "vecmat_accum: bad arguments");
+    const int kpb = 32;
+    vecmat_accum_kernel<<<dim3((N + 127) / 128, (K + kpb - 1) / kpb), 128, 0, as_stream(stream)>>>(x, W, ldw, y_accum, x_accum, K, N, kpb);
     VB_CUDA_CHECK(cudaGetLastError());
     return VB_OK;
 }

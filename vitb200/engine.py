@@ -486,6 +486,7 @@ class VitEngine(FlatParams):
             ws["dlogits"] = [torch.zeros(B, self.C_ld, device=dev, dtype=bf) for _ in range(2 if self.two_heads else 1)]
             ws["dy_tok"] = e(B * max(self.n_prefix, 1), D)
             ws["dh_cls"] = e(B, D)
+            ws["cs_tmp"] = e(D, dtype=f32)         # this backward's out-proj bias gradient (feeds the value-bias gradient)
             ws["stat_cls"] = [e(B, dtype=f32), e(B, dtype=f32)]
             ws["possum"] = e(S, D, dtype=f32)
             ws["dxp"] = e(B * self.P, D) if not self.tokens_mode else None
@@ -717,9 +718,17 @@ class VitEngine(FlatParams):
                 self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"))
                 ops.colsum_bf16(ws["da"], self.gview((li, "fc1_b")))
                 ops.gemm(ws["da"], self.w((li, "fc1_w")), dh, b_major=1)
+                # the out-proj bias gradient of THIS backward goes to a scratch first when it also yields the value-bias gradient
+                vb_chain = pd == 0 and pa == 0 and _QKV_COLSUM_MODE == "id"
+                if vb_chain:
+                    ws["cs_tmp"].zero_()
                 ops.layernorm_bwd(dh, buf["x1"].view(M, D), buf["mean2"], buf["rstd2"], self.f((li, "ln2_w")), dres=d_res, dx=d2,
                                   dx_bf16=d_bf if pd == 0 else None, dgamma=self.gview((li, "ln2_w")), dbeta=self.gview((li, "ln2_b")),
-                                  dx_colsum=self.gview((li, "proj_b")) if pd == 0 else None)
+                                  dx_colsum=(ws["cs_tmp"] if vb_chain else self.gview((li, "proj_b"))) if pd == 0 else None)
+                if vb_chain:   # d proj_b += cs;  d v-bias += cs W_proj  (= colsum(dO) = colsum(dV): DESIGN.md §3.2)
+                    ops.vecmat_accum(ws["cs_tmp"], self.f((li, "proj_w")).view(D, D), self.gview((li, "qkv_b"))[2 * D:],
+                                     x_accum=self.gview((li, "proj_b")))
+                    ws["vb_done"] = True
                 if pd > 0:
                     masked_operand(li, 0, (li, "proj_b"))
                 # ---- attention ----
@@ -728,7 +737,7 @@ class VitEngine(FlatParams):
             qkv, dqkv = buf["qkv"], ws["dqkv"]
             cs_mode = _QKV_COLSUM_MODE if (pa == 0 or _QKV_COLSUM_MODE != "id") else "1"   # the identity needs un-dropped P rows
             qkv_bg = self.gview((li, "qkv_b"))
-            if cs_mode == "id":
+            if cs_mode == "id" and not ws.pop("vb_done", False):
                 ops.colsum_bf16(dh, qkv_bg[2 * D:])          # d v-bias = colsum(dV) = colsum(dO): dO was just written by the out-proj dgrad
             ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], buf["o"], buf["lse"], dh, dqkv[:, :D], dqkv[:, D:2 * D],
                               dqkv[:, 2 * D:], ws["delta"], B=B, H=self.H, S=S, tok_stride=1, batch_stride=S,

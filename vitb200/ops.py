@@ -14,7 +14,7 @@ LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"vb_gemm_bf16": 1, "vb_layernorm_fwd": 1, "vb_layernorm_bwd": 1, "vb_attention_fwd": 1, "vb_attention_bwd": 1,
                      "vb_cast_f32_to_bf16": 1, "vb_patchify": 1, "vb_token_rows": 1, "vb_colsum_bf16": 1, "vb_embed_bwd": 2,
                      "vb_cross_entropy": 1, "vb_adam_step": 2, "vb_add_cast_bf16": 1, "vb_add3": 1, "vb_add_rows_bcast": 1, "vb_dropout_f32": 1, "vb_dropout_bf16_pair": 1,
-                     "vb_dropout_mask_u8": 1, "vb_cast_rows_bf16": 1, "vb_pos_embed_2d_fwd": 1, "vb_pos_embed_2d_bwd": 1}
+                     "vb_dropout_mask_u8": 1, "vb_cast_rows_bf16": 1, "vb_pos_embed_2d_fwd": 1, "vb_pos_embed_2d_bwd": 1, "vb_vecmat_accum": 1}
 
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_ACCUM = range(7)
 BF16, F32 = 0, 1
@@ -251,6 +251,14 @@ def colsum_bf16(x, out_accum):
     rows, cols = x.shape
     assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and out_accum.dtype == torch.float32
     _lib.check(lib.vb_colsum_bf16(x.data_ptr(), x.stride(0), rows, cols, out_accum.data_ptr(), _stream()), "vb_colsum_bf16")
+
+
+def vecmat_accum(x, W, y_accum, x_accum=None):
+    """y_accum += x @ W (fp32 vector [K] times fp32 matrix [K, N] view); x_accum += x (optional)."""
+    K, N = W.shape
+    assert x.dtype == torch.float32 and W.dtype == torch.float32 and W.stride(1) == 1 and x.numel() == K and y_accum.numel() == N
+    _lib.check(_lib.load().vb_vecmat_accum(x.data_ptr(), W.data_ptr(), W.stride(0), y_accum.data_ptr(), _p(x_accum), K, N, _stream()),
+               "vb_vecmat_accum")
 
 
 def embed_bwd(dx, possum, dx_patches, dpos, dtok0, dtok1, dbias, n_prefix):
