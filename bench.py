@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the instrumented eager steps (used under ncu for the launch list)")
     ap.add_argument("--no-extras", action="store_true", help="skip the same-GPU library baseline and the cfg3/4/5 measurements")
     ap.add_argument("--config", default="vit_b16_train", choices=["vit_b16_train", "deit_s_distill", "vit_l_infer", "detr_enc"],
                     help="BASELINE.json configs[1] (default, the headline) or configs[2] / [3] / [4] as a stand-alone line")
@@ -282,7 +283,7 @@ def main():
 
     # ---------------- roofline of the dominant kernel (tcgen05 GEMM), CUDA events around every launch of one step ----------
     roofline = None
-    if True:  # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports
+    if not args.no_roofline:  # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports
         peak, peak_sus, hbm, src = measured_peaks()
         rec = []
         orig = ops.gemm

@@ -1,5 +1,5 @@
 """Timing of the general attention path (DETR shapes: sequence-first, key-padding masks, S = 1050; decoder cross-attention 100 x 1050).
-VITB200_ATTN_GEN=0 selects the mma.sync kernels for comparison.  Usage: python tools/attn_gen_time.py [N]"""
+Usage: python tools/attn_gen_time.py [N]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -39,4 +39,4 @@ for (Sq, Sk, name) in ((1050, 1050, "encoder self-attention"), (100, 1050, "deco
     tf = timeit(lambda: ops.attention_fwd(q, k, v, o, lse, **kw))
     tb = timeit(lambda: ops.attention_bwd(q, k, v, o, lse, do, dq, dk, dv, delta, **kw))
     fl = 4.0 * Sq * Sk * 64 * N * H
-    print(f"GEN={os.environ.get('VITB200_ATTN_GEN', '1')} {name:26s} N={N} Sq={Sq} Sk={Sk}: fwd {tf:7.1f} us ({fl / tf / 1e6:6.0f} TF/s)  bwd {tb:7.1f} us ({2.5 * fl / tb / 1e6:6.0f} TF/s)")
+    print(f"{name:26s} N={N} Sq={Sq} Sk={Sk}: fwd {tf:7.1f} us ({fl / tf / 1e6:6.0f} TF/s)  bwd {tb:7.1f} us ({2.5 * fl / tb / 1e6:6.0f} TF/s)")

@@ -37,4 +37,4 @@ bwd = lambda: ops.attention_bwd(q, k, v, o, lse, do, dqkv[:, :D], dqkv[:, D:2 * 
                                 dqkv_colsum=cs)
 tf, tb = timeit(fwd), timeit(bwd)
 fl = 4.0 * S * S * 64 * B * H
-print(f"B={B} H={H} S={S} TC_BWD={os.environ.get('VITB200_ATTN_TC_BWD','0')}: fwd {tf*1e3:.1f} us ({fl/tf/1e9:.0f} TF/s)  bwd {tb*1e3:.1f} us ({2.5*fl/tb/1e9:.0f} TF/s)")
+print(f"B={B} H={H} S={S} : fwd {tf*1e3:.1f} us ({fl/tf/1e9:.0f} TF/s)  bwd {tb*1e3:.1f} us ({2.5*fl/tb/1e9:.0f} TF/s)")

@@ -1,6 +1,5 @@
 """In-kernel cycle stamps of the tcgen05 attention backward (CTA 0): where does an item's time go?"""
 import os, sys
-os.environ["VITB200_ATTN_TC_BWD"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vitb200 import ops, _lib

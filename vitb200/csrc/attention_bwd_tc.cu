@@ -732,12 +732,7 @@ static long long* g_dbg = nullptr;
 // Returns VB_OK if launched, 1 if this shape is not handled here.  delta = rowsum(dO o O) is computed inside (from d->o and d->dout).
 int attention_bwd_tc5(const VbAttnDesc* d, cudaStream_t stream) {
     using namespace bwd5;
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("VITB200_ATTN_TC_BWD");
-        enabled = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (!enabled || d->S > (int)kMaxQ || d->head_dim != 64 || d->tok_stride != 1 || d->key_padding_mask != nullptr) return 1;
+    if (d->S > (int)kMaxQ || d->head_dim != 64 || d->tok_stride != 1 || d->key_padding_mask != nullptr) return 1;
     VB_REQUIRE(d->o != nullptr && d->ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(d->o) & 31) == 0,
                "attention_bwd: the forward output o (32-byte aligned, pitch % 16 == 0) is needed for delta = rowsum(dO o O)");
     const int S = d->S, npad = (S + 15) / 16 * 16;

@@ -479,15 +479,10 @@ static long long* g_dbg = nullptr;
 }  // namespace fwd3
 void attention_fwd_tc3_set_debug(long long* p) { fwd3::g_dbg = p; }
 
-// Returns VB_OK if launched, 1 if this shape is not handled here (caller falls back to the mma.sync kernels).
+// Returns VB_OK if launched, 1 if this shape is not handled here.
 int attention_fwd_tc3(const VbAttnDesc* d, cudaStream_t stream) {
     using namespace fwd3;
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("VITB200_ATTN_TC");
-        enabled = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (!enabled || d->S > (int)kMaxQ || d->head_dim != 64 || d->tok_stride != 1 || d->key_padding_mask != nullptr) return 1;
+    if (d->S > (int)kMaxQ || d->head_dim != 64 || d->tok_stride != 1 || d->key_padding_mask != nullptr) return 1;
     const int S = d->S, npad = (S + 15) / 16 * 16;
     Args a{};
     a.B = d->B; a.H = d->H; a.S = S; a.nks = npad / 16; a.n_qt = (S + 127) / 128; a.total_heads = d->B * d->H;
