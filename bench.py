@@ -382,7 +382,15 @@ def main():
                 "cpu_baseline": cpu, "gpu_library_baseline": lib, "other_configs": others}
         print(json.dumps(line), flush=True)
     faulthandler.cancel_dump_traceback_later()
+    sys.stdout.flush()
     if world > 1:
+        # the result is out; nothing below may turn a finished measurement into a hung job (communicator teardown with captured
+        # collectives has been seen to block): leave hard after 20 s
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            trainer.close()
+        except NameError:
+            pass
         if os.environ.get("VITB200_BENCH_DEBUG"):
             print(f"[rank {rank}] before destroy_process_group", file=sys.stderr, flush=True)
         torch.cuda.synchronize()

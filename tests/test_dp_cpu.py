@@ -48,6 +48,15 @@ def _worker(rank, world, port, q):
         expect = torch.cat([torch.full((b - a,), sum(float(r + 1) * (i + 1) + step for r in range(world)))
                             for i, (a, b) in enumerate(eng.segment_bounds)])
         assert torch.equal(eng.flat_grad, expect), (rank, step)
+    # overlap=False (launch-bound models): no per-segment callbacks, one all-reduce of the whole buffer after backward
+    eng2 = _FakeEngine([100, 28])
+    red2 = GradReducer(overlap=False)
+    red2.attach(eng2)
+    assert eng2.grad_segment_hook is None
+    red2.begin_step()
+    eng2.flat_grad[:] = float(rank + 1)
+    red2.finish_step()
+    assert torch.equal(eng2.flat_grad, torch.full((128,), float(sum(r + 1 for r in range(world)))))
     q.put((rank, flushed))
     dist.destroy_process_group()
 

@@ -99,6 +99,7 @@ def detr_encoder_step(dev, N=4, reducer=None, seed=0):
         out = enc(src, src_key_padding_mask=mask, pos=pos)
         loss = out.float().square().mean()
         if reducer is not None:
+            loss = loss / reducer.world_size        # SUM all-reduce of the ranks' gradients = gradient of the global mean
             reducer.begin_step()
         loss.backward()
         if reducer is not None:
@@ -219,7 +220,7 @@ def bench_line(args):
         B = 4
         if world > 1:
             from vitb200.dp import GradReducer
-            reducer = GradReducer()
+            reducer = GradReducer(overlap=False)      # launch-bound model: graph-replayed forward / backward + one all-reduce
         step, enc = detr_encoder_step(dev, B, reducer=reducer, seed=rank)
         e2e_step, h2d = None, 0
         metric, unit, workload = "DETR encoder train images/sec", "images/sec", \
@@ -285,6 +286,11 @@ def bench_line(args):
                                          "kernel": "whole step, model FLOPs of SURVEY.md §8(d)", "peak_kind": f"bf16_tflops burst ({src})"}}
         print(json.dumps(line), flush=True)
     if world > 1:
+        import threading
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()      # a finished measurement must not become a hung job at teardown
+        if name == "deit_s_distill":
+            tr.close()
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()

@@ -89,6 +89,7 @@ def main():
         l = tr2.step(all_images[s, sl].to(dev), all_labels[s, sl].to(dev)).clone()
         dist.all_reduce(l)
         dp_losses.append(l.item() / world)
+    tr2.close()
     del tr2, m2
     torch.cuda.empty_cache()
 
@@ -130,6 +131,10 @@ def main():
         if os.path.isdir(out):
             with open(os.path.join(out, f"dp_parity_{world}gpu.json"), "w") as fh:
                 json.dump(res, fh, indent=1)
+    sys.stdout.flush()
+    import threading
+    threading.Timer(20.0, lambda: os._exit(0 if ok else 1)).start()   # captured collectives: teardown must not hang a finished check
+    tr.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     # every rank must also have agreed with rank 0

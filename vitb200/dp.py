@@ -12,12 +12,17 @@ import torch.distributed as dist
 
 
 class GradReducer:
-    def __init__(self, process_group=None, bucket_bytes=48 << 20):
+    def __init__(self, process_group=None, bucket_bytes=48 << 20, overlap=True):
+        """overlap=True: buckets are all-reduced on a side stream while backward is still running (the engine calls back per finished
+        segment; the step is then a single stream of eager launches or ONE captured graph).  overlap=False: one all-reduce of the whole
+        gradient buffer after backward — for small, launch-bound models (the DETR encoder at 4 images per GPU), whose forward / backward
+        are replayed from their own CUDA graphs and must not be interleaved with Python callbacks."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before creating a GradReducer")
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group)
         self.bucket_elems = bucket_bytes // 4
+        self.overlap = overlap
         self.engine = None
         self.comm_stream = None
         self._works = []
@@ -27,7 +32,7 @@ class GradReducer:
 
     def attach(self, engine):
         self.engine = engine
-        engine.grad_segment_hook = self._on_segment
+        engine.grad_segment_hook = self._on_segment if self.overlap else None
         self._last_segment = len(engine.segment_bounds) - 1
         self._synced = False
         self.sync_parameters(strict=False)
@@ -78,6 +83,9 @@ class GradReducer:
             self._flush()
 
     def finish_step(self):
+        if not self.overlap:     # everything at once, on the compute stream
+            dist.all_reduce(self.engine.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+            return
         self._flush()
         for w in self._works:
             w.wait()

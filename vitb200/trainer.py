@@ -71,15 +71,24 @@ class Trainer:
         self.engine = model._get_engine()
         self.opt = FusedAdam(model, lr, betas, eps, weight_decay)
         self.reducer = reducer
-        # Data parallel: the NCCL all-reduces on the side stream are launched eagerly by default.  VITB200_DP_GRAPH=1 captures them
-        # into the same CUDA graph as the kernels (works on 2 GPUs, measured no faster: 33.1-33.3 vs 32.8 ms/step).
-        self.use_cuda_graph = use_cuda_graph and (reducer is None or os.environ.get("VITB200_DP_GRAPH", "0") == "1")
+        # Data parallel: the NCCL all-reduces on the side stream are captured into the same CUDA graph as the kernels (round 2, 2 GPUs:
+        # 31.50 vs 31.86 ms/step with eager launches).  VITB200_DP_GRAPH=0 launches the data-parallel step eagerly.  A process that
+        # captured collectives must drop its graphs before destroying the process group (Trainer.close()).
+        self.use_cuda_graph = use_cuda_graph and (reducer is None or os.environ.get("VITB200_DP_GRAPH", "1") != "0")
         self._loss = None
         self._correct = None
         self._graphs = {}   # batch shape -> (graph, static_images, static_labels)
         self._eager_done = set()
         if reducer is not None:
             reducer.attach(self.engine)
+
+    def close(self):
+        """Drops the captured graphs (they hold NCCL kernels of the reducer's communicator): call before destroy_process_group()."""
+        import gc
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
 
     def invalidate(self):
         self.engine.bf16_fresh = False
