@@ -169,6 +169,16 @@ def main():
         import configs_bench
         return configs_bench.bench_line(args)
 
+    # stdout carries exactly ONE line (the JSON): everything else a library may print there at the C level — NCCL's version banner
+    # under NCCL_DEBUG=VERSION / INFO, which the driver may set to check the communicator — is sent to stderr by pointing fd 1 at fd 2
+    # for the lifetime of the run; the line itself is written to the saved descriptor.  NCCL_DEBUG is left as the caller set it.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     import faulthandler
     faulthandler.dump_traceback_later(240, exit=True)   # a hung rank prints where it is stuck instead of burning the time limit
     import torch
@@ -380,7 +390,7 @@ def main():
                 "per_gpu_tflops": step_tflops, "mfu_vs_burst_peak": step_tflops / peak, "mfu_vs_sustained_peak": step_tflops / peak_sus,
                 "final_loss": final_loss, "gpu_launches": launches, "clocks": sampler.summary(), "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": cpu, "gpu_library_baseline": lib, "other_configs": others}
-        print(json.dumps(line), flush=True)
+        emit(line)
     faulthandler.cancel_dump_traceback_later()
     sys.stdout.flush()
     if world > 1:

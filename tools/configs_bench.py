@@ -184,6 +184,9 @@ def summary(dev, peak_tflops):
 def bench_line(args):
     """`bench.py --config X --gpus N --steps K --warmup W`: one bench-contract JSON line for configs[2] / [3] / [4]."""
     import torch.distributed as dist
+    sys.stdout.flush()
+    json_fd = os.dup(1)      # stdout carries exactly one line; C-level prints of libraries (NCCL's banner) go to stderr
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -284,7 +287,7 @@ def bench_line(args):
                            "l2_policy": "activations exceed the 126 MB L2; no explicit flush"},
                 "e2e": e2e, "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
                                          "kernel": "whole step, model FLOPs of SURVEY.md §8(d)", "peak_kind": f"bf16_tflops burst ({src})"}}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         import threading
         sys.stdout.flush()
