@@ -90,6 +90,10 @@ typedef struct VbGemmDesc {
     float drelu_scale;        /* VB_EPI_DRELU only; 0 means 1.  1/(1-p) when AUX is the DROPPED relu output keep*relu(x)/(1-p)
                                * (transformer.py:223: linear2(dropout(activation(linear1(src))))) */
     int32_t reserved0;
+    float* a_colsum;          /* optional, a_major = 1 and batches = 1 only: a_colsum[m] += sum_k A[k, m] (fp32, atomicAdd), summed from the
+                               * operand tiles while they sit in shared memory for the MMA.  In a weight-gradient GEMM dW = dY^T X the A
+                               * operand is dY [tokens, out]: this is the bias gradient of the same nn.Linear (vanilla_vit.py:34,40;
+                               * torch/nn/functional.py:5835 in_proj_bias) with no second pass over dY */
 } VbGemmDesc;
 
 VB_API int vb_gemm_bf16(const VbGemmDesc* desc, void* stream);

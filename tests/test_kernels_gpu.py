@@ -92,6 +92,35 @@ torch.save(outs[0].cpu(), sys.argv[1])
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tokens,n_out,k_in,split", [(50432, 3072, 768, 2), (50432, 2304, 768, 3), (5000, 200, 304, 1), (777, 1000, 64, 4),
+                                                     (256, 3072, 768, 1), (12608, 384, 1536, 6)])
+def test_gemm_wgrad_bias_gradient_from_operand_stages(tokens, n_out, k_in, split):
+    """VbGemmDesc::a_colsum: the bias gradient (column sums of dY) taken from the A-operand stages of the weight-gradient GEMM equals
+    the fp32 sum of the same bf16 values, for every split-K / n-block partition (also with dynamic and static scheduling, ragged M,
+    N, K, accumulation onto a non-zero vector, and repeated launches), and leaves dW itself bit-identical."""
+    import torch
+    from vitb200 import ops
+    torch.manual_seed(tokens + n_out)
+    dy = (torch.randn(tokens, n_out, device="cuda") * 0.5 + 0.1).bfloat16()
+    x = torch.randn(tokens, k_in, device="cuda").bfloat16()
+    ref = dy.double().sum(0)
+    scale = dy.double().abs().sum(0)
+    dW0 = torch.zeros(n_out, k_in, device="cuda")
+    ops.gemm(dy, x, dW0, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split)
+    for rep in range(3):
+        db = torch.full((n_out,), 3.0, device="cuda")
+        dW = torch.zeros(n_out, k_in, device="cuda")
+        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split, a_colsum=db)
+        torch.cuda.synchronize()
+        err = ((db.double() - 3.0 - ref).abs() / scale).max().item()
+        assert err < 2e-6, err                                    # fp32 accumulation of exactly the same addends: 2e-6 of sum |dy|
+        if split == 1:
+            assert torch.equal(dW, dW0)                           # one unit per tile: same order of accumulation
+        else:
+            assert ((dW - dW0).norm() / dW0.norm()).item() < 1e-6  # split-K partials land through fp32 reduce-adds in any order
+
+
+@pytest.mark.gpu
 def test_attention_backward_fused_bias_gradient():
     """dqkv_colsum of vb_attention_bwd (in-projection bias gradient summed inside the tcgen05 backward) against the column sums
     of the stored dq | dk | dv; the key-bias part is mathematically zero and is left untouched by the tcgen05 path."""

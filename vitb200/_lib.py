@@ -30,6 +30,7 @@ class VbGemmDesc(Structure):
         ("bias", c_void_p),
         ("max_ctas", c_int32), ("debug_direct_store", c_int32),
         ("drelu_scale", c_float), ("reserved0", c_int32),
+        ("a_colsum", c_void_p),
     ]
 
 

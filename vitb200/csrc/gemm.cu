@@ -7,7 +7,8 @@
 // CTAs' shared memory, halving the per-SM shared-memory traffic of the B operand.  Roles per CTA:
 //   warp 0      TMA producer: fills a 4-6-stage ring of {A 128x64, B (256/CG)x64} bf16 tiles (128B swizzle)
 //   warp 1      MMA issuer (leader CTA): one thread issues tcgen05.mma into one of two TMEM accumulators
-//   warp 2      TMEM allocator (512 columns = 2 x 256 fp32 accumulator columns)
+//   warp 2      TMEM allocator (512 columns = 2 x 256 fp32 accumulator columns); with GemmArgs::a_colsum it then sums the
+//               MN-major A tiles over k straight from the operand stages (the bias gradient of a weight-gradient GEMM)
 //   warps 4-11  epilogue: tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store / reduce-add,
 //               overlapping the MMA of the next tile (double-buffered accumulator)
 // Operand majors are handled in the shared-memory descriptors (K-major or MN-major canonical SW128
@@ -45,6 +46,7 @@ struct GemmArgs {
     long long* dbg;       // optional: cycle accounting of cluster 0's MMA issuer (vb_debug_set_gemm_timeline)
     int* sched_counter;   // non-null: dynamic tile scheduling (units beyond the first per cluster are handed out by atomicAdd)
     const float* bias;
+    float* a_colsum;      // non-null (AMAJ = 1, one batch): a_colsum[m] += sum over k of A[k, m], read from the operand stages (warp 2)
     void* C;
     void* C2;
     const void* AUX;
@@ -208,7 +210,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* aux_bar = tmem_empty_bar + 2;         // [kEpiWarps]
     uint64_t* sched_full = aux_bar + kEpiWarps;          // [kSchedStages] scheduler ring: entry written
     uint64_t* sched_empty = sched_full + kSchedStages;   // [kSchedStages] (leader's copy) entry read by every consumer of the pair
-    int* sched_unit = reinterpret_cast<int*>(sched_empty + kSchedStages);   // [kSchedStages]
+    uint64_t* cs_done = sched_empty + kSchedStages;      // [kStages] a_colsum: the column-sum warp has finished reading the A stage
+    uint64_t* cs_ready = cs_done + kStages;              // [kStages] a_colsum, non-leader CTA: the leader saw the stage's loads complete
+    int* sched_unit = reinterpret_cast<int*>(cs_ready + kStages);   // [kSchedStages]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sched_unit + kSchedStages);
 
     const uint32_t warp_idx = threadIdx.x >> 5;
@@ -232,9 +236,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_init(&tmem_empty_bar[i], kEpiWarps * CG);   // (leader's copy) every epilogue warp of the pair arrives
         }
         for (uint32_t i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+        const uint32_t cs_readers = (AMAJ == 1 && args.a_colsum != nullptr) ? 1 : 0;
         for (uint32_t i = 0; i < kSchedStages; ++i) {
             mbar_init(&sched_full[i], 1);
-            mbar_init(&sched_empty[i], (1 + kEpiWarps) * CG + 1);   // producer + epilogue warps of each CTA, MMA issuer of the leader
+            // producer + epilogue warps (+ column-sum warp) of each CTA, MMA issuer of the leader
+            mbar_init(&sched_empty[i], (1 + kEpiWarps + cs_readers) * CG + 1);
+        }
+        for (uint32_t i = 0; i < kStages; ++i) {
+            mbar_init(&cs_done[i], 1);
+            mbar_init(&cs_ready[i], 1);
         }
         fence_barrier_init();
     }
@@ -255,6 +265,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // both CTAs through a small shared-memory ring — so a cluster that starts late (its SMs were held by a co-running kernel,
     // e.g. the NCCL all-reduce of the previous gradient bucket) simply takes fewer units instead of finishing a wave late.
     const bool dynamic = args.sched_counter != nullptr;
+    const bool colsum_on = (AMAJ == 1) && args.a_colsum != nullptr;
+    // a_colsum: k-block kb of a unit is summed by the unit whose n-block is kb mod n_blocks.  The roles keep a wrapping counter
+    // (0 = "mine") instead of taking a modulo per k-block: that sat on the issue path of the TMA producer and the MMA issuer.
+    auto cs_count0 = [&](const UnitCoord& c) -> int {
+        if (!colsum_on) return 0;
+        const int r = (c.kb0 - c.n_blk) % args.n_blocks;
+        return r < 0 ? r + args.n_blocks : r;
+    };
     const uint32_t sched_empty_leader = (CG == 2) ? mapa_u32(smem_u32(&sched_empty[0]), 0) : smem_u32(&sched_empty[0]);
     struct SchedReader {
         uint32_t stage = 0, phase = 0;
@@ -304,13 +322,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            uint32_t cs_mask = 0, cs_phase = 0;   // per-stage bits: awaiting the column-sum warp / phase of its barrier
             SchedReader rd;
             for (int u = unit0; u >= 0; u = sched_next(rd, u, false)) {
                 const UnitCoord c = decode_unit<CG>(args, u, rank);
                 const int bb = args.b_batched ? c.batch : 0;
                 const int n_row0 = c.n_blk * BN + rank * (BN / CG);   // this CTA's share of the B tile
+                int cs_cnt = cs_count0(c);
                 for (int kb = c.kb0; kb < c.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if constexpr (AMAJ == 1) {
+                        // a stage whose previous contents the column-sum warp reads is refilled only after it has said so
+                        if (cs_mask & (1u << stage)) {
+                            mbar_wait(&cs_done[stage], (cs_phase >> stage) & 1);
+                            cs_phase ^= 1u << stage;
+                            cs_mask &= ~(1u << stage);
+                        }
+                        if (colsum_on && cs_cnt == 0) cs_mask |= 1u << stage;
+                        if (++cs_cnt == args.n_blocks) cs_cnt = 0;
+                    }
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * kBStage;
                     if (CG == 1) {
@@ -364,6 +394,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             constexpr uint32_t b_kstep = (BMAJ == 0) ? UK * 2 : UK * 128;
             uint32_t stage = 0, phase = 0, it = 0;
             SchedReader rd;
+            const uint32_t cs_ready_peer = (CG == 2) ? mapa_u32(smem_u32(&cs_ready[0]), 1) : 0;
             const bool dbg_on = args.dbg != nullptr && blockIdx.x == 0;
             long long t_begin = 0, w_full = 0, w_tmem = 0, w_sched = 0, t0 = 0;
             if (dbg_on) t_begin = clock64();
@@ -376,6 +407,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (dbg_on) w_tmem += clock64() - t0;
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
+                int cs_cnt = cs_count0(c);
                 for (int kb = c.kb0; kb < c.kb1; ++kb) {
                     if (dbg_on) t0 = clock64();
                     mbar_wait(&full_bar[stage], phase);
@@ -393,6 +425,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     // frees the smem slot (in both CTAs of the pair) once these MMAs retire
                     if (CG == 2) umma_commit_2sm(&empty_bar[stage], 0x3);
                     else umma_commit(&empty_bar[stage]);
+                    if constexpr (AMAJ == 1) {
+                        if (colsum_on && cs_cnt == 0) {   // this stage is also read by the column-sum warps (after the issue: off its path)
+                            mbar_arrive(&cs_ready[stage]);
+                            if (CG == 2) mbar_arrive_cluster(cs_ready_peer + stage * 8);
+                        }
+                        if (++cs_cnt == args.n_blocks) cs_cnt = 0;
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 // accumulator complete -> epilogue warps of both CTAs
@@ -405,6 +444,77 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (dbg_on) {
                 args.dbg[0] = clock64() - t_begin; args.dbg[1] = w_full; args.dbg[2] = w_tmem; args.dbg[3] = w_sched; args.dbg[4] = it;
+            }
+        }
+    } else if (warp_idx == 2) {
+        // ===================================== column sums of the A operand (a_colsum) ===========================================
+        // A is MN-major: a stage holds BM/64 boxes of [BK k-rows][64 m] bf16 (128-byte rows, 16-byte chunks XOR-swizzled by k & 7).
+        // Of the n_blocks units that load the same A tiles (same m-group and k-range, different n-block), unit j sums the k-blocks
+        // with kb % n_blocks == j, so the extra shared-memory reads are spread evenly.  The stage is read WHILE the MMAs consume it
+        // (reading it after they retire delayed the refill of every third stage and cost the weight-gradient GEMMs ~20 %): the MMA
+        // issuer, who sees every TMA completion in order, relays it to this warp in both CTAs of a pair through cs_ready (the loads of
+        // both CTAs complete on the leader's barrier only; a parity wait on full_bar by a warp that skips stages would be ambiguous).
+        // The producer refills such a stage only after cs_done as well as the MMA's commit.
+        // Lane (r = lane >> 3, ch = lane & 7) owns 8 columns (one 16-byte chunk) of rows r, r + 4, ...
+        if constexpr (AMAJ == 1) {
+            if (colsum_on) {
+                static_assert(BM == 128 && BK == 64, "column-sum geometry");
+                uint32_t stage = 0, ready_phase = 0;
+                SchedReader rd;
+                const uint32_t ch = lane & 7, r4 = lane >> 3;
+                for (int u = unit0; u >= 0; u = sched_next(rd, u, true)) {
+                    const UnitCoord c = decode_unit<CG>(args, u, rank);
+                    float acc[2][8];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+                    int cs_cnt = cs_count0(c);
+                    for (int kb = c.kb0; kb < c.kb1; ++kb) {
+                        const bool mine = cs_cnt == 0;
+                        if (++cs_cnt == args.n_blocks) cs_cnt = 0;
+                        if (mine) {
+                            mbar_wait(&cs_ready[stage], (ready_phase >> stage) & 1);   // exactly one arrival per use (MMA issuer)
+                            ready_phase ^= 1u << stage;
+                            const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+#pragma unroll
+                            for (uint32_t half_ = 0; half_ < 2; ++half_) {
+                                uint32_t w[8][2][4];                      // 16 independent 16-byte loads in flight per lane
+#pragma unroll
+                                for (uint32_t it = 0; it < 8; ++it) {
+                                    const uint32_t k = (half_ * 8 + it) * 4 + r4;
+                                    const uint32_t off = k * 128 + ((ch ^ (k & 7)) << 4);
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j)
+                                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                                     : "=r"(w[it][j][0]), "=r"(w[it][j][1]), "=r"(w[it][j][2]), "=r"(w[it][j][3])
+                                                     : "r"(sa + j * (BK * 128) + off));
+                                }
+#pragma unroll
+                                for (uint32_t it = 0; it < 8; ++it)
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+                                                : "+f"(acc[j][2 * q]), "+f"(acc[j][2 * q + 1]) : "r"(w[it][j][q]));
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&cs_done[stage]);
+                        }
+                        if (++stage == kStages) stage = 0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float v = acc[j][e];
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            const int m = c.m_blk * int(BM) + j * 64 + int(ch) * 8 + e;
+                            if (r4 == 0 && m < args.M) atomicAdd(args.a_colsum + m, v);
+                        }
+                }
             }
         }
     } else if (warp_idx >= kFirstEpiWarp) {
@@ -829,6 +939,8 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     a.sched_counter = nullptr;
     a.dbg = g_gemm_dbg;
     a.bias = d->bias;
+    VB_REQUIRE(!d->a_colsum || (d->a_major == 1 && d->batches == 1), "a_colsum needs a_major = 1 and a single batch");
+    a.a_colsum = d->a_colsum;
     a.C = d->C; a.C2 = d->C2; a.AUX = d->AUX;
     a.ldc = d->ldc; a.ldc2 = d->ldc2; a.ldaux = d->ldaux;
     a.bsc = d->batch_stride_c; a.bsc2 = d->batch_stride_c2; a.bsaux = d->batch_stride_aux;

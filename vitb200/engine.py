@@ -19,7 +19,12 @@ _INFER_SPLIT_K = os.environ.get("VITB200_INFER_SPLIT_K", "0") == "1"
 # key offset) and, without attention dropout, the value part equals the column sum of dO (dV = P^T dO and every row of P sums to
 # one), so two bandwidth-bound passes over L2-hot [M, D] matrices (dq, dO) replace work on the attention kernel's critical path
 # (the in-kernel sums cost 60 us of a 240 us launch).  "1": in-kernel sums; "0": three column-sum passes over dq, dk, dv.
-_QKV_COLSUM_MODE = os.environ.get("VITB200_FUSED_QKV_COLSUM", "id")
+_QKV_COLSUM_MODE = os.environ.get("VITB200_FUSED_QKV_COLSUM", "gemm")
+# "gemm" (default): the in-projection and fc1 bias gradients are column sums of the weight-gradient GEMM's own A operand (dY), taken
+#         from its shared-memory operand stages (VbGemmDesc::a_colsum) — no separate pass over dY;
+# "id":   q-bias = colsum(dQ) kernel, v-bias through colsum(dV) = colsum(dO) = colsum(d) W_proj, k-bias = 0;
+# "1":    column sums inside the attention backward kernel;  "0": one colsum kernel over dqkv.
+_WGRAD_COLSUM = _QKV_COLSUM_MODE == "gemm"
 LAYER_ROLES = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
 _ALIGN = 64  # elements; keeps every parameter 256-byte (fp32) / 128-byte (bf16) aligned for TMA and float4 access
 
@@ -29,15 +34,17 @@ def _round_up(x, m):
 
 
 def pick_split_k(tiles, k_blocks, sms):
-    """Split-K factor for a wgrad GEMM: fill a whole number of waves of `sms` CTAs, keep >= 8 k-blocks per unit."""
-    best, best_eff = 1, 0.0
+    """Split-K factor for a wgrad GEMM (work units are tiles x splits, run in waves over `sms` CTA pairs): minimise
+    waves x (k-blocks per unit x 0.40 us + 2.1 us for the unit's fp32 reduce-add epilogue) — the two constants are a fit to
+    tools/wgrad_split_sweep.py on a B200 — keeping >= 8 k-blocks per unit.  (Filling the last wave to 99 % with 30 splits, which the
+    round-1 rule chose for the ViT-B in-projection, costs 11 epilogues per CTA pair instead of 3: 141 us against 124 us.)"""
+    best, best_t = 1, float("inf")
     for s in range(1, 33):
         if s > 1 and k_blocks // s < 8:
             break
-        units = tiles * s
-        eff = units / (-(-units // sms) * sms)
-        if eff > best_eff + 0.02:
-            best, best_eff = s, eff
+        t = -(-tiles * s // sms) * (-(-k_blocks // s) * 0.40 + 2.1)
+        if t < best_t * 0.995:
+            best, best_t = s, t
     return best
 
 
@@ -353,8 +360,9 @@ class FlatParams:
                 o = self.offsets[key]
                 p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
 
-    def _wgrad(self, dy, x, key, rows=None):
-        """dW[key] (or its first `rows` rows / a row slice) += dy^T x  with dy [M, N_out], x [M, K_in] (token-major bf16)."""
+    def _wgrad(self, dy, x, key, rows=None, bias_key=None):
+        """dW[key] (or its first `rows` rows / a row slice) += dy^T x  with dy [M, N_out], x [M, K_in] (token-major bf16);
+        with ``bias_key`` also d bias[bias_key] += column sums of dy (inside the same GEMM when _WGRAD_COLSUM, else one more kernel)."""
         dW = self.gview(key)
         if rows is not None:
             dW = dW[rows[0]:rows[1]]
@@ -362,7 +370,10 @@ class FlatParams:
         # work units are 256x256 tiles owned by CTA pairs (cta_group::2): sms // 2 pairs run concurrently
         tiles = (-(-(-(-n_out // 128)) // 2)) * (-(-k_in // 256))
         split = pick_split_k(tiles, -(-dy.shape[0] // 64), max(1, self._sms // 2))
-        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split)
+        fused = bias_key is not None and _WGRAD_COLSUM
+        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split, a_colsum=self.gview(bias_key) if fused else None)
+        if bias_key is not None and not fused:
+            ops.colsum_bf16(dy, self.gview(bias_key))
 
     def _seg_done(self, idx):
         if self.grad_segment_hook is not None:
@@ -700,8 +711,7 @@ class VitEngine(FlatParams):
                 da_c, dh_c = ws["da"][:B], ws["dh_cls"]
                 self._wgrad(d_c, buf["g"].view(B, S, Fd)[:, 0, :], (li, "fc2_w"))
                 ops.gemm(d_c, self.w((li, "fc2_w")), da_c, b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"].view(B, S, Fd)[:, 0, :])
-                self._wgrad(da_c, buf["h2"].view(B, S, D)[:, 0, :], (li, "fc1_w"))
-                ops.colsum_bf16(da_c, self.gview((li, "fc1_b")))
+                self._wgrad(da_c, buf["h2"].view(B, S, D)[:, 0, :], (li, "fc1_w"), bias_key=(li, "fc1_b"))
                 ops.gemm(da_c, self.w((li, "fc1_w")), dh_c, b_major=1)
                 ws["stat_cls"][0].copy_(buf["mean2"].view(B, S)[:, 0])
                 ws["stat_cls"][1].copy_(buf["rstd2"].view(B, S)[:, 0])
@@ -715,8 +725,7 @@ class VitEngine(FlatParams):
                 # ---- MLP ----
                 self._wgrad(d_bf, buf["g"], (li, "fc2_w"))
                 ops.gemm(d_bf, self.w((li, "fc2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"])
-                self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"))
-                ops.colsum_bf16(ws["da"], self.gview((li, "fc1_b")))
+                self._wgrad(ws["da"], buf["h2"], (li, "fc1_w"), bias_key=(li, "fc1_b"))
                 ops.gemm(ws["da"], self.w((li, "fc1_w")), dh, b_major=1)
                 # the out-proj bias gradient of THIS backward goes to a scratch first when it also yields the value-bias gradient
                 vb_chain = pd == 0 and pa == 0 and _QKV_COLSUM_MODE == "id"
@@ -745,7 +754,7 @@ class VitEngine(FlatParams):
                               dqkv_colsum=qkv_bg if cs_mode == "1" else None)
             if cs_mode == "id":
                 ops.colsum_bf16(dqkv[:, :D], qkv_bg[:D])     # d q-bias (the k-bias gradient is exactly zero)
-            self._wgrad(dqkv, buf["h1"], (li, "qkv_w"))
+            self._wgrad(dqkv, buf["h1"], (li, "qkv_w"), bias_key=(li, "qkv_b") if cs_mode == "gemm" else None)
             if cs_mode == "0":
                 ops.colsum_bf16(dqkv, qkv_bg)
             ops.gemm(dqkv, self.w((li, "qkv_w")), dh, b_major=1)

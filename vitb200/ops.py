@@ -42,10 +42,12 @@ def _mat(t, name):
 
 
 def gemm(A, B, C, *, a_major=0, b_major=0, epilogue=EPI_STORE, bias=None, aux=None, C2=None, split_k=1,
-         c_row_offset=0, aux_broadcast=False, max_ctas=0, direct=False, drelu_scale=1.0):
+         c_row_offset=0, aux_broadcast=False, max_ctas=0, direct=False, drelu_scale=1.0, a_colsum=None):
     """C = epilogue(A @ B^T). ``A`` is [M,K] (a_major 0) or stored [K,M] (a_major 1); ``B`` is [N,K] or stored [K,N].
 
     3-D tensors add a leading batch dimension (B may stay 2-D to be shared). ``C``/``C2``/``aux`` are [M(+off),N].
+    ``a_colsum`` (fp32 [M], a_major 1 only): += the sum of A over the contraction index, taken from the operand tiles in shared memory
+    (the bias gradient of a weight-gradient GEMM).
     """
     lib = _lib.load()
     d = VbGemmDesc()
@@ -79,6 +81,9 @@ def gemm(A, B, C, *, a_major=0, b_major=0, epilogue=EPI_STORE, bias=None, aux=No
     d.max_ctas = max_ctas
     d.debug_direct_store = int(direct)
     d.drelu_scale = float(drelu_scale)
+    if a_colsum is not None:
+        assert a_colsum.dtype == torch.float32 and a_colsum.is_contiguous() and a_colsum.numel() == M and a_major == 1 and nba == 1
+        d.a_colsum = a_colsum.data_ptr()
     _lib.check(lib.vb_gemm_bf16(ctypes.byref(d), _stream()), "vb_gemm_bf16")
     return out
 
