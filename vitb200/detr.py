@@ -298,8 +298,7 @@ class DetrEngine(FlatParams):
             self._wgrad(d_bf, act_out, (li, "lin2_w"))
             ops.gemm(d_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU if self.act == "relu" else ops.EPI_DGELU,
                      aux=buf["a"], **drelu)
-            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
-            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"), bias_key=(li, "lin1_b"))
             ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
             ops.layernorm_bwd(dh, buf["x1"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dres=d, dx=d, dx_bf16=d_bf if pd == 0 else None,
                               dgamma=self.gview((li, "norm2_w")), dbeta=self.gview((li, "norm2_b")),
@@ -313,11 +312,9 @@ class DetrEngine(FlatParams):
             ops.attention_bwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"], dh, dqk[:, :D], dqk[:, D:], dv,
                               ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm, dropout=drop3(li))
             in_w = self.w((li, "in_w"))
-            self._wgrad(dqk, buf["qk_bf"] if pos2 is not None else buf["x_bf"], (li, "in_w"), rows=(0, 2 * D))
-            self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
             gb = self.gview((li, "in_b"))
-            ops.colsum_bf16(dqk, gb[:2 * D])
-            ops.colsum_bf16(dv, gb[2 * D:])
+            self._wgrad(dqk, buf["qk_bf"] if pos2 is not None else buf["x_bf"], (li, "in_w"), rows=(0, 2 * D), bias_grad=gb[:2 * D])
+            self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D), bias_grad=gb[2 * D:])
             ops.gemm(dqk, in_w[:2 * D], dh, b_major=1)                 # d(norm1(x) + pos) through q and k
             ops.gemm(dv, in_w[2 * D:], dh2, b_major=1)                 # d norm1(x) through v
             if dpos is not None:
@@ -368,8 +365,7 @@ class DetrEngine(FlatParams):
                 ops.gemm(dB_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU, aux=buf["a"], **drelu)
             else:
                 ops.gemm(dB_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DGELU, aux=buf["a"])
-            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
-            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"), bias_key=(li, "lin1_b"))
             ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
             # norm1: its output x1 received dB (residual) + dh (through the FFN); input is x1pre = src + out_proj(attn)
             ops.layernorm_bwd(dB, buf["x1pre"], buf["mean1"], buf["rstd1"], self.f((li, "norm1_w")), dx=dA, dx_bf16=dA_bf if pd == 0 else None,
@@ -383,11 +379,9 @@ class DetrEngine(FlatParams):
             ops.attention_bwd(buf["qkb"][:, :D], buf["qkb"][:, D:], buf["vb"], buf["o"], buf["lse"], dh, dqk[:, :D], dqk[:, D:], dv,
                               ws["delta"], B=N, H=H, S=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm, dropout=drop3(li))
             in_w = self.w((li, "in_w"))
-            self._wgrad(dqk, buf["qk_bf"], (li, "in_w"), rows=(0, 2 * D))
-            self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
             gb = self.gview((li, "in_b"))
-            ops.colsum_bf16(dqk, gb[:2 * D])
-            ops.colsum_bf16(dv, gb[2 * D:])
+            self._wgrad(dqk, buf["qk_bf"], (li, "in_w"), rows=(0, 2 * D), bias_grad=gb[:2 * D])
+            self._wgrad(dv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D), bias_grad=gb[2 * D:])
             ops.gemm(dqk, in_w[:2 * D], dh, b_major=1)                 # d(src + pos) through q and k
             ops.gemm(dv, in_w[2 * D:], dh2, b_major=1)                 # d src through v
             # d src = dA (residual around attention) + dh + dh2; d pos += dh
@@ -729,8 +723,7 @@ class DetrDecoderEngine(DetrEngine):
             self._wgrad(d_bf, act_out, (li, "lin2_w"))
             ops.gemm(d_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU if self.act == "relu" else ops.EPI_DGELU,
                      aux=buf["a"], **drelu)
-            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
-            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"), bias_key=(li, "lin1_b"))
             ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
             ops.layernorm_bwd(dh, buf["t2"], buf["mean3"], buf["rstd3"], self.f((li, "norm3_w")), dres=d, dx=d, dx_bf16=d_bf if fuse else None,
                               dgamma=self.gview((li, "norm3_w")), dbeta=self.gview((li, "norm3_b")),
@@ -744,12 +737,9 @@ class DetrDecoderEngine(DetrEngine):
                               B=N, H=H, S=Q, S_kv=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm,
                               dropout=(pd, seed, site(li, 4)) if pd > 0 else None)
             cw, gcb = self.w((li, "cin_w")), self.gview((li, "cin_b"))
-            self._wgrad(ws["dcq"], buf["t1q_bf"] if ws["has_qpos"] else buf["t1_bf"], (li, "cin_w"), rows=(0, D))
-            self._wgrad(ws["dck"], ws["mk_bf"], (li, "cin_w"), rows=(D, 2 * D))
-            self._wgrad(ws["dcv"], ws["m_bf"], (li, "cin_w"), rows=(2 * D, 3 * D))
-            ops.colsum_bf16(ws["dcq"], gcb[:D])
-            ops.colsum_bf16(ws["dck"], gcb[D:2 * D])
-            ops.colsum_bf16(ws["dcv"], gcb[2 * D:])
+            self._wgrad(ws["dcq"], buf["t1q_bf"] if ws["has_qpos"] else buf["t1_bf"], (li, "cin_w"), rows=(0, D), bias_grad=gcb[:D])
+            self._wgrad(ws["dck"], ws["mk_bf"], (li, "cin_w"), rows=(D, 2 * D), bias_grad=gcb[D:2 * D])
+            self._wgrad(ws["dcv"], ws["m_bf"], (li, "cin_w"), rows=(2 * D, 3 * D), bias_grad=gcb[2 * D:])
             ops.gemm(ws["dcq"], cw[:D], dh, b_major=1)
             ops.gemm(ws["dck"], cw[D:2 * D], ws["dmk"], b_major=1)
             ops.gemm(ws["dcv"], cw[2 * D:], ws["dmv"], b_major=1)
@@ -767,10 +757,8 @@ class DetrDecoderEngine(DetrEngine):
             ops.attention_bwd(buf["sqk"][:, :D], buf["sqk"][:, D:], buf["sv"], buf["so"], buf["slse"], dh, dsqk[:, :D], dsqk[:, D:], dsv,
                               ws["delta"], B=N, H=H, S=Q, tok_stride=N, batch_stride=1, dropout=(pd, seed, site(li, 3)) if pd > 0 else None)
             in_w, gb = self.w((li, "in_w")), self.gview((li, "in_b"))
-            self._wgrad(dsqk, buf["qk_bf"] if ws["has_qpos"] else buf["x_bf"], (li, "in_w"), rows=(0, 2 * D))
-            self._wgrad(dsv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
-            ops.colsum_bf16(dsqk, gb[:2 * D])
-            ops.colsum_bf16(dsv, gb[2 * D:])
+            self._wgrad(dsqk, buf["qk_bf"] if ws["has_qpos"] else buf["x_bf"], (li, "in_w"), rows=(0, 2 * D), bias_grad=gb[:2 * D])
+            self._wgrad(dsv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D), bias_grad=gb[2 * D:])
             ops.gemm(dsqk, in_w[:2 * D], dh, b_major=1)       # d(norm1(t0) + query_pos)
             ops.gemm(dsv, in_w[2 * D:], dh2, b_major=1)       # d norm1(t0) through the values
             ops.add3(dqpos, dh, None, dqpos, None)
@@ -828,8 +816,7 @@ class DetrDecoderEngine(DetrEngine):
             self._wgrad(dU_bf, act_out, (li, "lin2_w"))
             ops.gemm(dU_bf, self.w((li, "lin2_w")), ws["da"], b_major=1, epilogue=ops.EPI_DRELU if self.act == "relu" else ops.EPI_DGELU,
                      aux=buf["a"], **drelu)
-            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"))
-            ops.colsum_bf16(ws["da"], self.gview((li, "lin1_b")))
+            self._wgrad(ws["da"], buf["x1_bf"], (li, "lin1_w"), bias_key=(li, "lin1_b"))
             ops.gemm(ws["da"], self.w((li, "lin1_w")), dh, b_major=1)
             # ---- cross-attention: t2 = norm2(u2), u2 = t1 + dropout2(out_proj(attn(t1 + qpos, memory + pos, memory))) ----
             ops.layernorm_bwd(dU, buf["u2"], buf["mean2"], buf["rstd2"], self.f((li, "norm2_w")), dx=dU2, dx_bf16=dU_bf if fuse else None,
@@ -843,12 +830,9 @@ class DetrDecoderEngine(DetrEngine):
                               B=N, H=H, S=Q, S_kv=S, tok_stride=N, batch_stride=1, key_padding_mask=kpm,
                               dropout=(pd, seed, site(li, 4)) if pd > 0 else None)
             cw, gcb = self.w((li, "cin_w")), self.gview((li, "cin_b"))
-            self._wgrad(ws["dcq"], buf["t1q_bf"] if ws["has_qpos"] else buf["t1_bf"], (li, "cin_w"), rows=(0, D))
-            self._wgrad(ws["dck"], ws["mk_bf"], (li, "cin_w"), rows=(D, 2 * D))
-            self._wgrad(ws["dcv"], ws["m_bf"], (li, "cin_w"), rows=(2 * D, 3 * D))
-            ops.colsum_bf16(ws["dcq"], gcb[:D])
-            ops.colsum_bf16(ws["dck"], gcb[D:2 * D])
-            ops.colsum_bf16(ws["dcv"], gcb[2 * D:])
+            self._wgrad(ws["dcq"], buf["t1q_bf"] if ws["has_qpos"] else buf["t1_bf"], (li, "cin_w"), rows=(0, D), bias_grad=gcb[:D])
+            self._wgrad(ws["dck"], ws["mk_bf"], (li, "cin_w"), rows=(D, 2 * D), bias_grad=gcb[D:2 * D])
+            self._wgrad(ws["dcv"], ws["m_bf"], (li, "cin_w"), rows=(2 * D, 3 * D), bias_grad=gcb[2 * D:])
             ops.gemm(ws["dcq"], cw[:D], dh, b_major=1)                                               # d(t1 + query_pos)
             ops.gemm(ws["dck"], cw[D:2 * D], ws["dmk"], b_major=1)                                   # d(memory + pos)
             ops.gemm(ws["dcv"], cw[2 * D:], ws["dmv"], b_major=1)                                    # d memory through the values
@@ -866,10 +850,8 @@ class DetrDecoderEngine(DetrEngine):
             ops.attention_bwd(buf["sqk"][:, :D], buf["sqk"][:, D:], buf["sv"], buf["so"], buf["slse"], dh, dsqk[:, :D], dsqk[:, D:], dsv,
                               ws["delta"], B=N, H=H, S=Q, tok_stride=N, batch_stride=1, dropout=(pd, seed, site(li, 3)) if pd > 0 else None)
             in_w, gb = self.w((li, "in_w")), self.gview((li, "in_b"))
-            self._wgrad(dsqk, buf["qk_bf"], (li, "in_w"), rows=(0, 2 * D))
-            self._wgrad(dsv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D))
-            ops.colsum_bf16(dsqk, gb[:2 * D])
-            ops.colsum_bf16(dsv, gb[2 * D:])
+            self._wgrad(dsqk, buf["qk_bf"], (li, "in_w"), rows=(0, 2 * D), bias_grad=gb[:2 * D])
+            self._wgrad(dsv, buf["x_bf"], (li, "in_w"), rows=(2 * D, 3 * D), bias_grad=gb[2 * D:])
             ops.gemm(dsqk, in_w[:2 * D], dh, b_major=1)                                              # d(t0 + query_pos) through q and k
             ops.gemm(dsv, in_w[2 * D:], dh2, b_major=1)                                              # d t0 through v
             ops.add3(dU, dh, dh2, dT, dqpos)                                                         # d t0 = dU + dh + dh2; d qpos += dh

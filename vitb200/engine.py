@@ -360,20 +360,23 @@ class FlatParams:
                 o = self.offsets[key]
                 p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
 
-    def _wgrad(self, dy, x, key, rows=None, bias_key=None):
+    def _wgrad(self, dy, x, key, rows=None, bias_key=None, bias_grad=None):
         """dW[key] (or its first `rows` rows / a row slice) += dy^T x  with dy [M, N_out], x [M, K_in] (token-major bf16);
-        with ``bias_key`` also d bias[bias_key] += column sums of dy (inside the same GEMM when _WGRAD_COLSUM, else one more kernel)."""
+        with ``bias_key`` (or ``bias_grad``, an fp32 [N_out] slice of the flat gradient) also d bias += column sums of dy — inside the
+        same GEMM when _WGRAD_COLSUM, else one more kernel."""
         dW = self.gview(key)
+        if bias_key is not None:
+            bias_grad = self.gview(bias_key)
         if rows is not None:
             dW = dW[rows[0]:rows[1]]
         n_out, k_in = dW.shape
         # work units are 256x256 tiles owned by CTA pairs (cta_group::2): sms // 2 pairs run concurrently
         tiles = (-(-(-(-n_out // 128)) // 2)) * (-(-k_in // 256))
         split = pick_split_k(tiles, -(-dy.shape[0] // 64), max(1, self._sms // 2))
-        fused = bias_key is not None and _WGRAD_COLSUM
-        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split, a_colsum=self.gview(bias_key) if fused else None)
-        if bias_key is not None and not fused:
-            ops.colsum_bf16(dy, self.gview(bias_key))
+        fused = bias_grad is not None and _WGRAD_COLSUM
+        ops.gemm(dy, x, dW, a_major=1, b_major=1, epilogue=ops.EPI_ACCUM, split_k=split, a_colsum=bias_grad if fused else None)
+        if bias_grad is not None and not fused:
+            ops.colsum_bf16(dy, bias_grad)
 
     def _seg_done(self, idx):
         if self.grad_segment_hook is not None:
