@@ -42,6 +42,7 @@ struct GemmArgs {
     int split_k, kb_per_split, num_units;
     int c_row_offset, aux_bcast, b_batched;
     int direct;
+    int tail_cols;        // a last n-block with at most this many valid columns runs as a 256x128 MMA (128; 0 disables)
     float drelu_scale;    // VB_EPI_DRELU: kept elements are multiplied by this (1/(1-p) of the dropout after the activation)
     long long* dbg;       // optional: cycle accounting of cluster 0's MMA issuer (vb_debug_set_gemm_timeline)
     int* sched_counter;   // non-null: dynamic tile scheduling (units beyond the first per cluster are handed out by atomicAdd)
@@ -327,7 +328,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int u = unit0; u >= 0; u = sched_next(rd, u, false)) {
                 const UnitCoord c = decode_unit<CG>(args, u, rank);
                 const int bb = args.b_batched ? c.batch : 0;
-                const int n_row0 = c.n_blk * BN + rank * (BN / CG);   // this CTA's share of the B tile
+                // this CTA's share of the B tile.  A last n-block with at most 128 valid columns (N = 384: DeiT-S) runs as a 256x128
+                // MMA: each CTA of a pair then supplies 64 of them (the box still loads 128 rows; the extra ones are not read)
+                const bool tail128 = args.N - c.n_blk * int(BN) <= args.tail_cols;
+                const int n_row0 = c.n_blk * BN + rank * ((tail128 ? 128 : BN) / CG);
                 int cs_cnt = cs_count0(c);
                 for (int kb = c.kb0; kb < c.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -385,7 +389,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp_idx == 1) {
         // ===================================== MMA issuer =======================================
         if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, AMAJ, BMAJ);
+            constexpr uint32_t idesc_full = umma_idesc_bf16(BM * CG, BN, AMAJ, BMAJ);
+            constexpr uint32_t idesc_tail = umma_idesc_bf16(BM * CG, 128, AMAJ, BMAJ);   // n-block with <= 128 valid columns
             // K-major SW128: 8-row groups 1024 B apart (SBO); MN-major SW128: 64-wide MN atoms BK*128 B apart
             // (LBO) and 8-deep K groups 1024 B apart (SBO).
             constexpr uint64_t a_base = (AMAJ == 0) ? umma_smem_desc_base(0, 1024) : umma_smem_desc_base(BK * 128, 1024);
@@ -407,6 +412,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (dbg_on) w_tmem += clock64() - t0;
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t idesc = (args.N - c.n_blk * int(BN) <= args.tail_cols) ? idesc_tail : idesc_full;
                 int cs_cnt = cs_count0(c);
                 for (int kb = c.kb0; kb < c.kb1; ++kb) {
                     if (dbg_on) t0 = clock64();
@@ -935,6 +941,8 @@ extern "C" int vb_gemm_bf16(const VbGemmDesc* d, void* stream_) {
     a.aux_bcast = d->aux_batch_broadcast;
     a.b_batched = d->batch_stride_b != 0;
     a.direct = d->debug_direct_store;
+    static const int tail_on = [] { const char* e = getenv("VITB200_GEMM_TAIL128"); return e ? atoi(e) : 1; }();
+    a.tail_cols = tail_on ? 128 : 0;
     a.drelu_scale = d->drelu_scale > 0.f ? d->drelu_scale : 1.0f;
     a.sched_counter = nullptr;
     a.dbg = g_gemm_dbg;
