@@ -599,7 +599,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 // 10.4 k vs 7.5 k cycles per tile (round 1); 256-bit STG.256 / LDG.256 for the aux operand (round 2): fc1 + GELU
                 // 235 -> 265 us, fc2 dgrad x gelu' 205 -> 250 us, out-proj + residual 82 -> 103 us.  Also rejected in round 2: a
                 // MUFU-free-reciprocal erf (degree-8 polynomial for erfcx, one MUFU per element instead of two): 235 us unchanged —
-                // the two-output epilogue is bound by shared-memory staging traffic next to the operand reads, not by the math.)
+                // the two-output epilogue is bound by shared-memory staging traffic next to the operand reads, not by the math.
+                // Late round 2, the fp32-residual epilogue at K = 768 (12.4-12.6 k cycles per tile, MMA floor 6.2 k): (a) in-place
+                // double buffering of the aux tile — the TMA load of the next chunk's aux in flight during the whole chunk — 12.4 k;
+                // (b) no staging at all: tcgen05.ld.16x256b fragments (four lanes own 32 contiguous bytes of a row), 8-byte LDG / STG
+                // on whole sectors, L2 prefetch two chunks ahead — 14.3 k.  Same bytes, same time: that GEMM is bound by the L2->SM
+                // throughput share of an SM (384 KB operands + 256 KB fp32 aux / out per CTA and tile))
                 uint8_t* obuf = buf_o0;
 #pragma unroll
                 for (int g = 0; g < int(CPC / 32); ++g) {
