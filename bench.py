@@ -257,11 +257,14 @@ def main():
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+        e2e_dbg = os.environ.get("VITB200_BENCH_E2E_DEBUG", "")   # diagnostics only: "noh2d" / "nod2h" drop one leg (the line is then not an e2e number)
+
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[i & 1])
-                bufs[i & 1][0].copy_(host_images, non_blocking=True)
-                bufs[i & 1][1].copy_(host_labels, non_blocking=True)
+                if e2e_dbg != "noh2d":
+                    bufs[i & 1][0].copy_(host_images, non_blocking=True)
+                    bufs[i & 1][1].copy_(host_labels, non_blocking=True)
                 ready[i & 1].record(copy_stream)
 
         def e2e_loop(n):
@@ -274,7 +277,8 @@ def main():
                 torch.cuda.current_stream().wait_event(ready[i & 1])
                 l = trainer.step(bufs[i & 1][0], bufs[i & 1][1])
                 consumed[i & 1].record(torch.cuda.current_stream())
-                loss_host.copy_(l, non_blocking=True)
+                if e2e_dbg != "nod2h":
+                    loss_host.copy_(l, non_blocking=True)
 
         e2e_loop(3)
         barrier()
