@@ -172,6 +172,48 @@ def test_standalone_encoder_matches_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("S,D,H,Fd", [(65, 256, 4, 512), (197, 768, 12, 3072)])
+def test_standalone_encoder_block_matches_oracle(S, D, H, Fd):
+    """vitb200.vit.EncoderBlock called on its own (vanilla_vit.py:73-83 — what nn.Sequential does inside the reference's Encoder): tokens
+    in, tokens out (no position embedding, no final norm), gradients for the tokens and every parameter; a second sequence length
+    through the same module; then the same block inside an Encoder still works (its engine re-binds the parameters)."""
+    import torch
+    from oracle import vit_oracle as O
+    from vitb200.vit import EncoderBlock
+    B = 3
+    blk = EncoderBlock(H, D, Fd, 0.0, 0.0)
+    g = torch.Generator().manual_seed(43)
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            if n in ("ln_1.weight", "ln_2.weight"):
+                p.add_(1.0)
+    sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    blk = blk.cuda().train()
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    for s_len in (S, S - 7):
+        x = torch.randn(B, s_len, D, generator=g)
+        gout = torch.randn(B, s_len, D, generator=g)
+        blk.zero_grad()
+        xc = x.cuda().requires_grad_(True)
+        out = blk(xc)
+        out.backward(gout.cuda())
+        ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        xr = x.clone().requires_grad_(True)
+        ref = O.encoder_block(xr, ref_sd, "", H, 1e-6)
+        ref.backward(gout)
+        assert rel(out, ref) < 1.5e-2                       # one block of bf16 GEMMs against fp32: same flat bounds as the small-shape tests
+        assert rel(xc.grad, xr.grad) < 3e-2
+        worst = max((rel(p.grad, ref_sd[n].grad), n) for n, p in blk.named_parameters())
+        assert worst[0] < 3e-2, worst
+    blk.eval()
+    with torch.no_grad():
+        assert rel(blk(x.cuda()), ref) < 1.5e-2
+    with pytest.raises(RuntimeError):
+        blk(x)                                              # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
 def test_small_batch_inference_graph_replay_matches_eager(monkeypatch):
     """Eval forwards at small batch are replayed from a CUDA graph (engine.forward_inference): bit-identical to the eager kernel
     sequence for fresh inputs, and parameter edits between calls are seen (the bf16 cast is part of the graph)."""

@@ -387,9 +387,11 @@ class VitEngine(FlatParams):
     """Sequences the kernels for `n_prefix` token rows (1 = cls, 2 = cls + dist) + patches through L pre-norm blocks."""
 
     def __init__(self, *, image_size, patch_size, hidden_dim, num_heads, mlp_dim, num_layers, num_classes, n_prefix, eps,
-                 globals_, layers, seq_length=None):
+                 globals_, layers, seq_length=None, block_mode=False):
         """globals_: role -> Parameter for cls, [dist], pos, conv_w, conv_b, lnf_w, lnf_b, head_w, head_b, [headd_w, headd_b];
-        layers: list of dicts role -> Parameter (LAYER_ROLES)."""
+        layers: list of dicts role -> Parameter (LAYER_ROLES).
+        block_mode (with seq_length): the bare block stack, tokens in -> tokens out, no position embedding and no final norm — a
+        stand-alone EncoderBlock (vanilla_vit.py:73-83); outputs / gradients are requested with want="block"."""
         if hidden_dim % 64 != 0 or hidden_dim // num_heads != 64 or hidden_dim > 1024:
             # every config of the reference has head_dim 64: ViT 256/4, DeiT 192/3, 384/6, 768/12 (utils/args.py:6-15,43-61)
             raise NotImplementedError(f"vitb200 kernels need head_dim == 64 and hidden_dim <= 1024 (got hidden_dim {hidden_dim}, "
@@ -397,6 +399,8 @@ class VitEngine(FlatParams):
         # tokens mode (seq_length given): the stack is fed [B, S, D] tokens instead of images — a stand-alone Encoder
         # (vanilla_vit.py:88-106): input + pos_embedding, dropout, L blocks, final LayerNorm; no patch embedding, no heads.
         self.tokens_mode = seq_length is not None
+        self.block_mode = bool(block_mode)
+        assert self.tokens_mode or not self.block_mode
         if self.tokens_mode:
             image_size, patch_size = 4, 4
         assert patch_size % 4 == 0 and image_size % patch_size == 0
@@ -425,17 +429,19 @@ class VitEngine(FlatParams):
         self.has_peg = bool(layers) and "peg_w" in layers[0]
         self.has_pos = "pos" in globals_
         assert not (self.has_cpe or self.has_peg) or (n_prefix == 1 and not self.tokens_mode), "CPE / PEG: class-token ViT only"
-        assert self.has_pos or self.has_cpe, "a model without a position embedding needs a CPE"
+        assert self.has_pos or self.has_cpe or self.block_mode, "a model without a position embedding needs a CPE"
         emb = (["pos"] if self.has_pos else []) + (["cpe_w", "cpe_b"] if self.has_cpe else []) + ["cls"] \
             + (["dist"] if n_prefix == 2 else []) + ["conv_w", "conv_b"]
         if self.tokens_mode:
             seg0, emb = ["lnf_w", "lnf_b"], ["pos"]
+        if self.block_mode:
+            seg0, emb = [], []
         roles = (("peg_w", "peg_b") if self.has_peg else ()) + LAYER_ROLES
         self._order = [(("g", r), globals_[r]) for r in seg0]
         for li in range(num_layers - 1, -1, -1):
             self._order += [((li, r), layers[li][r]) for r in roles]
         self._order += [(("g", r), globals_[r]) for r in emb]
-        self._layout([len(seg0)] + [len(roles)] * num_layers + [len(emb)])
+        self._layout(([len(seg0)] if seg0 else []) + [len(roles)] * num_layers + ([len(emb)] if emb else []))
 
     # ------------------------------------------------------------------ dropout -----------------------------------
     EMBED_SITE = 4000
@@ -510,6 +516,9 @@ class VitEngine(FlatParams):
     # ------------------------------------------------------------------ forward -----------------------------------
     def _embed(self, ws, images):
         B = ws["B"]
+        if self.block_mode:    # a bare block: the caller's tokens are the block input
+            ws["x"][0].view(ws["M"], self.D).copy_(images.view(ws["M"], self.D))
+            return
         if self.tokens_mode:   # images = caller-supplied tokens [B, S, D]
             x02 = ws["x"][0].view(ws["M"], self.D)
             ops.add_rows_bcast(images.view(ws["M"], self.D), self.f(("g", "pos")).view(self.S, self.D), x02)
@@ -616,6 +625,8 @@ class VitEngine(FlatParams):
         x_last = xs[self.L] if training else xs[self.L & 1]
         ws["x_last"] = x_last
         S, D, M = self.S, self.D, ws["M"]
+        if want == "block":
+            return [x_last], ws
         if want == "features":
             if ws["y_all"] is None:
                 ws["y_all"] = torch.empty(B, S, D, device=x_last.device, dtype=torch.float32)
@@ -656,7 +667,17 @@ class VitEngine(FlatParams):
             ops.colsum_bf16(d_bf, self.gview(bias_key))
         peg = self.has_peg
         fuse_tail = pd == 0 and not peg   # the LayerNorm backward also emits the bf16 operand + fc2 bias gradient of the block behind it
-        if want == "features":
+        if want == "block":
+            # no final norm behind the last block: its output gradient is the stream gradient; the bf16 operand and the fc2 bias
+            # gradient the final LayerNorm backward would have emitted are made here
+            gy = grads[0]
+            if gy.dtype != torch.float32 or not gy.is_contiguous():
+                gy = gy.contiguous().float()
+            d2.copy_(gy.view(M, D))
+            if fuse_tail:
+                ops.cast_bf16(d2.view(-1), d_bf.view(-1))
+                ops.colsum_bf16(d_bf, self.gview(last_b2))
+        elif want == "features":
             gy = grads[0]
             if gy.dtype != torch.float32 or not gy.is_contiguous():
                 gy = gy.contiguous().float()
@@ -768,6 +789,8 @@ class VitEngine(FlatParams):
             if pd > 0 and li > 0 and not peg:
                 masked_operand(li - 1, 2, (li - 1, "fc2_b"))
             self._seg_done(L - li)
+        if self.block_mode:    # d is the gradient w.r.t. the caller's tokens
+            return d
         # ---- embedding ----
         if pd > 0:   # Encoder.dropout (vanilla_vit.py:104): gradient of x + pos is keep * d / (1 - p)
             ops.dropout_f32(d2, pd, seed, self.EMBED_SITE, dst=d2)

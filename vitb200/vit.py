@@ -53,6 +53,21 @@ def _norm_eps(norm_module):
     return float(getattr(norm_module, "eps", 1e-6))
 
 
+def _deepcopy_without_engine(module, memo):
+    """copy.deepcopy of a module that caches an engine (flat buffers, workspaces, CUDA graphs): the copy starts without one."""
+    import copy
+    eng = module.__dict__.pop("_engine", None)
+    try:
+        new = module.__class__.__new__(module.__class__)
+        memo[id(module)] = new
+        for k, v in module.__dict__.items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__["_engine"] = None
+    finally:
+        module.__dict__["_engine"] = eng
+    return new
+
+
 class EncoderBlock(nn.Module):
     """Parameter container for one pre-norm block (vanilla_vit.py:59-71); executed by the enclosing Encoder/ViT."""
 
@@ -73,8 +88,40 @@ class EncoderBlock(nn.Module):
                 "ln2_w": self.ln_2.weight, "ln2_b": self.ln_2.bias,
                 "fc1_w": self.mlp[0].weight, "fc1_b": self.mlp[0].bias, "fc2_w": self.mlp[3].weight, "fc2_b": self.mlp[3].bias}
 
+    # Stand-alone use (vanilla_vit.py:73-83: x = dropout(MHA(ln_1(input))) + input; return x + mlp(ln_2(x))): a one-layer block-mode
+    # engine over this module's own parameters, one per sequence length.  Inside an Encoder / ViT the parent's engine runs the block
+    # (this forward is then never called); using both alternately works — each engine re-binds the parameters when it finds them moved.
+    def _get_engine(self, seq_length):
+        engines = self.__dict__.get("_engine")
+        if engines is None:
+            engines = self.__dict__["_engine"] = {}
+        eng = engines.get(seq_length)
+        if eng is None:
+            eng = VitEngine(image_size=4, patch_size=4, hidden_dim=self.ln_1.weight.shape[0], num_heads=self.num_heads,
+                            mlp_dim=self.mlp[0].out_features, num_layers=1, num_classes=1, n_prefix=0, eps=_norm_eps(self.ln_1),
+                            globals_={}, layers=[self.roles()], seq_length=seq_length, block_mode=True)
+            eng.tokens_want = "block"
+            engines[seq_length] = eng
+        return eng
+
     def forward(self, input: torch.Tensor):
-        raise RuntimeError("vitb200.EncoderBlock is executed by its parent ViT (fused path); it has no standalone forward")
+        torch._assert(input.dim() == 3, f"Expected (batch_size, seq_length, hidden_dim) got {input.shape}")
+        torch._assert(input.shape[2] == self.ln_1.weight.shape[0], f"Expected hidden_dim {self.ln_1.weight.shape[0]} got {input.shape}")
+        if not input.is_cuda:
+            raise RuntimeError("vitb200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        eng = self._get_engine(int(input.shape[1]))
+        eng.p_drop, eng.p_attn = (float(self.dropout.p), float(self.self_attention.dropout)) if self.training else (0.0, 0.0)
+        params = [p for _, p in eng._order]
+        x = input.contiguous().float()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+            return _TokensFn.apply(eng, x, *params)
+        outs, _ = eng.forward(x, training=(eng.p_drop > 0 or eng.p_attn > 0), want="block")
+        return outs[0].clone()
+
+    __getstate__ = getstate_without_engine
+
+    def __deepcopy__(self, memo):
+        return _deepcopy_without_engine(self, memo)
 
 
 class Encoder(nn.Module):
@@ -122,17 +169,7 @@ class Encoder(nn.Module):
     __getstate__ = getstate_without_engine
 
     def __deepcopy__(self, memo):
-        import copy
-        eng = self.__dict__.pop("_engine", None)
-        try:
-            new = self.__class__.__new__(self.__class__)
-            memo[id(self)] = new
-            for k, v in self.__dict__.items():
-                new.__dict__[k] = copy.deepcopy(v, memo)
-            new.__dict__["_engine"] = None
-        finally:
-            self.__dict__["_engine"] = eng
-        return new
+        return _deepcopy_without_engine(self, memo)
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -163,14 +200,15 @@ class _TokensFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine, tokens, *params):
-        outs, ws = engine.forward(tokens, training=True, want="features")
-        ctx.engine, ctx.ws, ctx.n_params = engine, ws, len(params)
+        want = getattr(engine, "tokens_want", "features")   # "block": a bare EncoderBlock (no position embedding, no final norm)
+        outs, ws = engine.forward(tokens, training=True, want=want)
+        ctx.engine, ctx.ws, ctx.n_params, ctx.want = engine, ws, len(params), want
         ctx.lease = WorkspaceLease(ws)
         return outs[0].clone()
 
     @staticmethod
     def backward(ctx, grad):
-        d = ctx.engine.backward(ctx.ws, [grad], want="features").clone()
+        d = ctx.engine.backward(ctx.ws, [grad], want=ctx.want).clone()
         ctx.lease.release()
         return (None, d) + (None,) * ctx.n_params
 
